@@ -1,0 +1,111 @@
+// Shared helpers for libtsw_sm100.so kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tsw.h"
+
+namespace tsw {
+
+void set_error(const char* fmt, ...);
+
+#define TSW_CHECK_ARG(cond, ...)              \
+  do {                                        \
+    if (!(cond)) {                            \
+      ::tsw::set_error(__VA_ARGS__);          \
+      return TSW_E_INVALID;                   \
+    }                                         \
+  } while (0)
+
+#define TSW_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) {                                                                        \
+      ::tsw::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return TSW_E_CUDA;                                                                            \
+    }                                                                                               \
+  } while (0)
+
+#define TSW_LAUNCH_CHECK() TSW_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(tsw_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int sm_count();  // cached per device
+
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int code = TSW_F32; };
+template <> struct DT<__nv_bfloat16> { static constexpr int code = TSW_BF16; };
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum/max through one smem round; `red` needs >= 33 floats. All threads get the result.
+template <bool IS_MAX>
+__device__ __forceinline__ float block_reduce(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  v = IS_MAX ? warp_max(v) : warp_sum(v);
+  __syncthreads();  // protect `red` from a previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = (lane < nwarp) ? red[lane] : (IS_MAX ? -INFINITY : 0.f);
+  r = IS_MAX ? warp_max(r) : warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* red) { return block_reduce<false>(v, red); }
+__device__ __forceinline__ float block_max(float v, float* red) { return block_reduce<true>(v, red); }
+
+// exact GELU (erf), as F.gelu / nn.GELU() default and HF ACT2FN["gelu"]
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// 8 x bf16 <-> 8 x f32 through one 16-byte access
+struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+
+template <typename T> struct Vec;  // 16-byte vector access: N elements of T
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* out) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  }
+  __device__ static void store(float* p, const float* in) { *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]); }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* out) {
+    bf16x8 t = *reinterpret_cast<const bf16x8*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(t.v[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* in) {
+    bf16x8 t;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t.v[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+    *reinterpret_cast<bf16x8*>(p) = t;
+  }
+};
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace tsw

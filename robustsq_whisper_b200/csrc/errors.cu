@@ -1,0 +1,39 @@
+// Error reporting + device queries for libtsw_sm100.so
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace tsw {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+}  // namespace tsw
+
+extern "C" int tsw_abi_version(void) { return TSW_ABI_VERSION; }
+extern "C" const char* tsw_last_error(void) { return tsw::g_err; }
+extern "C" int tsw_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0, maj = 0, min = 0;
+  TSW_CUDA(cudaGetDevice(&dev));
+  TSW_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  TSW_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = tsw::sm_count();
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  if (maj != 10) { tsw::set_error("device cc %d.%d is not sm_100 (B200)", maj, min); return TSW_E_UNSUPPORTED; }
+  return TSW_OK;
+}

@@ -1,0 +1,43 @@
+// tsw_gemm: argument validation + dispatch between the tcgen05 kernel (gemm_tc.cu) and the fp32-accumulate SIMT
+// kernel (gemm_simt.cu).  See include/tsw.h for the contract.
+#include "gemm_common.cuh"
+
+using namespace tsw;
+
+extern "C" size_t tsw_gemm_workspace_bytes(const tsw_gemm_desc* d) { (void)d; return 0; }
+
+extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspace_bytes, tsw_stream_t stream) {
+  (void)workspace; (void)workspace_bytes;
+  TSW_CHECK_ARG(d != nullptr, "gemm: null descriptor");
+  const tsw_gemm_desc& g = *d;
+  TSW_CHECK_ARG(g.A && g.B && g.D, "gemm: null operand");
+  TSW_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0 && g.batch_outer >= 1 && g.batch_inner >= 1, "gemm: bad sizes M=%lld N=%lld K=%lld", (long long)g.M, (long long)g.N, (long long)g.K);
+  TSW_CHECK_ARG((g.a_dtype | 1) == 1 && (g.b_dtype | 1) == 1 && (g.d_dtype | 1) == 1, "gemm: bad dtype");
+  TSW_CHECK_ARG(g.lda >= (g.a_mn_major ? g.M : g.K) && g.ldb >= (g.b_mn_major ? g.N : g.K) && g.ldd >= g.N, "gemm: leading dimension too small");
+  TSW_CHECK_ARG(g.epilogue >= TSW_EPI_NONE && g.epilogue <= TSW_EPI_MUL_DGELU, "gemm: bad epilogue");
+  TSW_CHECK_ARG(g.epilogue != TSW_EPI_MUL_DGELU || g.aux_in, "gemm: MUL_DGELU needs aux_in");
+  TSW_CHECK_ARG(!g.residual || (g.res_dtype == g.d_dtype && g.ldres >= g.N), "gemm: residual must have the output dtype");
+  TSW_CHECK_ARG(g.beta == 0.f || g.beta == 1.f, "gemm: beta must be 0 or 1");
+
+  EpiParams ep;
+  ep.D = g.D; ep.ldd = g.ldd;
+  ep.bias = g.bias;
+  ep.residual = g.residual; ep.ldres = g.ldres; ep.res_row_mod = g.res_row_mod;
+  ep.aux_in = g.aux_in; ep.aux_out = g.aux_out;
+  ep.epilogue = g.epilogue;
+  ep.alpha = g.alpha; ep.beta = g.beta;
+  ep.M = g.M; ep.N = g.N;
+  const int vn = g.d_dtype == TSW_F32 ? 4 : 8;
+  auto ok = [&](const void* p, int64_t ld, int64_t so, int64_t si) {
+    return !p || (aligned16(p) && ld % vn == 0 && so % vn == 0 && si % vn == 0);
+  };
+  ep.vec_ok = ok(g.D, g.ldd, g.d_stride_outer, g.d_stride_inner) && ok(g.aux_in, g.ldd, 0, 0) && ok(g.aux_out, g.ldd, 0, 0) &&
+              ok(g.residual, g.ldres, g.res_stride_outer, g.res_stride_inner) && (!g.bias || aligned16(g.bias));
+
+  cudaStream_t st = as_stream(stream);
+  if (g.impl == TSW_GEMM_SIMT) return gemm_simt_launch(g, ep, st);
+  if (g.impl == TSW_GEMM_TCGEN05) return gemm_tc_launch(g, ep, st);
+  TSW_CHECK_ARG(g.impl == TSW_GEMM_AUTO, "gemm: bad impl %d", g.impl);
+  if (gemm_tc_supported(g, nullptr)) return gemm_tc_launch(g, ep, st);
+  return gemm_simt_launch(g, ep, st);
+}

@@ -1,0 +1,88 @@
+// Epilogue shared by the SIMT and the tcgen05 GEMM kernels (see tsw.h for the contract).
+#pragma once
+#include "common.cuh"
+
+namespace tsw {
+
+struct EpiParams {
+  void* D; int64_t ldd;
+  const float* bias;
+  const void* residual; int64_t ldres; int64_t res_row_mod;
+  const void* aux_in; void* aux_out;
+  int epilogue;
+  float alpha, beta;
+  int64_t M, N;
+  int vec_ok;  // D/residual/aux rows are 16-byte aligned at 8-element (bf16) / 4-element (fp32) column granularity
+};
+
+// One output row segment of NV consecutive columns starting at n0 (n0 % NV == 0 when vec_ok).
+template <typename DT, int NV>
+__device__ __forceinline__ void epi_store(const EpiParams& p, const float* acc, int64_t m, int64_t n0,
+                                          int64_t d_off, int64_t res_off) {
+  constexpr int VN = Vec<DT>::N;
+  static_assert(NV % VN == 0, "segment must be a whole number of 16-byte vectors");
+  if (m >= p.M || n0 >= p.N) return;
+  const int64_t rrow = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
+  DT* drow = reinterpret_cast<DT*>(p.D) + d_off + m * p.ldd;
+  const DT* rrowp = p.residual ? reinterpret_cast<const DT*>(p.residual) + res_off + rrow * p.ldres : nullptr;
+  const DT* ain = p.aux_in ? reinterpret_cast<const DT*>(p.aux_in) + d_off + m * p.ldd : nullptr;
+  DT* aout = p.aux_out ? reinterpret_cast<DT*>(p.aux_out) + d_off + m * p.ldd : nullptr;
+  const bool full = p.vec_ok && (n0 + NV <= p.N);
+#pragma unroll
+  for (int v0 = 0; v0 < NV; v0 += VN) {
+    float v[VN];
+#pragma unroll
+    for (int j = 0; j < VN; ++j) v[j] = p.alpha * acc[v0 + j];
+    const int64_t n = n0 + v0;
+    if (full) {
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[j] += __ldg(p.bias + n + j);
+      }
+      if (aout) Vec<DT>::store(aout + n, v);
+      if (p.epilogue == TSW_EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[j] = gelu_f(v[j]);
+      } else if (p.epilogue == TSW_EPI_MUL_DGELU) {
+        float a[VN];
+        Vec<DT>::load(ain + n, a);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[j] *= dgelu_f(a[j]);
+      }
+      if (rrowp) {
+        float r[VN];
+        Vec<DT>::load(rrowp + n, r);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[j] += r[j];
+      }
+      if (p.beta != 0.f) {
+        float o[VN];
+        Vec<DT>::load(drow + n, o);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[j] += p.beta * o[j];
+      }
+      Vec<DT>::store(drow + n, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        if (n + j < p.N) {
+          float x = v[j];
+          if (p.bias) x += p.bias[n + j];
+          if (aout) aout[n + j] = from_f32<DT>(x);
+          if (p.epilogue == TSW_EPI_GELU) x = gelu_f(x);
+          else if (p.epilogue == TSW_EPI_MUL_DGELU) x *= dgelu_f(to_f32(ain[n + j]));
+          if (rrowp) x += to_f32(rrowp[n + j]);
+          if (p.beta != 0.f) x += p.beta * to_f32(drow[n + j]);
+          drow[n + j] = from_f32<DT>(x);
+        }
+      }
+    }
+  }
+}
+
+int gemm_simt_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st);
+// returns TSW_E_UNSUPPORTED (with the reason in tsw_last_error) when the operands do not meet the TMA constraints
+int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st);
+bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why);
+
+}  // namespace tsw

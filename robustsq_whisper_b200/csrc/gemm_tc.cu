@@ -1,0 +1,364 @@
+// K5 — bf16 GEMM on the 5th-generation tensor cores of sm_100a: TMA -> 128B-swizzled shared memory -> tcgen05.mma with
+// the accumulator in TMEM -> tcgen05.ld epilogue (bias / GELU / GELU' / residual / positional table / accumulate).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0      TMA producer   (cp.async.bulk.tensor into a kStages-deep ring, mbarrier complete_tx)
+//   warp 1      MMA issuer     (one elected lane; tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 per instruction;
+//                               tcgen05.commit releases ring slots and publishes the accumulator)
+//   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns, so the epilogue of tile i overlaps the
+//                               main loop of tile i+1)
+//   warps 4-7   epilogue       (each warp owns the 32 TMEM lanes = tile rows its index allows; 32 columns per tcgen05.ld)
+// Operands may be K-major ([rows][K]) or MN-major ([K][rows]) in global memory — the layouts forward, dgrad and wgrad
+// GEMMs need — without any transposition pass: MN-major tiles are fetched as 64-wide column panels and described to
+// the tensor core with the MN-major canonical layout (LBO = panel stride, SBO = 8-row group stride).
+// Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "gemm_common.cuh"
+
+namespace tsw {
+
+constexpr int TBM = 128;       // tile rows  (UMMA M, cta_group::1)
+constexpr int TBK = 64;        // K per stage = one 128-byte swizzle row of bf16
+constexpr int TC_THREADS = 256;
+constexpr uint32_t kPanelBytes = 64 * 128;  // one MN-major panel: 64 K-rows x 128 B
+
+struct TcParams {
+  int64_t M, N, K;
+  int batch_inner, batches;
+  int a_mn, b_mn;
+  int64_t d_so, d_si, r_so, r_si;
+  int tiles_m, tiles_n;
+  int64_t total_tiles;
+};
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: ~2 s of SM clocks, then trap (surfaces as a CUDA error instead of a hung GPU).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 4000000000ll) {
+      printf("tsw gemm_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version 1); offsets in bytes
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format = F32
+  d |= 1u << 7;                      // a_format = BF16
+  d |= 1u << 10;                     // b_format = BF16
+  d |= (uint32_t)(a_mn & 1) << 15;   // a_major (0 = K, 1 = MN)
+  d |= (uint32_t)(b_mn & 1) << 16;   // b_major
+  d |= (uint32_t)(n >> 3) << 17;     // n_dim
+  d |= (uint32_t)(TBM >> 4) << 24;   // m_dim
+  return d;
+}
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr uint32_t kABytes = TBM * TBK * 2;
+  static constexpr uint32_t kBBytes = BN * TBK * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256;
+};
+
+template <int BN, int STAGES, typename DT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p, const EpiParams ep) {
+  using S = TcSmem<BN, STAGES>;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * S::kStageBytes);
+  uint64_t* full = bars;                 // [STAGES]
+  uint64_t* empty = bars + STAGES;       // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = (int)((p.K + TBK - 1) / TBK);
+  const int64_t tiles_per_batch = (int64_t)p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const int bt = (int)(t / tiles_per_batch);
+        const int64_t r = t - (int64_t)bt * tiles_per_batch;
+        const int mt = (int)(r / p.tiles_n), nt = (int)(r - (int64_t)mt * p.tiles_n);
+        const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
+        const int m0 = mt * TBM, n0 = nt * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = tiles + (size_t)stage * S::kStageBytes;
+          unsigned char* sb = sa + S::kABytes;
+          mbar_expect_tx(&full[stage], S::kStageBytes);
+          const int k0 = kb * TBK;
+          if (!p.a_mn) {
+            tma_load_4d(&tmA, &full[stage], sa, k0, m0, bi, bo);                       // box {64 k, 128 m}
+          } else {
+#pragma unroll
+            for (int j = 0; j < TBM / 64; ++j) tma_load_4d(&tmA, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);  // box {64 m, 64 k}
+          }
+          if (!p.b_mn) {
+            tma_load_4d(&tmB, &full[stage], sb, k0, n0, bi, bo);                       // box {64 k, BN n}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_4d(&tmB, &full[stage], sb + j * kPanelBytes, n0 + 64 * j, k0, bi, bo);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.a_mn, p.b_mn, BN);
+      const uint32_t a_lbo = p.a_mn ? kPanelBytes : 16, b_lbo = p.b_mn ? kPanelBytes : 16;
+      const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;  // bytes per UMMA_K = 16
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * S::kStageBytes);
+          const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+          for (int k = 0; k < TBK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);       // accumulator complete
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (TMEM -> registers -> global)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int as = 0; uint32_t aphase = 0;
+    for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const int bt = (int)(t / tiles_per_batch);
+      const int64_t r = t - (int64_t)bt * tiles_per_batch;
+      const int mt = (int)(r / p.tiles_n), nt = (int)(r - (int64_t)mt * p.tiles_n);
+      const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
+      const int64_t d_off = bo * p.d_so + bi * p.d_si, r_off = bo * p.r_so + bi * p.r_si;
+      const int64_t m = (int64_t)mt * TBM + q * 32 + lane;
+      const int64_t n0 = (int64_t)nt * BN;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(taddr + c, v);  // warp-collective: executed by all lanes even for rows/columns out of range
+        if (n0 + c < p.N) epi_store<DT, 32>(ep, v, m, n0 + c, d_off, r_off);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
+}
+
+// ----------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// operand stored [rows][K] (mn_major = 0) or [K][rows] (mn_major = 1); 4-D map {inner, outer, batch_inner, batch_outer}
+static int make_operand_map(CUtensorMap* tm, const void* base, int mn_major, int64_t rows, int64_t K, int64_t ld, int bi_count,
+                            int64_t s_inner, int bo_count, int64_t s_outer, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("gemm(tcgen05): cuTensorMapEncodeTiled entry point unavailable"); return TSW_E_CUDA; }
+  const cuuint64_t inner = mn_major ? (cuuint64_t)rows : (cuuint64_t)K;
+  const cuuint64_t outer = mn_major ? (cuuint64_t)K : (cuuint64_t)rows;
+  cuuint64_t dims[4] = {inner, outer, (cuuint64_t)bi_count, (cuuint64_t)bo_count};
+  const cuuint64_t fallback = (cuuint64_t)ld * 2 * outer;
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, bi_count > 1 ? (cuuint64_t)s_inner * 2 : fallback,
+                           bo_count > 1 ? (cuuint64_t)s_outer * 2 : fallback};
+  for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
+  cuuint32_t box[4] = {64u, mn_major ? 64u : (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%lld ld=%lld mn=%d)", (int)r, (long long)rows, (long long)K, (long long)ld, mn_major); return TSW_E_CUDA; }
+  return TSW_OK;
+}
+
+bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
+  auto bad = [&](const char* w) { if (why) *why = w; return false; };
+  if (g.a_dtype != TSW_BF16 || g.b_dtype != TSW_BF16) return bad("operands must be bf16");
+  if (!aligned16(g.A) || !aligned16(g.B)) return bad("operand base pointers must be 16-byte aligned");
+  if (g.lda % 8 || g.ldb % 8) return bad("leading dimensions must be multiples of 8 elements");
+  if ((g.batch_inner > 1 && (g.a_stride_inner % 8 || g.b_stride_inner % 8)) || (g.batch_outer > 1 && (g.a_stride_outer % 8 || g.b_stride_outer % 8)))
+    return bad("batch strides must be multiples of 8 elements");
+  if (g.M < 1 || g.N < 1 || g.K < 1) return bad("empty problem");
+  if (g.M >= (1ll << 31) || g.N >= (1ll << 31) || g.K >= (1ll << 31)) return bad("dimension exceeds 2^31");
+  return true;
+}
+
+template <int BN, int STAGES, typename DT>
+static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
+  using S = TcSmem<BN, STAGES>;
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, g.A, g.a_mn_major, g.M, g.K, g.lda, g.batch_inner, g.a_stride_inner, g.batch_outer, g.a_stride_outer, TBM);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, g.B, g.b_mn_major, g.N, g.K, g.ldb, g.batch_inner, g.b_stride_inner, g.batch_outer, g.b_stride_outer, BN);
+  if (rc) return rc;
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.batch_inner = g.batch_inner; p.batches = g.batch_inner * g.batch_outer;
+  p.a_mn = g.a_mn_major; p.b_mn = g.b_mn_major;
+  p.d_so = g.d_stride_outer; p.d_si = g.d_stride_inner; p.r_so = g.res_stride_outer; p.r_si = g.res_stride_inner;
+  p.tiles_m = (int)((g.M + TBM - 1) / TBM); p.tiles_n = (int)((g.N + BN - 1) / BN);
+  p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * p.batches;
+  auto kern = gemm_tc_kernel<BN, STAGES, DT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
+    attr_done = true;
+  }
+  const int grid = (int)std::min<int64_t>(p.total_tiles, sm_count());
+  kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, p, ep);
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
+  const char* why = nullptr;
+  if (!gemm_tc_supported(g, &why)) { set_error("gemm(tcgen05): %s", why); return TSW_E_UNSUPPORTED; }
+  // wide tiles when N is large enough to fill them; narrow tiles keep more CTAs busy on small N
+  const bool wide = g.N > 128;
+  if (g.d_dtype == TSW_BF16) return wide ? tc_go<256, 4, __nv_bfloat16>(g, ep, st) : tc_go<128, 6, __nv_bfloat16>(g, ep, st);
+  if (g.d_dtype == TSW_F32) return wide ? tc_go<256, 4, float>(g, ep, st) : tc_go<128, 6, float>(g, ep, st);
+  set_error("gemm(tcgen05): bad output dtype");
+  return TSW_E_INVALID;
+}
+
+}  // namespace tsw

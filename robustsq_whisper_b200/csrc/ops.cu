@@ -1,0 +1,509 @@
+// K6 LayerNorm + the HBM-bound glue kernels of the TS-ASR step (casts, bias-gradient column sums, GELU, conv-stem
+// staging, attention softmax, decoder token embedding).  All are coalesced, 16-byte-vectorised, fp32-statistics
+// kernels with warp-shuffle reductions; grids are sized in multiples of the SM count where the work allows.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace tsw {
+
+// ============================================================================================ LayerNorm
+// One warp per row, the row kept in registers (d <= 32 lanes * kLnChunks vectors).
+constexpr int kLnChunks = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ sum_out, float* __restrict__ mean,
+                     float* __restrict__ rstd, int64_t rows, int d, float eps) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = d / VN;
+  float v[kLnChunks][VN];
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    const int i = lane + 32 * c;
+    if (i < nvec) {
+      Vec<T>::load(x + row * d + (int64_t)i * VN, v[c]);
+      if (res != nullptr) {
+        float r[VN];
+        Vec<T>::load(res + row * d + (int64_t)i * VN, r);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[c][j] = to_f32(from_f32<T>(v[c][j] + r[j]));  // round like the unfused sum
+        if (sum_out != nullptr) Vec<T>::store(sum_out + row * d + (int64_t)i * VN, v[c]);
+      }
+#pragma unroll
+      for (int j = 0; j < VN; ++j) s += v[c][j];
+    }
+  }
+  const float mu = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    if (lane + 32 * c < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { const float t = v[c][j] - mu; q += t * t; }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    const int i = lane + 32 * c;
+    if (i < nvec) {
+      float o[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o[j] = (v[c][j] - mu) * rs * gamma[i * VN + j] + beta[i * VN + j];
+      Vec<T>::store(y + row * d + (int64_t)i * VN, o);
+    }
+  }
+}
+
+// Each warp walks rows (grid-stride), emits dx and keeps dgamma/dbeta for the columns its lanes own in registers;
+// CTA partials land in workspace [gridDim.x][2][d] and are reduced by colreduce_kernel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
+                     float* __restrict__ partial, int64_t rows, int d) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int NC = 32 / VN;  // vectors per lane for d = 1024
+  extern __shared__ float sm[];  // [2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int nvec = d / VN;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float dg[NC][VN], db[NC][VN];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < VN; ++j) dg[c][j] = db[c][j] = 0.f;
+
+  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NC][VN], g[NC][VN];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float xv[VN], dv[VN];
+        Vec<T>::load(x + row * d + (int64_t)i * VN, xv);
+        Vec<T>::load(dy + row * d + (int64_t)i * VN, dv);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          xh[c][j] = (xv[j] - mu) * rs;
+          g[c][j] = dv[j] * gamma[i * VN + j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+          dg[c][j] += dv[j] * xh[c][j];
+          db[c][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float o[VN];
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+        Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int i = lane + 32 * c;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        atomicAdd(&sm[i * VN + j], dg[c][j]);
+        atomicAdd(&sm[d + i * VN + j], db[c][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) partial[(int64_t)blockIdx.x * 2 * d + i] = sm[i];
+}
+
+// out[c] = sum_p partial[p][c], c < n
+__global__ void colreduce_kernel(const float* __restrict__ partial, int nparts, int64_t n, float* __restrict__ out0,
+                                 float* __restrict__ out1, int64_t split) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partial[(int64_t)p * n + c];
+  if (c < split) out0[c] = s; else out1[c - split] = s;
+}
+
+// ============================================================================================ column sums (bias grads)
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t n, int64_t ld, int64_t rows_per_chunk,
+                                      float* __restrict__ partial) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int64_t r = r0;
+  for (; r + 3 < r1; r += 4) {
+    s0 += to_f32(x[r * ld + c]); s1 += to_f32(x[(r + 1) * ld + c]);
+    s2 += to_f32(x[(r + 2) * ld + c]); s3 += to_f32(x[(r + 3) * ld + c]);
+  }
+  for (; r < r1; ++r) s0 += to_f32(x[r * ld + c]);
+  partial[(int64_t)blockIdx.y * n + c] = (s0 + s1) + (s2 + s3);
+}
+
+// ============================================================================================ elementwise
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[i + j] = from_f32<D>(to_f32(s[i + j]));
+    } else {
+      for (int64_t j = i; j < n; ++j) d[j] = from_f32<D>(to_f32(s[j]));
+    }
+  }
+}
+
+enum { EW_ADD = 0, EW_GELU = 1, EW_DGELU = 2 };
+template <typename T, int OP>
+__global__ void ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t nv = n / VN;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float av[VN], bv[VN], o[VN];
+    Vec<T>::load(a + i * VN, av);
+    if (OP != EW_GELU) Vec<T>::load(b + i * VN, bv);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) o[j] = OP == EW_ADD ? av[j] + bv[j] : OP == EW_GELU ? gelu_f(av[j]) : bv[j] * dgelu_f(av[j]);
+    Vec<T>::store(y + i * VN, o);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int64_t i = nv * VN; i < n; ++i) {
+      const float av = to_f32(a[i]), bv = OP != EW_GELU ? to_f32(b[i]) : 0.f;
+      y[i] = from_f32<T>(OP == EW_ADD ? av + bv : OP == EW_GELU ? gelu_f(av) : bv * dgelu_f(av));
+    }
+  }
+}
+
+// ============================================================================================ conv-stem staging
+// out[(b*To + t)*3C + c*3 + k] = in[b, t*stride + k - 1, c]  (column order matches conv.weight.view(d, C*3))
+template <typename T>
+__global__ void im2col_k3_kernel(const T* __restrict__ in, int channels_first, int64_t B, int C, int64_t Tin, int stride,
+                                 int64_t To, T* __restrict__ out) {
+  const int64_t row = blockIdx.x;  // b*To + t
+  const int64_t b = row / To, t = row - b * To;
+  const int K3 = 3 * C;
+  for (int j = threadIdx.x; j < K3; j += blockDim.x) {
+    const int c = j / 3, k = j - c * 3;
+    const int64_t ti = t * stride + k - 1;
+    T v = from_f32<T>(0.f);
+    if (ti >= 0 && ti < Tin) v = channels_first ? in[(b * C + c) * Tin + ti] : in[(b * Tin + ti) * C + c];
+    out[row * K3 + j] = v;
+  }
+}
+
+// din[b, ti, c] = sum_{k} dcol[(b*To + t)*3C + c*3 + k] with t*stride + k - 1 == ti
+template <typename T>
+__global__ void col2im_k3_kernel(const T* __restrict__ dcol, int64_t B, int C, int64_t Tin, int stride, int64_t To,
+                                 T* __restrict__ din) {
+  const int64_t row = blockIdx.x;  // b*Tin + ti
+  const int64_t b = row / Tin, ti = row - b * Tin;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int64_t num = ti + 1 - k;
+      if (num >= 0 && num % stride == 0) {
+        const int64_t t = num / stride;
+        if (t < To) s += to_f32(dcol[(b * To + t) * 3 * C + c * 3 + k]);
+      }
+    }
+    din[row * C + c] = from_f32<T>(s);
+  }
+}
+
+// ============================================================================================ attention softmax
+// One warp per row; three passes over a row that stays in L1 (<= 6 KB).
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_fwd_kernel(const T* __restrict__ s, T* __restrict__ p, int64_t rows, int64_t heads, int64_t sq, int sk, int64_t ld,
+                   float scale, const int32_t* __restrict__ key_len, int causal) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t qi = row % sq, b = row / (sq * heads);
+  int limit = sk;
+  if (key_len) limit = min(limit, key_len[b]);
+  if (causal) limit = min(limit, (int)qi + causal);  // columns [0, qi + causal) are visible (causal = 1: j <= i)
+  const T* sr = s + row * ld;
+  T* pr = p + row * ld;
+  float m = -INFINITY;
+  for (int j = lane; j < limit; j += 32) m = fmaxf(m, to_f32(sr[j]) * scale);
+  m = warp_max(m);
+  float z = 0.f;
+  for (int j = lane; j < limit; j += 32) z += __expf(to_f32(sr[j]) * scale - m);
+  z = warp_sum(z);
+  const float inv = limit > 0 ? 1.f / z : 0.f;
+  for (int j = lane; j < sk; j += 32) pr[j] = from_f32<T>(j < limit ? __expf(to_f32(sr[j]) * scale - m) * inv : 0.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const T* __restrict__ p, const T* __restrict__ dp, T* __restrict__ ds, int64_t rows, int sk, int64_t ld,
+                   float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* pr = p + row * ld;
+  const T* dr = dp + row * ld;
+  T* o = ds + row * ld;
+  float dot = 0.f;
+  for (int j = lane; j < sk; j += 32) dot += to_f32(pr[j]) * to_f32(dr[j]);
+  dot = warp_sum(dot);
+  for (int j = lane; j < sk; j += 32) o[j] = from_f32<T>(scale * to_f32(pr[j]) * (to_f32(dr[j]) - dot));
+}
+
+// ============================================================================================ decoder token embedding
+template <typename T, typename PT>
+__global__ void decoder_embed_kernel(const float* __restrict__ E, const float* __restrict__ pos, const PT* __restrict__ prompt,
+                                     const int64_t* __restrict__ ids, int64_t n_tok, int64_t q, int d, int64_t sop,
+                                     T* __restrict__ out) {
+  const int64_t U = 1 + q + n_tok;
+  const int64_t row = blockIdx.x, b = row / U, u = row - b * U;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float v;
+    if (u == 0) v = E[sop * d + c];
+    else if (u <= q) v = to_f32(prompt[(b * q + (u - 1)) * d + c]);
+    else v = E[ids[b * n_tok + (u - 1 - q)] * d + c];
+    out[row * d + c] = from_f32<T>(v + pos[u * d + c]);
+  }
+}
+
+template <typename T, typename PT>
+__global__ void decoder_embed_bwd_kernel(const T* __restrict__ dout, const int64_t* __restrict__ ids, int64_t n_tok, int64_t q,
+                                         int d, int64_t sop, float* __restrict__ dE, float* __restrict__ dpos,
+                                         PT* __restrict__ dprompt) {
+  const int64_t U = 1 + q + n_tok;
+  const int64_t row = blockIdx.x, b = row / U, u = row - b * U;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const float g = to_f32(dout[row * d + c]);
+    atomicAdd(&dpos[u * d + c], g);
+    if (u == 0) atomicAdd(&dE[sop * d + c], g);
+    else if (u <= q) dprompt[(b * q + (u - 1)) * d + c] = from_f32<PT>(g);
+    else atomicAdd(&dE[ids[b * n_tok + (u - 1 - q)] * d + c], g);
+  }
+}
+
+// ============================================================================================ L2 normalise rows (fp32)
+__global__ void __launch_bounds__(256)
+l2norm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ norm, int64_t rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int j = lane; j < d; j += 32) { const float v = x[row * d + j]; s += v * v; }
+  const float nrm = sqrtf(warp_sum(s));
+  const float inv = 1.f / fmaxf(nrm, eps);
+  if (lane == 0 && norm) norm[row] = nrm;
+  for (int j = lane; j < d; j += 32) y[row * d + j] = x[row * d + j] * inv;
+}
+
+__global__ void __launch_bounds__(256)
+l2norm_bwd_kernel(const float* __restrict__ y, const float* __restrict__ norm, const float* __restrict__ gy,
+                  float* __restrict__ gx, int64_t rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float nrm = norm[row];
+  float dot = 0.f;
+  for (int j = lane; j < d; j += 32) dot += y[row * d + j] * gy[row * d + j];
+  dot = warp_sum(dot);
+  if (nrm > eps) {
+    const float inv = 1.f / nrm;
+    for (int j = lane; j < d; j += 32) gx[row * d + j] = (gy[row * d + j] - y[row * d + j] * dot) * inv;
+  } else {
+    const float inv = 1.f / eps;
+    for (int j = lane; j < d; j += 32) gx[row * d + j] = gy[row * d + j] * inv;
+  }
+}
+
+static inline unsigned grid_for(int64_t n_items, int per_block) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_items + per_block - 1) / per_block, (int64_t)sm_count() * 16));
+}
+
+}  // namespace tsw
+
+using namespace tsw;
+
+#define DISPATCH_T(dtype, ...)                                   \
+  if ((dtype) == TSW_F32) { using T = float; __VA_ARGS__; }      \
+  else if ((dtype) == TSW_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+  else { set_error("bad dtype %d", (int)(dtype)); return TSW_E_INVALID; }
+
+extern "C" int tsw_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* sum_out,
+                                 float* mean, float* rstd, int64_t rows, int64_t d, float eps, int dtype, tsw_stream_t stream) {
+  TSW_CHECK_ARG(x && y && gamma && beta && rows > 0 && d > 0, "layernorm_fwd: null/empty argument");
+  const int vn = dtype == TSW_F32 ? 4 : 8;
+  TSW_CHECK_ARG(d % vn == 0 && d / vn <= 32 * kLnChunks, "layernorm_fwd: d=%lld unsupported (need d %% %d == 0, d <= %d)",
+                (long long)d, vn, 32 * kLnChunks * vn);
+  TSW_CHECK_ARG(aligned16(x) && aligned16(y) && (!res || aligned16(res)) && (!sum_out || aligned16(sum_out)), "layernorm_fwd: pointers must be 16-byte aligned");
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)res, gamma, beta, (T*)y,
+                                                                                 (T*)sum_out, mean, rstd, rows, (int)d, eps)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+static int ln_bwd_grid() { return sm_count() * 2; }
+
+extern "C" size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d) { return sizeof(float) * 2 * (size_t)d * ln_bwd_grid(); }
+
+extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
+                                 float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
+                                 size_t workspace_bytes, tsw_stream_t stream) {
+  TSW_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "layernorm_bwd: null/empty argument");
+  const int vn = dtype == TSW_F32 ? 4 : 8;
+  TSW_CHECK_ARG(d % vn == 0 && d <= 1024, "layernorm_bwd: d=%lld unsupported (d %% %d == 0, d <= 1024)", (long long)d, vn);
+  if (!workspace || workspace_bytes < tsw_layernorm_bwd_workspace_bytes(rows, d)) { set_error("layernorm_bwd: workspace too small"); return TSW_E_WORKSPACE; }
+  const int grid = (int)std::min<int64_t>(ln_bwd_grid(), (rows + 7) / 8);
+  float* partial = (float*)workspace;
+  const size_t smem = sizeof(float) * 2 * d;
+  DISPATCH_T(dtype, (layernorm_bwd_kernel<T><<<grid, 256, smem, as_stream(stream)>>>((const T*)dy, (const T*)x, gamma, mean, rstd,
+                                                                                     (T*)dx, partial, rows, (int)d)));
+  TSW_LAUNCH_CHECK();
+  colreduce_kernel<<<(unsigned)((2 * d + 255) / 256), 256, 0, as_stream(stream)>>>(partial, grid, 2 * d, dgamma, dbeta, d);
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, tsw_stream_t stream) {
+  TSW_CHECK_ARG(src && dst && n >= 0, "cast: null argument");
+  if (n == 0) return TSW_OK;
+  const unsigned grid = grid_for(n, 1024);
+  cudaStream_t st = as_stream(stream);
+  if (src_dtype == TSW_F32 && dst_dtype == TSW_BF16) cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == TSW_BF16 && dst_dtype == TSW_F32) cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == TSW_F32 && dst_dtype == TSW_F32) cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == TSW_BF16 && dst_dtype == TSW_BF16) cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else { set_error("cast: bad dtypes %d -> %d", src_dtype, dst_dtype); return TSW_E_INVALID; }
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+static int64_t colsum_chunks(int64_t rows, int64_t n) {
+  const int64_t col_blocks = (n + 255) / 256;
+  int64_t chunks = std::max<int64_t>(1, ((int64_t)sm_count() * 8) / col_blocks);
+  chunks = std::min<int64_t>(chunks, (rows + 15) / 16);
+  return std::max<int64_t>(1, std::min<int64_t>(chunks, 65535));
+}
+extern "C" size_t tsw_colsum_workspace_bytes(int64_t rows, int64_t n) { return sizeof(float) * (size_t)n * colsum_chunks(rows, n); }
+
+extern "C" int tsw_colsum(const void* x, int dtype, int64_t rows, int64_t n, int64_t ld, float* out, void* workspace,
+                          size_t workspace_bytes, tsw_stream_t stream) {
+  TSW_CHECK_ARG(x && out && rows > 0 && n > 0 && ld >= n, "colsum: bad argument");
+  if (!workspace || workspace_bytes < tsw_colsum_workspace_bytes(rows, n)) { set_error("colsum: workspace too small"); return TSW_E_WORKSPACE; }
+  const int64_t chunks = colsum_chunks(rows, n);
+  const int64_t rpc = (rows + chunks - 1) / chunks;
+  dim3 grid((unsigned)((n + 255) / 256), (unsigned)chunks);
+  float* partial = (float*)workspace;
+  DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, rows, n, ld, rpc, partial)));
+  TSW_LAUNCH_CHECK();
+  colreduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, (int)chunks, n, out, out, n);
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+template <int OP>
+static int ew_launch(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_stream_t stream) {
+  TSW_CHECK_ARG(a && y && (OP == EW_GELU || b) && n >= 0, "elementwise: null argument");
+  TSW_CHECK_ARG(aligned16(a) && aligned16(y) && (!b || aligned16(b)), "elementwise: pointers must be 16-byte aligned");
+  if (n == 0) return TSW_OK;
+  const unsigned grid = grid_for(n / 4 + 1, 256);
+  DISPATCH_T(dtype, (ew_kernel<T, OP><<<grid, 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)y, n)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+extern "C" int tsw_add(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_ADD>(a, b, y, dtype, n, stream); }
+extern "C" int tsw_gelu_fwd(const void* x, void* y, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_GELU>(x, nullptr, y, dtype, n, stream); }
+extern "C" int tsw_gelu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_DGELU>(x, dy, dx, dtype, n, stream); }
+
+extern "C" int tsw_im2col_k3(const void* in, int dtype, int channels_first, int64_t B, int64_t C, int64_t Tin, int stride, void* out,
+                             tsw_stream_t stream) {
+  TSW_CHECK_ARG(in && out && B > 0 && C > 0 && Tin > 0 && (stride == 1 || stride == 2), "im2col_k3: bad argument");
+  const int64_t To = (Tin + 2 - 3) / stride + 1;
+  TSW_CHECK_ARG(B * To < (1ll << 31), "im2col_k3: too many rows");
+  DISPATCH_T(dtype, (im2col_k3_kernel<T><<<(unsigned)(B * To), 256, 0, as_stream(stream)>>>((const T*)in, channels_first, B, (int)C, Tin, stride, To, (T*)out)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_col2im_k3(const void* dcol, int dtype, int64_t B, int64_t C, int64_t Tin, int stride, void* din, tsw_stream_t stream) {
+  TSW_CHECK_ARG(dcol && din && B > 0 && C > 0 && Tin > 0 && (stride == 1 || stride == 2), "col2im_k3: bad argument");
+  const int64_t To = (Tin + 2 - 3) / stride + 1;
+  TSW_CHECK_ARG(B * Tin < (1ll << 31), "col2im_k3: too many rows");
+  DISPATCH_T(dtype, (col2im_k3_kernel<T><<<(unsigned)(B * Tin), 256, 0, as_stream(stream)>>>((const T*)dcol, B, (int)C, Tin, stride, To, (T*)din)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_softmax_fwd(const void* s, void* p, int dtype, int64_t batch, int64_t heads, int64_t sq, int64_t sk, int64_t ld,
+                               float scale, const int32_t* key_len, int causal, tsw_stream_t stream) {
+  TSW_CHECK_ARG(s && p && batch > 0 && heads > 0 && sq > 0 && sk > 0 && ld >= sk, "softmax_fwd: bad argument");
+  const int64_t rows = batch * heads * sq;
+  TSW_CHECK_ARG((rows + 7) / 8 < (1ll << 31), "softmax_fwd: too many rows");
+  DISPATCH_T(dtype, (softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>((const T*)s, (T*)p, rows, heads, sq, (int)sk, ld, scale, key_len, causal)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_softmax_bwd(const void* p, const void* dp, void* ds, int dtype, int64_t rows, int64_t sk, int64_t ld, float scale,
+                               tsw_stream_t stream) {
+  TSW_CHECK_ARG(p && dp && ds && rows > 0 && sk > 0 && ld >= sk, "softmax_bwd: bad argument");
+  DISPATCH_T(dtype, (softmax_bwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>((const T*)p, (const T*)dp, (T*)ds, rows, (int)sk, ld, scale)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_decoder_embed(const float* E, const float* pos, const void* prompt, int prompt_dtype, const int64_t* ids,
+                                 int64_t B, int64_t n_tok, int64_t q, int64_t d, int64_t sop, void* out, int dtype, tsw_stream_t stream) {
+  TSW_CHECK_ARG(E && pos && ids && out && B > 0 && n_tok > 0 && q >= 0 && d > 0 && (q == 0 || prompt), "decoder_embed: bad argument");
+  TSW_CHECK_ARG(prompt_dtype == dtype, "decoder_embed: prompt dtype must equal the output dtype");
+  const unsigned grid = (unsigned)(B * (1 + q + n_tok));
+  DISPATCH_T(dtype, (decoder_embed_kernel<T, T><<<grid, 128, 0, as_stream(stream)>>>(E, pos, (const T*)prompt, ids, n_tok, q, (int)d, sop, (T*)out)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_decoder_embed_bwd(const void* dout, int dtype, const int64_t* ids, int64_t B, int64_t n_tok, int64_t q, int64_t d,
+                                     int64_t sop, float* dE, float* dpos, void* dprompt, int prompt_dtype, tsw_stream_t stream) {
+  TSW_CHECK_ARG(dout && ids && dE && dpos && B > 0 && n_tok > 0 && (q == 0 || dprompt), "decoder_embed_bwd: bad argument");
+  TSW_CHECK_ARG(prompt_dtype == dtype, "decoder_embed_bwd: prompt dtype must equal the gradient dtype");
+  const unsigned grid = (unsigned)(B * (1 + q + n_tok));
+  DISPATCH_T(dtype, (decoder_embed_bwd_kernel<T, T><<<grid, 128, 0, as_stream(stream)>>>((const T*)dout, ids, n_tok, q, (int)d, sop, dE, dpos, (T*)dprompt)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_l2norm_fwd(const float* x, float* y, float* norm, int64_t rows, int64_t d, float eps, tsw_stream_t stream) {
+  TSW_CHECK_ARG(x && y && rows > 0 && d > 0, "l2norm_fwd: bad argument");
+  l2norm_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(x, y, norm, rows, (int)d, eps);
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+extern "C" int tsw_l2norm_bwd(const float* y, const float* norm, const float* gy, float* gx, int64_t rows, int64_t d, float eps,
+                              tsw_stream_t stream) {
+  TSW_CHECK_ARG(y && norm && gy && gx && rows > 0 && d > 0, "l2norm_bwd: bad argument");
+  l2norm_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, as_stream(stream)>>>(y, norm, gy, gx, rows, (int)d, eps);
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}

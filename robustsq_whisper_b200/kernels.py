@@ -1,0 +1,355 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd here; see functional.py).
+
+PyTorch is used for device memory, streams and workspace allocation only: every arithmetic result below is produced by
+a hand-written sm_100a kernel in libtsw_sm100.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _C
+from ._C import BF16, F32, GemmDesc, check, dtype_code, ptr, require_cuda, stream
+
+_logmel_ready = set()
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ----------------------------------------------------------------------------------------------- K1 log-mel
+def _hz_to_mel(f):
+    f = np.asanyarray(f, dtype=np.float64)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    logstep = np.log(6.4) / 27.0
+    return np.where(f >= min_log_hz, min_log_hz / f_sp + np.log(np.maximum(f, 1e-10) / min_log_hz) / logstep, f / f_sp)
+
+
+def _mel_to_hz(m):
+    m = np.asanyarray(m, dtype=np.float64)
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    logstep = np.log(6.4) / 27.0
+    return np.where(m >= min_log_hz / f_sp, min_log_hz * np.exp(logstep * (m - min_log_hz / f_sp)), f_sp * m)
+
+
+def whisper_mel_filterbank(n_mels: int = 80, n_fft: int = 400, sr: int = 16000) -> np.ndarray:
+    """The 80 x 201 slaney-scale, slaney-normalised triangular filterbank Whisper ships as assets/mel_filters.npz
+    (== librosa.filters.mel(sr=16000, n_fft=400, n_mels=80)); reference call site whisper_encoder.py:52,113."""
+    n_freq = n_fft // 2 + 1
+    freqs = np.linspace(0.0, sr / 2.0, n_freq)
+    pts = _mel_to_hz(np.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), n_mels + 2))
+    width = np.diff(pts)
+    ramps = pts[:, None] - freqs[None, :]
+    fb = np.maximum(0.0, np.minimum(-ramps[:-2] / width[:-1, None], ramps[2:] / width[1:, None]))
+    fb *= (2.0 / (pts[2:] - pts[:-2]))[:, None]
+    return np.ascontiguousarray(fb, dtype=np.float32)
+
+
+def logmel(audio: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """audio (B, N) fp32 cuda -> (B, 80, N // 160) log-mel (whisper_encoder.py:99-129)."""
+    require_cuda(audio)
+    lib = _C.load()
+    if audio.dtype != torch.float32:
+        raise _C.TswError("logmel: audio must be float32")
+    if audio.stride(-1) != 1:
+        audio = audio.contiguous()
+    dev = audio.device.index or 0
+    if dev not in _logmel_ready:
+        fb = whisper_mel_filterbank()
+        with torch.cuda.device(audio.device):
+            check(lib.tsw_logmel_init(fb.ctypes.data_as(ctypes.c_void_p), 80, 201), "tsw_logmel_init")
+        _logmel_ready.add(dev)
+    B, N = audio.shape
+    out = torch.empty((B, 80, N // 160), dtype=out_dtype, device=audio.device)
+    code = dtype_code(out_dtype)
+    ws = _ws(lib.tsw_logmel_workspace_bytes(B, N, code), audio.device)
+    check(lib.tsw_logmel_fwd(ptr(audio), B, N, audio.stride(0), ptr(out), code, ptr(ws), ws.numel(), stream()), "tsw_logmel_fwd")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- K5 GEMM
+def gemm(
+    a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+    lda: Optional[int] = None, ldb: Optional[int] = None,
+    batch: Tuple[int, int] = (1, 1),
+    a_strides: Tuple[int, int] = (0, 0), b_strides: Tuple[int, int] = (0, 0),
+    out: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None, ldd: Optional[int] = None,
+    d_strides: Tuple[int, int] = (0, 0),
+    bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, ldres: Optional[int] = None,
+    res_strides: Tuple[int, int] = (0, 0), res_row_mod: int = 0,
+    aux_in: Optional[Tensor] = None, aux_out: Optional[Tensor] = None, epilogue: int = _C.EPI_NONE,
+    alpha: float = 1.0, beta: float = 0.0, impl: int = _C.GEMM_AUTO,
+) -> Tensor:
+    """D = epilogue(alpha * A @ B) with the operand layouts of include/tsw.h.  ``a``/``b`` are only used for their
+    storage (data_ptr, dtype): the logical shapes come from M/N/K, the majors and the leading dimensions.
+    batch = (outer, inner); *_strides = (outer stride, inner stride) in elements."""
+    require_cuda(a, b, out, bias, residual, aux_in, aux_out)
+    lib = _C.load()
+    bo, bi = batch
+    if out is None:
+        assert bo == 1 and bi == 1, "batched gemm needs an explicit output tensor + strides"
+        out = torch.empty((M, N), dtype=out_dtype or a.dtype, device=a.device)
+    g = GemmDesc()
+    g.M, g.N, g.K = M, N, K
+    g.batch_outer, g.batch_inner = bo, bi
+    g.A, g.a_dtype, g.a_mn_major = ptr(a), dtype_code(a.dtype), int(a_mn)
+    g.lda = lda if lda is not None else (M if a_mn else K)
+    g.a_stride_outer, g.a_stride_inner = a_strides
+    g.B, g.b_dtype, g.b_mn_major = ptr(b), dtype_code(b.dtype), int(b_mn)
+    g.ldb = ldb if ldb is not None else (N if b_mn else K)
+    g.b_stride_outer, g.b_stride_inner = b_strides
+    g.D, g.d_dtype = ptr(out), dtype_code(out.dtype)
+    g.ldd = ldd if ldd is not None else N
+    g.d_stride_outer, g.d_stride_inner = d_strides
+    if bias is not None and bias.dtype != torch.float32:
+        raise _C.TswError("gemm: bias must be float32")
+    g.bias = ptr(bias)
+    g.residual = ptr(residual)
+    g.res_dtype = dtype_code(residual.dtype) if residual is not None else 0
+    g.ldres = ldres if ldres is not None else N
+    g.res_stride_outer, g.res_stride_inner = res_strides
+    g.res_row_mod = res_row_mod
+    g.aux_in, g.aux_out = ptr(aux_in), ptr(aux_out)
+    g.epilogue, g.impl = epilogue, impl
+    g.alpha, g.beta = alpha, beta
+    check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- K6 LayerNorm
+def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optional[Tensor] = None, want_sum: bool = False):
+    require_cuda(x, gamma, beta, res)
+    lib = _C.load()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    x = x.contiguous()
+    if res is not None:
+        res = res.contiguous()
+    y = torch.empty_like(x)
+    sum_out = torch.empty_like(x) if (res is not None and want_sum) else None
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    check(lib.tsw_layernorm_fwd(ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(y), ptr(sum_out), ptr(mean), ptr(rstd), rows, d,
+                                eps, dtype_code(x.dtype), stream()), "tsw_layernorm_fwd")
+    return y, sum_out, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+    lib = _C.load()
+    d = x.shape[-1]
+    rows = x.numel() // d
+    dy = dy.contiguous()
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
+    ws = _ws(lib.tsw_layernorm_bwd_workspace_bytes(rows, d), x.device)
+    check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
+                                dtype_code(x.dtype), ptr(ws), ws.numel(), stream()), "tsw_layernorm_bwd")
+    return dx, dgamma, dbeta
+
+
+# ----------------------------------------------------------------------------------------------- elementwise / reductions
+def cast(x: Tensor, dtype: torch.dtype, out: Optional[Tensor] = None) -> Tensor:
+    require_cuda(x)
+    lib = _C.load()
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    check(lib.tsw_cast(ptr(x), dtype_code(x.dtype), ptr(out), dtype_code(dtype), x.numel(), stream()), "tsw_cast")
+    return out
+
+
+def colsum(x: Tensor, rows: int, n: int, ld: Optional[int] = None) -> Tensor:
+    lib = _C.load()
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    ws = _ws(lib.tsw_colsum_workspace_bytes(rows, n), x.device)
+    check(lib.tsw_colsum(ptr(x), dtype_code(x.dtype), rows, n, ld if ld is not None else n, ptr(out), ptr(ws), ws.numel(), stream()), "tsw_colsum")
+    return out
+
+
+def add(a: Tensor, b: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    lib = _C.load()
+    a, b = a.contiguous(), b.contiguous()
+    assert a.shape == b.shape and a.dtype == b.dtype
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib.tsw_add(ptr(a), ptr(b), ptr(out), dtype_code(a.dtype), a.numel(), stream()), "tsw_add")
+    return out
+
+
+def gelu_fwd(x: Tensor) -> Tensor:
+    lib = _C.load()
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    check(lib.tsw_gelu_fwd(ptr(x), ptr(y), dtype_code(x.dtype), x.numel(), stream()), "tsw_gelu_fwd")
+    return y
+
+
+def gelu_bwd(x: Tensor, dy: Tensor) -> Tensor:
+    lib = _C.load()
+    x, dy = x.contiguous(), dy.contiguous()
+    dx = torch.empty_like(x)
+    check(lib.tsw_gelu_bwd(ptr(x), ptr(dy), ptr(dx), dtype_code(x.dtype), x.numel(), stream()), "tsw_gelu_bwd")
+    return dx
+
+
+def im2col_k3(x: Tensor, channels_first: bool, stride: int) -> Tensor:
+    """x (B,C,T) if channels_first else (B,T,C) -> (B*T_out, 3*C), column = c*3 + k (matches conv.weight.view(d, C*3))."""
+    lib = _C.load()
+    x = x.contiguous()
+    if channels_first:
+        B, C, T = x.shape
+    else:
+        B, T, C = x.shape
+    To = (T + 2 - 3) // stride + 1
+    out = torch.empty((B * To, 3 * C), dtype=x.dtype, device=x.device)
+    check(lib.tsw_im2col_k3(ptr(x), dtype_code(x.dtype), int(channels_first), B, C, T, stride, ptr(out), stream()), "tsw_im2col_k3")
+    return out
+
+
+def col2im_k3(dcol: Tensor, B: int, C: int, T: int, stride: int) -> Tensor:
+    lib = _C.load()
+    dcol = dcol.contiguous()
+    din = torch.empty((B, T, C), dtype=dcol.dtype, device=dcol.device)
+    check(lib.tsw_col2im_k3(ptr(dcol), dtype_code(dcol.dtype), B, C, T, stride, ptr(din), stream()), "tsw_col2im_k3")
+    return din
+
+
+def softmax_fwd(s: Tensor, batch: int, heads: int, sq: int, sk: int, scale: float, key_len: Optional[Tensor] = None,
+                causal: int = 0, ld: Optional[int] = None, inplace: bool = True) -> Tensor:
+    lib = _C.load()
+    p = s if inplace else torch.empty_like(s)
+    check(lib.tsw_softmax_fwd(ptr(s), ptr(p), dtype_code(s.dtype), batch, heads, sq, sk, ld if ld is not None else sk, scale,
+                              ptr(key_len), causal, stream()), "tsw_softmax_fwd")
+    return p
+
+
+def softmax_bwd(p: Tensor, dp: Tensor, rows: int, sk: int, scale: float, ld: Optional[int] = None) -> Tensor:
+    lib = _C.load()
+    check(lib.tsw_softmax_bwd(ptr(p), ptr(dp), ptr(dp), dtype_code(p.dtype), rows, sk, ld if ld is not None else sk, scale, stream()), "tsw_softmax_bwd")
+    return dp
+
+
+def decoder_embed(E: Tensor, pos: Tensor, prompt: Tensor, ids: Tensor, sop: int, dtype: torch.dtype) -> Tensor:
+    lib = _C.load()
+    B, n_tok = ids.shape
+    q, d = prompt.shape[1], E.shape[1]
+    prompt = prompt.contiguous()
+    ids = ids.contiguous()
+    out = torch.empty((B, 1 + q + n_tok, d), dtype=dtype, device=E.device)
+    check(lib.tsw_decoder_embed(ptr(E), ptr(pos), ptr(prompt), dtype_code(prompt.dtype), ptr(ids), B, n_tok, q, d, sop, ptr(out),
+                                dtype_code(dtype), stream()), "tsw_decoder_embed")
+    return out
+
+
+def decoder_embed_bwd(dout: Tensor, ids: Tensor, q: int, sop: int, vocab: int, n_pos: int):
+    lib = _C.load()
+    dout = dout.contiguous()
+    B, n_tok = ids.shape
+    d = dout.shape[-1]
+    dE = torch.zeros((vocab, d), dtype=torch.float32, device=dout.device)
+    dpos = torch.zeros((n_pos, d), dtype=torch.float32, device=dout.device)
+    dprompt = torch.empty((B, q, d), dtype=dout.dtype, device=dout.device)
+    check(lib.tsw_decoder_embed_bwd(ptr(dout), dtype_code(dout.dtype), ptr(ids), B, n_tok, q, d, sop, ptr(dE), ptr(dpos), ptr(dprompt),
+                                    dtype_code(dout.dtype), stream()), "tsw_decoder_embed_bwd")
+    return dE, dpos, dprompt
+
+
+# ----------------------------------------------------------------------------------------------- K7 ASP
+def asp_pool_fwd(x: Tensor, gamma: float):
+    require_cuda(x)
+    lib = _C.load()
+    x = x.contiguous()
+    B, T, d = x.shape
+    f32 = dict(dtype=torch.float32, device=x.device)
+    ms, ptil, var, saved = torch.empty((B, 2 * d), **f32), torch.empty((B, d), **f32), torch.empty((B, d), **f32), torch.empty((B, 4), **f32)
+    check(lib.tsw_asp_pool_fwd(ptr(x), dtype_code(x.dtype), B, T, d, gamma, ptr(ms), ptr(ptil), ptr(var), ptr(saved), stream()), "tsw_asp_pool_fwd")
+    return ms, ptil, var, saved
+
+
+def asp_pool_bwd(x: Tensor, gamma: float, ms: Tensor, ptil: Tensor, var: Tensor, saved: Tensor, g_ms: Tensor) -> Tensor:
+    lib = _C.load()
+    B, T, d = x.shape
+    gx = torch.empty_like(x)
+    g_ms = g_ms.contiguous().float()
+    check(lib.tsw_asp_pool_bwd(ptr(x), dtype_code(x.dtype), B, T, d, gamma, ptr(ms), ptr(ptil), ptr(var), ptr(saved), ptr(g_ms), ptr(gx), stream()), "tsw_asp_pool_bwd")
+    return gx
+
+
+def l2norm_fwd(x: Tensor, eps: float):
+    lib = _C.load()
+    x = x.contiguous()
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    norm = torch.empty(rows, dtype=torch.float32, device=x.device)
+    check(lib.tsw_l2norm_fwd(ptr(x), ptr(y), ptr(norm), rows, d, eps, stream()), "tsw_l2norm_fwd")
+    return y, norm
+
+
+def l2norm_bwd(y: Tensor, norm: Tensor, gy: Tensor, eps: float) -> Tensor:
+    lib = _C.load()
+    gy = gy.contiguous()
+    rows, d = y.shape
+    gx = torch.empty_like(y)
+    check(lib.tsw_l2norm_bwd(ptr(y), ptr(norm), ptr(gy), ptr(gx), rows, d, eps, stream()), "tsw_l2norm_bwd")
+    return gx
+
+
+# ----------------------------------------------------------------------------------------------- K8 / K9 / K10
+def aam_softmax_fwd_bwd(f: Tensor, w: Tensor, labels: Tensor, margin: float, temp: float):
+    """-> loss (1,) fp32, ncorrect (1,) int32, gf (B,d), gw (C,d): gradients of the mean CE."""
+    require_cuda(f, w, labels)
+    lib = _C.load()
+    f, w, labels = f.contiguous(), w.contiguous(), labels.contiguous()
+    B, d = f.shape
+    C = w.shape[0]
+    loss = torch.empty(1, dtype=torch.float32, device=f.device)
+    nc = torch.empty(1, dtype=torch.int32, device=f.device)
+    gf, gw = torch.empty_like(f), torch.empty_like(w)
+    ws = _ws(lib.tsw_aam_workspace_bytes(B, C, d), f.device)
+    check(lib.tsw_aam_softmax_fwd_bwd(ptr(f), ptr(w), ptr(labels), B, C, d, margin, temp, ptr(loss), ptr(nc), ptr(gf), ptr(gw),
+                                      ptr(ws), ws.numel(), stream()), "tsw_aam_softmax_fwd_bwd")
+    return loss, nc, gf, gw
+
+
+def arc_infonce_fwd_bwd(prompt: Tensor, z: Tensor, pos_index: Tensor, neg_idx: Tensor, margin: float, temp: float):
+    """-> loss (1,), ncorrect (1,), gprompt (B,q,d), gz (P,d)."""
+    require_cuda(prompt, z, pos_index, neg_idx)
+    lib = _C.load()
+    prompt, z = prompt.contiguous(), z.contiguous()
+    pos_index, neg_idx = pos_index.contiguous(), neg_idx.contiguous()
+    B, q, d = prompt.shape
+    P, K = z.shape[0], neg_idx.shape[1]
+    loss = torch.empty(1, dtype=torch.float32, device=z.device)
+    nc = torch.empty(1, dtype=torch.int32, device=z.device)
+    gprompt = torch.empty_like(prompt)
+    gz = torch.empty_like(z)
+    ws = _ws(lib.tsw_infonce_workspace_bytes(B, K, d), z.device)
+    check(lib.tsw_arc_infonce_fwd_bwd(ptr(prompt), dtype_code(prompt.dtype), B, q, d, ptr(z), P, ptr(pos_index), ptr(neg_idx), K, margin,
+                                      temp, ptr(loss), ptr(nc), ptr(gprompt), ptr(gz), ptr(ws), ws.numel(), stream()), "tsw_arc_infonce_fwd_bwd")
+    return loss, nc, gprompt, gz
+
+
+def lsce_fwd_bwd(logits: Tensor, rows: int, V: int, ld: int, targets: Tensor, ignore_id: int, smoothing: float,
+                 grad_scale: float = 1.0, dlogits: Optional[Tensor] = None, ld_dl: int = 0):
+    """-> loss_sum (1,), counts (2,) int32 = [#correct, #valid]; fills dlogits (if given) with grad_scale * dloss_sum/dlogits."""
+    lib = _C.load()
+    targets = targets.contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    counts = torch.empty(2, dtype=torch.int32, device=logits.device)
+    check(lib.tsw_lsce_fwd_bwd(ptr(logits), dtype_code(logits.dtype), rows, V, ld, ptr(targets), ignore_id, smoothing, grad_scale,
+                               ptr(loss), ptr(counts), ptr(dlogits), dtype_code(dlogits.dtype) if dlogits is not None else 0, ld_dl,
+                               stream()), "tsw_lsce_fwd_bwd")
+    return loss, counts
+
+
+def log_softmax(logits: Tensor, rows: int, V: int, ld: int) -> Tensor:
+    lib = _C.load()
+    out = torch.empty((rows, V), dtype=torch.float32, device=logits.device)
+    check(lib.tsw_log_softmax(ptr(logits), dtype_code(logits.dtype), rows, V, ld, ptr(out), stream()), "tsw_log_softmax")
+    return out

@@ -1,0 +1,412 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle (oracle/port.py, plain torch
+CPU ops) and the golden fixtures produced by the real reference.  Tolerances: bit-level is not available for
+floating point; fp32 kernels are held to ~1e-5 relative, bf16 kernels to 1e-2 relative (BASELINE.json north_star),
+log-mel to 1e-4 absolute."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import port, synth, upstream  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def K():
+    from robustsq_whisper_b200 import kernels
+    return kernels
+
+
+def dev(t):
+    return t.cuda() if torch.is_tensor(t) else t
+
+
+def rel_err(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+# ------------------------------------------------------------------------------------------------ K1
+def test_logmel_golden_and_port(K, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "logmel.npz"))
+    g = torch.Generator().manual_seed(11)
+    audio = 0.1 * torch.randn(2, 32000, generator=g)
+    audio[1, 20000:] = 0.0
+    mel = K.logmel(audio.cuda()).cpu()
+    assert mel.shape == (2, 80, 200)
+    assert (mel - torch.from_numpy(gold["mel"])).abs().max().item() < 1e-4
+    odd = synth.speech_like(torch.Generator().manual_seed(12), 1, 16123)
+    mel_odd = K.logmel(odd.cuda()).cpu()
+    assert (mel_odd - torch.from_numpy(gold["mel_odd"])).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("kind,B,secs", [("gauss", 4, 30.0), ("speech", 3, 10.0), ("gauss", 1, 0.03)])
+def test_logmel_full_size_vs_port(K, kind, B, secs):
+    b = synth.make_batch(B, secs, 1.0, kind=kind)
+    ref, _ = port.log_mel_spectrogram(b["speech"])
+    got = K.logmel(b["speech"].cuda()).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() < 1e-4
+    got16 = K.logmel(b["speech"].cuda(), torch.bfloat16).float().cpu()
+    assert (got16 - ref).abs().max().item() < 2e-2
+
+
+def test_logmel_rejects_cpu_tensor(K):
+    from robustsq_whisper_b200._C import TswError
+    with pytest.raises(TswError):
+        K.logmel(torch.zeros(1, 16000))
+
+
+# ------------------------------------------------------------------------------------------------ K6 + elementwise
+@pytest.mark.parametrize("dtype,d,rows", [(torch.float32, 384, 77), (torch.float32, 1024, 300), (torch.bfloat16, 1024, 301), (torch.bfloat16, 768, 64), (torch.bfloat16, 512, 9)])
+def test_layernorm_fwd_bwd(K, dtype, d, rows):
+    torch.manual_seed(0)
+    x = torch.randn(rows, d) * 2 + 0.3
+    gamma, beta = torch.randn(d) * 0.5 + 1, torch.randn(d) * 0.1
+    dy = torch.randn(rows, d)
+    xq, dyq = x.to(dtype), dy.to(dtype)
+    xr = xq.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (d,), gr, br, 1e-5)
+    yr.backward(dyq.float())
+    y, _, mean, rstd = K.layernorm_fwd(xq.cuda(), gamma.cuda(), beta.cuda(), 1e-5)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(y.float(), yr) < tol
+    dx, dg, db = K.layernorm_bwd(dyq.cuda(), xq.cuda(), gamma.cuda(), mean, rstd)
+    assert rel_err(dx.float(), xr.grad) < tol
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
+def test_layernorm_fused_residual(K):
+    torch.manual_seed(1)
+    x, r = torch.randn(50, 768), torch.randn(50, 768)
+    g, b = torch.rand(768) + 0.5, torch.randn(768)
+    y, s, _, _ = K.layernorm_fwd(x.cuda(), g.cuda(), b.cuda(), 1e-12, res=r.cuda(), want_sum=True)
+    assert rel_err(s, x + r) < 1e-6
+    assert rel_err(y, F.layer_norm(x + r, (768,), g, b, 1e-12)) < 1e-5
+
+
+def test_elementwise_and_reductions(K):
+    torch.manual_seed(2)
+    x = torch.randn(1000, 777)
+    assert torch.equal(K.cast(x.cuda(), torch.bfloat16).cpu(), x.bfloat16())
+    assert torch.equal(K.cast(x.bfloat16().cuda(), torch.float32).cpu(), x.bfloat16().float())
+    assert rel_err(K.colsum(x.cuda(), 1000, 777), x.sum(0)) < 1e-5
+    assert rel_err(K.colsum(x.bfloat16().cuda(), 1000, 777), x.bfloat16().float().sum(0)) < 1e-5
+    a, b = torch.randn(4099), torch.randn(4099)
+    a, b = a[:4096], b[:4096]
+    assert rel_err(K.add(a.cuda(), b.cuda()), a + b) < 1e-7
+    xr = a.clone().requires_grad_(True)
+    yr = F.gelu(xr)
+    yr.backward(b)
+    assert rel_err(K.gelu_fwd(a.cuda()), yr) < 1e-6
+    assert rel_err(K.gelu_bwd(a.cuda(), b.cuda()), xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("stride,cf", [(1, True), (2, False)])
+def test_im2col_matches_conv1d(K, stride, cf):
+    torch.manual_seed(3)
+    B, C, T, Dout = 2, 80 if cf else 48, 101, 32
+    x = torch.randn(B, C, T)
+    w, bias = torch.randn(Dout, C, 3), torch.randn(Dout)
+    ref = F.conv1d(x, w, bias, stride=stride, padding=1).permute(0, 2, 1)  # (B, To, D)
+    xin = x if cf else x.permute(0, 2, 1).contiguous()
+    col = K.im2col_k3(xin.cuda(), cf, stride)
+    To = ref.shape[1]
+    assert col.shape == (B * To, 3 * C)
+    out = K.gemm(col, w.view(Dout, 3 * C).cuda(), M=B * To, N=Dout, K=3 * C, bias=bias.cuda(), impl=1)
+    assert rel_err(out.view(B, To, Dout), ref) < 1e-5
+    if not cf:
+        dcol = torch.randn(B * To, 3 * C)
+        xr = xin.clone().requires_grad_(True)
+        cols_ref = F.unfold(xr.permute(0, 2, 1).unsqueeze(-1), kernel_size=(3, 1), padding=(1, 0), stride=(stride, 1))  # (B, C*3, To)
+        cols_ref.permute(0, 2, 1).reshape(B * To, 3 * C).backward(dcol)
+        din = K.col2im_k3(dcol.cuda(), B, C, T, stride)
+        assert rel_err(din, xr.grad) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_softmax_masks_fwd_bwd(K, dtype):
+    torch.manual_seed(4)
+    B, H, Sq, Sk = 2, 3, 37, 53
+    s = torch.randn(B, H, Sq, Sk).to(dtype)
+    key_len = torch.tensor([53, 31], dtype=torch.int32)
+    scale = 0.37
+    mask = torch.arange(Sk)[None, None, None, :] >= key_len[:, None, None, None]
+    ref = torch.softmax((s.float() * scale).masked_fill(mask, float("-inf")), -1)
+    p = K.softmax_fwd(s.cuda().clone(), B, H, Sq, Sk, scale, key_len=key_len.cuda())
+    tol = 1e-6 if dtype == torch.float32 else 1e-2
+    assert rel_err(p.float(), ref) < tol
+    # causal (square)
+    s2 = torch.randn(B, H, Sq, Sq).to(dtype)
+    cm = torch.full((Sq, Sq), float("-inf")).triu_(1)
+    ref2 = torch.softmax(s2.float() * scale + cm, -1)
+    p2 = K.softmax_fwd(s2.cuda().clone(), B, H, Sq, Sq, scale, causal=1)
+    assert rel_err(p2.float(), ref2) < tol
+    # backward
+    pr = ref2.to(dtype).float()
+    dp = torch.randn(B, H, Sq, Sq).to(dtype)
+    ds_ref = scale * pr * (dp.float() - (dp.float() * pr).sum(-1, keepdim=True))
+    ds = K.softmax_bwd(pr.to(dtype).cuda(), dp.cuda().clone(), B * H * Sq, Sq, scale)
+    assert rel_err(ds.float(), ds_ref) < tol
+
+
+def test_decoder_embed_fwd_bwd(K):
+    torch.manual_seed(5)
+    V, d, B, n, q, sop = 200, 64, 3, 7, 4, 150
+    E = torch.randn(V, d, requires_grad=True)
+    pos = torch.randn(32, d, requires_grad=True)
+    prompt = torch.randn(B, q, d, requires_grad=True)
+    ids = torch.randint(0, V, (B, n))
+    ref = torch.cat([E[torch.full((B, 1), sop)], prompt, E[ids]], 1) + pos[: 1 + q + n]
+    out = K.decoder_embed(E.detach().cuda(), pos.detach().cuda(), prompt.detach().cuda(), ids.cuda(), sop, torch.float32)
+    assert rel_err(out, ref) < 1e-6
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    dE, dpos, dprompt = K.decoder_embed_bwd(g.cuda(), ids.cuda(), q, sop, V, 32)
+    assert rel_err(dE, E.grad) < 1e-5 and rel_err(dpos, pos.grad) < 1e-5 and rel_err(dprompt, prompt.grad) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ K7 ASP
+@pytest.mark.parametrize("dtype,B,T,d", [(torch.float32, 6, 37, 64), (torch.float32, 3, 150, 384), (torch.bfloat16, 4, 500, 1024),
+                                        (torch.float32, 2, 500, 1024), (torch.bfloat16, 5, 3, 512), (torch.float32, 2, 1, 64)])
+def test_asp_pool_fwd_bwd(K, dtype, B, T, d):
+    torch.manual_seed(6)
+    x = (torch.randn(B, T, d) * 0.7 + 0.1).to(dtype)
+    gamma = 6.0
+    W = torch.randn(d, 2 * d) * 0.05
+    bias = torch.zeros(d)
+    xr = x.float().requires_grad_(True)
+    # reference [mu; sigma] through the oracle formulae (port.asp_pool minus projection)
+    ptil = F.normalize(xr.mean(1), dim=-1)
+    alpha = torch.softmax(gamma * (ptil[:, None] * xr).sum(-1), -1)[..., None]
+    mu = (alpha * xr).sum(1)
+    sig = torch.sqrt(torch.clamp((alpha * xr * xr).sum(1) - mu * mu, min=0) + 1e-8)
+    ms_ref = torch.cat([mu, sig], -1)
+    g_ms = torch.randn(B, 2 * d)
+    ms_ref.backward(g_ms)
+    ms, pt, var, saved = K.asp_pool_fwd(x.cuda(), gamma)
+    tol = 2e-5 if dtype == torch.float32 else 2e-5  # statistics are fp32 either way; x is exact in both
+    assert rel_err(ms, ms_ref) < tol
+    gx = K.asp_pool_bwd(x.cuda(), gamma, ms, pt, var, saved, g_ms.cuda())
+    assert rel_err(gx.float(), xr.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+def test_l2norm(K):
+    torch.manual_seed(7)
+    x = torch.randn(9, 384)
+    x[3] = 0
+    xr = x.clone().requires_grad_(True)
+    yr = F.normalize(xr, dim=-1)
+    g = torch.randn_like(x)
+    yr.backward(g)
+    y, n = K.l2norm_fwd(x.cuda(), 1e-12)
+    assert rel_err(y, yr) < 1e-6
+    gx = K.l2norm_bwd(y, n, g.cuda(), 1e-12)
+    mask = torch.ones(9, dtype=torch.bool); mask[3] = False
+    assert rel_err(gx.cpu()[mask], xr.grad[mask]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ K8 / K9 vs the real reference's fixture
+@pytest.mark.parametrize("epoch", [0, 6])
+def test_heads_against_reference_fixture(K, golden_dir, epoch):
+    gold = np.load(os.path.join(golden_dir, "heads.npz"))
+    t = f"e{epoch}_"
+    cfg = port.TSConfig()
+    x = torch.tensor(gold["x"]).cuda()
+    prompt = torch.tensor(gold["prompt"]).cuda()
+    W, b, Wc = (torch.tensor(gold[t + k]).cuda() for k in ("asp_w", "asp_b", "aam_w"))
+    gamma = float(gold[t + "gamma"])
+    B, T, d = x.shape
+    ms, pt, var, saved = K.asp_pool_fwd(x, gamma)
+    u = K.gemm(ms, W, M=B, N=d, K=2 * d, bias=b, impl=1)
+    z, un = K.l2norm_fwd(u, 1e-12)
+    assert (z.cpu() - torch.tensor(gold[t + "pooled"])).abs().max().item() < 2e-6
+    labels = torch.tensor(gold[t + "labels"]).cuda()
+    margin = 0.0 if epoch < cfg.warm_up_epochs else cfg.aam_margin
+    loss_aam, nc_aam, gf, gWc = K.aam_softmax_fwd_bwd(z, Wc, labels, margin, cfg.aam_temp)
+    assert loss_aam.item() == pytest.approx(gold[t + "loss_aam"].item(), rel=2e-5)
+    assert nc_aam.item() / B == gold[t + "acc_aam"].item()
+    neg_idx = torch.tensor(gold[t + "neg_idx"]).cuda()
+    pos_index = torch.arange(B).cuda()
+    loss_con, nc_con, gprompt, gz = K.arc_infonce_fwd_bwd(prompt, z, pos_index, neg_idx, 0.15, cfg.contrastive_temp)
+    assert loss_con.item() == pytest.approx(gold[t + "loss_con"].item(), rel=2e-5)
+    assert nc_con.item() / B == gold[t + "acc_con"].item()
+    # total = loss_con + 0.4 * loss_aam, back through normalise -> projection -> ASP
+    gzt = gz + 0.4 * gf
+    gu = K.l2norm_bwd(z, un, gzt, 1e-12)
+    gW = K.gemm(gu, ms, M=d, N=2 * d, K=B, a_mn=True, b_mn=True, lda=d, ldb=2 * d, impl=1)
+    gms = K.gemm(gu, W, M=B, N=2 * d, K=d, b_mn=True, ldb=2 * d, impl=1)
+    gb = K.colsum(gu, B, d)
+    gx = K.asp_pool_bwd(x, gamma, ms, pt, var, saved, gms)
+    for got, name in ((gx, "gx"), (gprompt, "gprompt"), (gW, "gW"), (gb, "gb"), (0.4 * gWc, "gWc")):
+        ref = torch.tensor(gold[t + name])
+        assert (got.cpu() - ref).abs().max().item() <= 2e-4 * max(ref.abs().max().item(), 1e-6) + 1e-7, name
+
+
+@pytest.mark.parametrize("B,C,d", [(32, 1000, 1024), (7, 13, 384)])
+def test_aam_softmax_vs_port(K, B, C, d):
+    torch.manual_seed(8)
+    f = F.normalize(torch.randn(B, d), dim=-1).requires_grad_(True)
+    w = (torch.randn(C, d) * 0.03).requires_grad_(True)
+    labels = torch.randint(0, min(B, C), (B,))
+    loss, acc, _ = port.aam_softmax_loss(f, w, labels, 0.25, 0.0333)
+    loss.backward()
+    l, nc, gf, gw = K.aam_softmax_fwd_bwd(f.detach().cuda(), w.detach().cuda(), labels.cuda(), 0.25, 0.0333)
+    assert l.item() == pytest.approx(loss.item(), rel=1e-4)
+    assert nc.item() / B == acc
+    assert rel_err(gf, f.grad) < 2e-4 and rel_err(gw, w.grad) < 2e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_arc_infonce_vs_port(K, dtype):
+    torch.manual_seed(9)
+    B, q, d, Kn = 16, 16, 512, 20
+    prompt = (torch.randn(B, q, d) * 0.5).to(dtype)
+    z = F.normalize(torch.randn(B, d), dim=-1)
+    neg_idx = torch.randint(0, B, (B, Kn))
+    pr = prompt.float().requires_grad_(True)
+    zr = z.clone().requires_grad_(True)
+    loss, acc, _ = port.arc_infonce_loss(pr, zr, neg_idx, 0.1)
+    loss.backward()
+    l, nc, gp, gz = K.arc_infonce_fwd_bwd(prompt.cuda(), z.cuda(), torch.arange(B).cuda(), neg_idx.cuda(), 0.15, 0.1)
+    assert l.item() == pytest.approx(loss.item(), rel=1e-4)
+    assert nc.item() / B == acc
+    assert rel_err(gz, zr.grad) < 2e-4
+    assert rel_err(gp.float(), pr.grad) < (2e-4 if dtype == torch.float32 else 1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ K10
+@pytest.mark.parametrize("smoothing,V", [(0.1, 51865), (0.0, 1000)])
+def test_label_smoothed_ce(K, smoothing, V):
+    torch.manual_seed(10)
+    B, U = 3, 11
+    logits = (torch.randn(B, U, V) * 2).requires_grad_(True)
+    tgt = torch.randint(0, V, (B, U))
+    tgt[2, -4:] = -1
+    crit = upstream.LabelSmoothingLoss(V, -1, smoothing)
+    loss = crit(logits, tgt)
+    loss.backward()
+    acc = upstream.th_accuracy(logits.detach().view(-1, V), tgt, -1)
+    ldp = (V + 7) // 8 * 8
+    dl = torch.empty(B * U, ldp, device="cuda")
+    ls, counts = K.lsce_fwd_bwd(logits.detach().cuda(), B * U, V, V, tgt.view(-1).cuda(), -1, smoothing, 1.0 / B, dl, ldp)
+    assert ls.item() / B == pytest.approx(loss.item(), rel=1e-5)
+    assert counts[0].item() / counts[1].item() == pytest.approx(acc)
+    assert counts[1].item() == int((tgt != -1).sum())
+    assert rel_err(dl[:, :V].view(B, U, V), logits.grad) < 1e-5
+    lp = K.log_softmax(logits.detach().cuda(), B * U, V, V)
+    assert rel_err(lp, torch.log_softmax(logits.detach().view(-1, V), -1)) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ K5 GEMM
+def _gemm_ref(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    Bm = b.float() if b_mn else b.float().t()
+    return A @ Bm
+
+
+def _mk(M, K_, mn, dtype, ld_pad=0):
+    shape = (K_, M + ld_pad) if mn else (M, K_ + ld_pad)
+    t = (torch.randn(shape) * 0.5).to(dtype)
+    view = t[:, :M] if mn else t[:, :K_]
+    return t, view, shape[1]
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_gemm_simt_layouts(K, a_mn, b_mn, dtype):
+    torch.manual_seed(11)
+    M, N, Kd = 131, 77, 45
+    at, av, lda = _mk(M, Kd, a_mn, dtype, 3)
+    bt, bv, ldb = _mk(N, Kd, b_mn, dtype, 5)
+    ref = _gemm_ref(av, bv, a_mn, b_mn)
+    out = K.gemm(at.cuda(), bt.cuda(), M=M, N=N, K=Kd, a_mn=a_mn, b_mn=b_mn, lda=lda, ldb=ldb, out_dtype=torch.float32, impl=1)
+    assert rel_err(out, ref) < 1e-5
+
+
+TC_SHAPES = [(128, 256, 64), (256, 128, 128), (300, 520, 200), (1516, 1024, 1024), (77, 64, 72), (128, 2048, 16)]
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_gemm_tcgen05_layouts(K, a_mn, b_mn, shape):
+    torch.manual_seed(12)
+    M, N, Kd = shape
+    at, av, lda = _mk(M, Kd, a_mn, torch.bfloat16, 8)
+    bt, bv, ldb = _mk(N, Kd, b_mn, torch.bfloat16, 16)
+    ref = _gemm_ref(av, bv, a_mn, b_mn)
+    out = K.gemm(at.cuda(), bt.cuda(), M=M, N=N, K=Kd, a_mn=a_mn, b_mn=b_mn, lda=lda, ldb=ldb, out_dtype=torch.float32, impl=2)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 2e-5, f"max err {rel_err(out, ref)}"
+    out16 = K.gemm(at.cuda(), bt.cuda(), M=M, N=N, K=Kd, a_mn=a_mn, b_mn=b_mn, lda=lda, ldb=ldb, out_dtype=torch.bfloat16, impl=2)
+    assert rel_err(out16.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_gemm_epilogues(K, impl):
+    torch.manual_seed(13)
+    M, N, Kd = 200, 264, 128
+    dt = torch.bfloat16
+    a, w = (torch.randn(M, Kd) * 0.5).to(dt), (torch.randn(N, Kd) * 0.2).to(dt)
+    bias = torch.randn(N)
+    res = torch.randn(M, N).to(dt)
+    pre = a.float() @ w.float().t() * 0.5 + bias
+    # bias + GELU + residual, pre-activation saved
+    aux = torch.empty(M, N, dtype=dt, device="cuda")
+    out = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, bias=bias.cuda(), residual=res.cuda(), aux_out=aux, epilogue=1, alpha=0.5,
+                 out_dtype=dt, impl=impl)
+    assert rel_err(aux.float(), pre) < 1e-2
+    assert rel_err(out.float(), F.gelu(pre) + res.float()) < 1e-2
+    # dgelu epilogue
+    dy = (torch.randn(M, N)).to(dt)
+    xr = aux.float().cpu().requires_grad_(True)
+    F.gelu(xr).backward(torch.ones_like(xr))
+    out2 = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, aux_in=aux, epilogue=2, out_dtype=dt, impl=impl)
+    assert rel_err(out2.float(), (a.float() @ w.float().t()) * xr.grad) < 1e-2
+    # positional table (res_row_mod) + accumulate (beta = 1), fp32 output
+    pos = torch.randn(50, N)
+    acc0 = torch.randn(M, N)
+    out3 = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, residual=pos.cuda(), res_row_mod=50, out=acc0.clone().cuda(), beta=1.0, impl=impl)
+    ref3 = a.float() @ w.float().t() + pos.repeat(4, 1) + acc0
+    assert rel_err(out3, ref3) < 1e-4
+
+
+@pytest.mark.parametrize("impl", [1, 2])
+def test_gemm_batched_attention_shapes(K, impl):
+    """scores = Q K^T and out = P V over (batch, head) with the (B, S, h*dh) activations addressed in place."""
+    torch.manual_seed(14)
+    B, H, S, dh = 2, 3, 150, 64
+    d = H * dh
+    dt = torch.bfloat16
+    q, k, v = ((torch.randn(B, S, d) * 0.3).to(dt) for _ in range(3))
+    qh, kh, vh = (t.float().view(B, S, H, dh).permute(0, 2, 1, 3) for t in (q, k, v))
+    s_ref = qh @ kh.transpose(-1, -2)
+    Sp = (S + 7) // 8 * 8
+    scores = torch.zeros(B, H, S, Sp, dtype=dt, device="cuda")
+    K.gemm(q.cuda(), k.cuda(), M=S, N=S, K=dh, lda=d, ldb=d, batch=(B, H), a_strides=(S * d, dh), b_strides=(S * d, dh),
+           out=scores, ldd=Sp, d_strides=(H * S * Sp, S * Sp), impl=impl)
+    assert rel_err(scores[..., :S].float(), s_ref) < 1e-2
+    p = torch.softmax(s_ref, -1).to(dt)
+    pp = torch.zeros(B, H, S, Sp, dtype=dt); pp[..., :S] = p
+    o_ref = (p.float() @ vh).permute(0, 2, 1, 3).reshape(B, S, d)
+    out = torch.empty(B, S, d, dtype=dt, device="cuda")
+    K.gemm(pp.cuda(), v.cuda(), M=S, N=dh, K=S, lda=Sp, b_mn=True, ldb=d, batch=(B, H), a_strides=(H * S * Sp, S * Sp), b_strides=(S * d, dh),
+           out=out, ldd=d, d_strides=(S * d, dh), impl=impl)
+    assert rel_err(out.float(), o_ref) < 1e-2
+
+
+def test_gemm_auto_falls_back_to_simt_for_unaligned(K):
+    torch.manual_seed(15)
+    a, b = torch.randn(33, 45).bfloat16(), torch.randn(21, 45).bfloat16()  # ld = 45 breaks the TMA 16-byte rule
+    out = K.gemm(a.cuda(), b.cuda(), M=33, N=21, K=45, out_dtype=torch.float32)
+    assert rel_err(out, a.float() @ b.float().t()) < 1e-5
+    from robustsq_whisper_b200._C import TswError
+    with pytest.raises(TswError):
+        K.gemm(a.cuda(), b.cuda(), M=33, N=21, K=45, out_dtype=torch.float32, impl=2)
