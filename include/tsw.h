@@ -88,6 +88,7 @@ typedef struct {
   int32_t epilogue;    /* TSW_EPI_* */
   int32_t impl;        /* TSW_GEMM_* */
   float alpha, beta;   /* beta in {0,1} */
+  const float* alpha_dev; /* optional device scalar multiplied into alpha (upstream loss gradient), or NULL */
 } tsw_gemm_desc;
 
 size_t tsw_gemm_workspace_bytes(const tsw_gemm_desc* d);
@@ -111,6 +112,8 @@ int tsw_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n
 size_t tsw_colsum_workspace_bytes(int64_t rows, int64_t n);
 int tsw_colsum(const void* x, int dtype, int64_t rows, int64_t n, int64_t ld, float* out, void* workspace,
                size_t workspace_bytes, tsw_stream_t stream);
+/* y = x * s_host * (s_dev ? *s_dev : 1) ; y may alias x. */
+int tsw_scale(const void* x, void* y, int dtype, int64_t n, float s_host, const float* s_dev, tsw_stream_t stream);
 /* y = a + b (same dtype, n elements) ; y may alias a. */
 int tsw_add(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_stream_t stream);
 /* exact (erf) GELU forward / backward for the fp32 SIMT regime when not fused. */

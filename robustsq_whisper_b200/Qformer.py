@@ -1,0 +1,204 @@
+"""SQ-Former (Q-Former) on the sm_100a kernels — same surface as the reference's ``espnet2.asr.adapter.Qformer``:
+``BertConfig`` and ``BertLMHeadModel(config).bert(input_ids=<float feats>, query_embeds=..., attention_mask=...,
+encoder_hidden_states=..., encoder_attention_mask=..., return_dict=True).last_hidden_state`` (reference
+model/Qformer.py:789-950, call site model/qformer_adapter.py:77-84), same state-dict keys.
+
+What is computed (Qformer.py:69-87, 148-268, 382-467): tokens = LN([queries ; Linear(enroll) + sinusoid]); per layer:
+self-attention over all tokens with a key-padding mask, cross-attention from the first q rows to the mixture features
+(key-padding mask), separate GELU FFNs for the query rows and the enrollment rows, every sub-block closed by
+LN(x + residual) with eps 1e-12.  The additive masks of the reference ((1-m)*-10000 and (1-m)*finfo.min) underflow
+to exactly zero probability in fp32, so they are applied as key lengths inside the softmax kernel.
+Not reproduced: dropout 0.1 of BertConfig in training mode (parity runs use p = 0) and the LM/MLM
+heads' forward (never called on this path) — the dead ``cls`` head is kept as frozen parameters for checkpoint keys.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+from . import functional as F
+from .whisper_model import sinusoids
+
+
+class BertConfig:
+    """The BertConfig fields the SQ-Former reads (HF defaults), plus the Q-Former extras set by QFormerAdapter."""
+
+    def __init__(self, **kw):
+        self.vocab_size = 30522
+        self.hidden_size = 768
+        self.num_hidden_layers = 12
+        self.num_attention_heads = 12
+        self.intermediate_size = 3072
+        self.hidden_act = "gelu"
+        self.hidden_dropout_prob = 0.1
+        self.attention_probs_dropout_prob = 0.1
+        self.max_position_embeddings = 512
+        self.layer_norm_eps = 1e-12
+        self.initializer_range = 0.02
+        self.encoder_width = 768
+        self.add_cross_attention = False
+        self.cross_attention_freq = 1
+        self.query_length = 1
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class _SelfParams(nn.Module):
+    def __init__(self, cfg: BertConfig, is_cross: bool):
+        super().__init__()
+        kv_in = cfg.encoder_width if is_cross else cfg.hidden_size
+        self.query = nn.Linear(cfg.hidden_size, cfg.hidden_size)
+        self.key = nn.Linear(kv_in, cfg.hidden_size)
+        self.value = nn.Linear(kv_in, cfg.hidden_size)
+
+
+class _OutParams(nn.Module):
+    def __init__(self, in_f: int, cfg: BertConfig):
+        super().__init__()
+        self.dense = nn.Linear(in_f, cfg.hidden_size)
+        self.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+
+
+class _AttnParams(nn.Module):
+    def __init__(self, cfg: BertConfig, is_cross: bool = False):
+        super().__init__()
+        self.self = _SelfParams(cfg, is_cross)
+        self.output = _OutParams(cfg.hidden_size, cfg)
+
+
+class _InterParams(nn.Module):
+    def __init__(self, cfg: BertConfig):
+        super().__init__()
+        self.dense = nn.Linear(cfg.hidden_size, cfg.intermediate_size)
+
+
+class BertLayer(nn.Module):
+    def __init__(self, cfg: BertConfig, layer_num: int):
+        super().__init__()
+        self.attention = _AttnParams(cfg)
+        self.has_cross_attention = bool(cfg.add_cross_attention and layer_num % cfg.cross_attention_freq == 0)
+        if self.has_cross_attention:
+            self.crossattention = _AttnParams(cfg, is_cross=True)
+        self.intermediate = _InterParams(cfg)
+        self.output = _OutParams(cfg.intermediate_size, cfg)
+        self.intermediate_query = _InterParams(cfg)
+        self.output_query = _OutParams(cfg.intermediate_size, cfg)
+
+
+class BertEmbeddings(nn.Module):
+    def __init__(self, cfg: BertConfig):
+        super().__init__()
+        self.word_embeddings = nn.Linear(cfg.encoder_width, cfg.hidden_size)
+        self.register_buffer("position_embeddings", sinusoids(cfg.max_position_embeddings, cfg.hidden_size))
+        self.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+
+
+class BertEncoder(nn.Module):
+    def __init__(self, cfg: BertConfig):
+        super().__init__()
+        self.layer = nn.ModuleList([BertLayer(cfg, i) for i in range(cfg.num_hidden_layers)])
+
+
+def _attention_block(p: _AttnParams, hidden: Tensor, n_head: int, key_len: Optional[Tensor], kv: Optional[Tensor] = None) -> Tensor:
+    """BertSelfAttention + BertSelfOutput (Qformer.py:148-268)."""
+    src = hidden if kv is None else kv
+    q = F.linear(hidden, p.self.query.weight, p.self.query.bias)
+    k = F.linear(src, p.self.key.weight, p.self.key.bias)
+    v = F.linear(src, p.self.value.weight, p.self.value.bias)
+    dh = q.shape[-1] // n_head
+    ctx = F.attention(q, k, v, n_head, dh ** -0.5, key_len=key_len)
+    out = F.linear(ctx, p.output.dense.weight, p.output.dense.bias)
+    ln = p.output.LayerNorm
+    return F.layernorm(out, ln.weight, ln.bias, ln.eps, res=hidden)
+
+
+def _ffn(inter: _InterParams, outp: _OutParams, x: Tensor) -> Tensor:
+    """BertIntermediate + BertOutput (Qformer.py:329-355)."""
+    y = F.mlp(x, inter.dense.weight, inter.dense.bias, outp.dense.weight, outp.dense.bias, residual=None)
+    return F.layernorm(y, outp.LayerNorm.weight, outp.LayerNorm.bias, outp.LayerNorm.eps, res=x)
+
+
+class BertModel(nn.Module):
+    def __init__(self, config: BertConfig, add_pooling_layer: bool = False):
+        super().__init__()
+        self.config = config
+        self.embeddings = BertEmbeddings(config)
+        self.encoder = BertEncoder(config)
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, head_mask=None, query_embeds=None,
+                encoder_hidden_states=None, encoder_attention_mask=None, past_key_values=None, use_cache=None,
+                output_attentions=None, output_hidden_states=None, return_dict=None, is_decoder=False,
+                key_lens: Optional[Tensor] = None, encoder_key_lens: Optional[Tensor] = None):
+        """``input_ids`` carries float enrollment features (B, Se, width) as in the reference call.  Masks must be
+        key-padding masks (prefix of ones): they are converted to lengths unless ``key_lens``/``encoder_key_lens``
+        (int32, cuda) are passed directly."""
+        if input_ids is None or query_embeds is None or encoder_hidden_states is None:
+            raise NotImplementedError("the B200 SQ-Former implements the adapter path: enrollment feats + queries + mixture feats")
+        if is_decoder or past_key_values is not None or output_attentions or output_hidden_states:
+            raise NotImplementedError("decoder / cache / attention outputs are outside the TS-ASR hot path")
+        cfg = self.config
+        emb = self.embeddings
+        q = query_embeds.shape[1]
+        dt = input_ids.dtype
+        pos = F.shadow(emb.position_embeddings, dt)[: input_ids.shape[1]].contiguous()
+        rows_per = input_ids.shape[1]
+        e = F.linear_pos(input_ids, emb.word_embeddings.weight, emb.word_embeddings.bias, pos, rows_per)
+        h = torch.cat([query_embeds.to(dt), e], dim=1)
+        h = F.layernorm(h, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
+        if key_lens is None:
+            key_lens = attention_mask.to(torch.int32).sum(dim=1).to(torch.int32) if attention_mask is not None else None
+        if encoder_key_lens is None:
+            encoder_key_lens = (encoder_attention_mask.to(torch.int32).sum(dim=1).to(torch.int32)
+                                if encoder_attention_mask is not None else None)
+        nh = cfg.num_attention_heads
+        for layer in self.encoder.layer:
+            a = _attention_block(layer.attention, h, nh, key_lens)
+            qa = a[:, :q].contiguous()
+            if layer.has_cross_attention:
+                qa = _attention_block(layer.crossattention, qa, nh, encoder_key_lens, kv=encoder_hidden_states)
+            out_q = _ffn(layer.intermediate_query, layer.output_query, qa)
+            if a.shape[1] > q:
+                out_e = _ffn(layer.intermediate, layer.output, a[:, q:].contiguous())
+                h = torch.cat([out_q, out_e], dim=1)
+            else:
+                h = out_q
+        return SimpleNamespace(last_hidden_state=h, pooler_output=None)
+
+
+class _DeadLMHead(nn.Module):
+    """Parameters of the reference's never-called ``cls`` head (Qformer.py:577-636,961), kept frozen so that ESPnet
+    checkpoints load with identical keys."""
+
+    def __init__(self, cfg: BertConfig):
+        super().__init__()
+        self.predictions = nn.Module()
+        self.predictions.transform = nn.Module()
+        self.predictions.transform.dense = nn.Linear(cfg.hidden_size, cfg.hidden_size)
+        self.predictions.transform.LayerNorm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+        self.predictions.decoder = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
+        self.predictions.bias = nn.Parameter(torch.zeros(cfg.vocab_size))
+        self.predictions.decoder.bias = self.predictions.bias
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+
+class BertLMHeadModel(nn.Module):
+    def __init__(self, config: BertConfig):
+        super().__init__()
+        self.config = config
+        self.bert = BertModel(config, add_pooling_layer=False)
+        self.cls = _DeadLMHead(config)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, module):
+        """Qformer.py:649-659: N(0, initializer_range) weights, zero biases, unit LayerNorm."""
+        if isinstance(module, (nn.Linear, nn.Embedding)):
+            module.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        elif isinstance(module, nn.LayerNorm):
+            module.bias.data.zero_()
+            module.weight.data.fill_(1.0)
+        if isinstance(module, nn.Linear) and module.bias is not None:
+            module.bias.data.zero_()

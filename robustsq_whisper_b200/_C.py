@@ -36,6 +36,7 @@ class GemmDesc(Structure):
         ("aux_in", c_void_p), ("aux_out", c_void_p),
         ("epilogue", c_int32), ("impl", c_int32),
         ("alpha", c_float), ("beta", c_float),
+        ("alpha_dev", c_void_p),
     ]
 
 
@@ -56,6 +57,7 @@ SIGNATURES = {
     "tsw_cast": (c_int, [_P, _I, _P, _I, _I64, _P]),
     "tsw_colsum_workspace_bytes": (_SZ, [_I64, _I64]),
     "tsw_colsum": (c_int, [_P, _I, _I64, _I64, _I64, _P, _P, _SZ, _P]),
+    "tsw_scale": (c_int, [_P, _P, _I, _I64, _F, _P, _P]),
     "tsw_add": (c_int, [_P, _P, _P, _I, _I64, _P]),
     "tsw_gelu_fwd": (c_int, [_P, _P, _I, _I64, _P]),
     "tsw_gelu_bwd": (c_int, [_P, _P, _P, _I, _I64, _P]),

@@ -25,7 +25,7 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   ep.residual = g.residual; ep.ldres = g.ldres; ep.res_row_mod = g.res_row_mod;
   ep.aux_in = g.aux_in; ep.aux_out = g.aux_out;
   ep.epilogue = g.epilogue;
-  ep.alpha = g.alpha; ep.beta = g.beta;
+  ep.alpha = g.alpha; ep.beta = g.beta; ep.alpha_dev = g.alpha_dev;
   ep.M = g.M; ep.N = g.N;
   const int vn = g.d_dtype == TSW_F32 ? 4 : 8;
   auto ok = [&](const void* p, int64_t ld, int64_t so, int64_t si) {

@@ -11,6 +11,7 @@ struct EpiParams {
   const void* aux_in; void* aux_out;
   int epilogue;
   float alpha, beta;
+  const float* alpha_dev;
   int64_t M, N;
   int vec_ok;  // D/residual/aux rows are 16-byte aligned at 8-element (bf16) / 4-element (fp32) column granularity
 };
@@ -28,11 +29,12 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, const float* acc, 
   const DT* ain = p.aux_in ? reinterpret_cast<const DT*>(p.aux_in) + d_off + m * p.ldd : nullptr;
   DT* aout = p.aux_out ? reinterpret_cast<DT*>(p.aux_out) + d_off + m * p.ldd : nullptr;
   const bool full = p.vec_ok && (n0 + NV <= p.N);
+  const float alpha = p.alpha_dev ? p.alpha * __ldg(p.alpha_dev) : p.alpha;
 #pragma unroll
   for (int v0 = 0; v0 < NV; v0 += VN) {
     float v[VN];
 #pragma unroll
-    for (int j = 0; j < VN; ++j) v[j] = p.alpha * acc[v0 + j];
+    for (int j = 0; j < VN; ++j) v[j] = alpha * acc[v0 + j];
     const int64_t n = n0 + v0;
     if (full) {
       if (p.bias) {

@@ -173,6 +173,13 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
   }
 }
 
+template <typename T>
+__global__ void scale_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float s_host, const float* __restrict__ s_dev) {
+  const float s = s_dev ? s_host * __ldg(s_dev) : s_host;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f32<T>(to_f32(x[i]) * s);
+}
+
 enum { EW_ADD = 0, EW_GELU = 1, EW_DGELU = 2 };
 template <typename T, int OP>
 __global__ void ew_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, int64_t n) {
@@ -430,6 +437,13 @@ static int ew_launch(const void* a, const void* b, void* y, int dtype, int64_t n
   if (n == 0) return TSW_OK;
   const unsigned grid = grid_for(n / 4 + 1, 256);
   DISPATCH_T(dtype, (ew_kernel<T, OP><<<grid, 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (T*)y, n)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+extern "C" int tsw_scale(const void* x, void* y, int dtype, int64_t n, float s_host, const float* s_dev, tsw_stream_t stream) {
+  TSW_CHECK_ARG(x && y && n >= 0, "scale: null argument");
+  if (n == 0) return TSW_OK;
+  DISPATCH_T(dtype, (scale_kernel<T><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, n, s_host, s_dev)));
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }

@@ -1,0 +1,525 @@
+"""Autograd-aware operators of the TS-ASR hot path.  Every forward/backward below is a sequence of C-ABI kernel calls
+(kernels.py); PyTorch contributes autograd bookkeeping, views and memory only.
+
+Precision regimes (one per model instance, chosen by the activation dtype):
+  * bf16  — activations/GEMM operands bf16 (tcgen05), fp32 accumulation, fp32 LayerNorm/softmax statistics, fp32 master
+            weights with per-step bf16 shadows.  This is the training regime (the reference under ESPnet AMP autocast).
+  * fp32  — everything fp32 on the fp32-accumulate SIMT GEMM: the exact regime used for fp32 parity and greedy decode.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+from torch.autograd import Function
+
+from . import _C
+from . import kernels as K
+
+_shadow_cache = {}
+
+
+def shadow(p: Tensor, dtype: torch.dtype) -> Tensor:
+    """bf16 shadow of an fp32 master parameter, refreshed when the parameter is updated in place (optimizer step)."""
+    if p.dtype == dtype:
+        return p.detach()
+    key = (id(p), dtype)
+    ent = _shadow_cache.get(key)
+    ver = p._version
+    if ent is not None and ent[0] == ver and ent[1].data_ptr() != 0 and ent[2] == p.data_ptr():
+        return ent[1]
+    s = K.cast(p.detach(), dtype)
+    _shadow_cache[key] = (ver, s, p.data_ptr())
+    return s
+
+
+def clear_shadow_cache() -> None:
+    _shadow_cache.clear()
+
+
+def _impl_for(dtype: torch.dtype) -> int:
+    return _C.GEMM_AUTO if dtype == torch.bfloat16 else _C.GEMM_SIMT
+
+
+# ------------------------------------------------------------------------------------------------ Linear (+bias, +residual)
+class _Linear(Function):
+    """y = x W^T + b (+ residual).  x (rows, K) compute dtype; W (N, K) fp32 master."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Optional[Tensor], residual: Optional[Tensor]):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows, Kd = x2.shape
+        N = w.shape[0]
+        w16 = shadow(w, x.dtype)
+        res2 = None if residual is None else residual.reshape(rows, N).contiguous()
+        y = K.gemm(x2, w16, M=rows, N=N, K=Kd, bias=None if b is None else b.detach(), residual=res2, out_dtype=x.dtype,
+                   impl=_impl_for(x.dtype))
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.has_res = residual is not None
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, w = ctx.saved_tensors
+        rows, Kd = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(rows, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        impl = _impl_for(x2.dtype)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm(dy2, shadow(w, x2.dtype), M=rows, N=Kd, K=N, b_mn=True, ldb=Kd, out_dtype=x2.dtype, impl=impl).view(ctx.in_shape)
+        if ctx.needs_input_grad[1]:
+            dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dy2, rows, N)
+        dres = dy if ctx.has_res else None
+        return dx, dw, db, dres
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
+    return _Linear.apply(x, w, b, residual)
+
+
+class _LinearPos(Function):
+    """y[r] = x[r] W^T + b + table[r % period] — the BertEmbeddings projection + sinusoid add (Qformer.py:77-78)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor, table: Tensor, period: int):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        rows, Kd = x2.shape
+        N = w.shape[0]
+        y = K.gemm(x2, shadow(w, x.dtype), M=rows, N=N, K=Kd, bias=b.detach(), residual=table, res_row_mod=period,
+                   out_dtype=x.dtype, impl=_impl_for(x.dtype))
+        ctx.save_for_backward(x2, w)
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, w = ctx.saved_tensors
+        rows, Kd = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(rows, N).contiguous()
+        impl = _impl_for(x2.dtype)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm(dy2, shadow(w, x2.dtype), M=rows, N=Kd, K=N, b_mn=True, ldb=Kd, out_dtype=x2.dtype, impl=impl).view(ctx.in_shape)
+        dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl)
+        return dx, dw, K.colsum(dy2, rows, N), None, None
+
+
+def linear_pos(x: Tensor, w: Tensor, b: Tensor, table: Tensor, period: int) -> Tensor:
+    return _LinearPos.apply(x, w, b, table, period)
+
+
+# ------------------------------------------------------------------------------------------------ MLP block (fc1 -> GELU -> fc2 [+ residual])
+class _MLP(Function):
+    """y = residual + W2 gelu(W1 x + b1) + b2 — fc1's GELU and fc2's residual ride in the GEMM epilogues; backward fuses
+    gelu'(h) into the dgrad epilogue of fc2."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, residual: Optional[Tensor]):
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows, d = x2.shape
+        H = w1.shape[0]
+        N = w2.shape[0]
+        dt = x.dtype
+        impl = _impl_for(dt)
+        h = torch.empty((rows, H), dtype=dt, device=x.device)
+        g = K.gemm(x2, shadow(w1, dt), M=rows, N=H, K=d, bias=b1.detach(), aux_out=h, epilogue=_C.EPI_GELU, out_dtype=dt, impl=impl)
+        res2 = None if residual is None else residual.reshape(rows, N).contiguous()
+        y = K.gemm(g, shadow(w2, dt), M=rows, N=N, K=H, bias=b2.detach(), residual=res2, out_dtype=dt, impl=impl)
+        ctx.save_for_backward(x2, h, g, w1, w2)
+        ctx.has_res = residual is not None
+        ctx.in_shape = x.shape
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, h, g, w1, w2 = ctx.saved_tensors
+        rows, d = x2.shape
+        H, N = w1.shape[0], w2.shape[0]
+        dt = x2.dtype
+        impl = _impl_for(dt)
+        dy2 = dy.reshape(rows, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl)
+        db2 = K.colsum(dy2, rows, N)
+        dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_DGELU, out_dtype=dt, impl=impl)
+        dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl)
+        db1 = K.colsum(dh, rows, H)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.gemm(dh, shadow(w1, dt), M=rows, N=d, K=H, b_mn=True, ldb=d, out_dtype=dt, impl=impl).view(ctx.in_shape)
+        return dx, dw1, db1, dw2, db2, (dy if ctx.has_res else None)
+
+
+def mlp(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+    return _MLP.apply(x, w1, b1, w2, b2, residual)
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+class _LayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optional[Tensor]):
+        y, s, mean, rstd = K.layernorm_fwd(x, gamma.detach(), beta.detach(), eps, res=res, want_sum=res is not None)
+        ctx.save_for_backward(s if res is not None else x.contiguous(), gamma, mean, rstd)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        xin, gamma, mean, rstd = ctx.saved_tensors
+        dx, dg, db = K.layernorm_bwd(dy, xin, gamma.detach(), mean, rstd)
+        return dx, dg, db, None, (dx if ctx.has_res else None)
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, res: Optional[Tensor] = None) -> Tensor:
+    """LN(x) or, with ``res``, LN(x + res) (the BertSelfOutput / BertOutput pattern, Qformer.py:264-268,351-355)."""
+    return _LayerNorm.apply(x, gamma, beta, eps, res)
+
+
+# ------------------------------------------------------------------------------------------------ residual add
+class _Add(Function):
+    @staticmethod
+    def forward(ctx, a: Tensor, b: Tensor):
+        return K.add(a, b)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        return dy, dy
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    return _Add.apply(a, b)
+
+
+class _Scale(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, s: float):
+        ctx.s = s
+        return K.scale(x, s)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        return K.scale(dy, ctx.s), None
+
+
+def scale(x: Tensor, s: float) -> Tensor:
+    return _Scale.apply(x, float(s))
+
+
+# ------------------------------------------------------------------------------------------------ multi-head attention core
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class _Attention(Function):
+    """softmax(scale * Q K^T + mask) V over (batch, head), Q/K/V addressed in place inside their (B, S, h*dh) tensors.
+    mask: key padding (key_len per batch item) and/or causal.  Probabilities are kept (compute dtype) for backward."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor], causal: bool):
+        B, Sq, d = q.shape
+        Sk = k.shape[1]
+        dh = d // n_head
+        dt = q.dtype
+        impl = _impl_for(dt)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        Skp = _pad8(Sk)
+        p = torch.empty((B, n_head, Sq, Skp), dtype=dt, device=q.device)
+        if Skp != Sk:
+            p[..., Sk:].zero_()
+        K.gemm(q, k, M=Sq, N=Sk, K=dh, lda=d, ldb=d, batch=(B, n_head), a_strides=(Sq * d, dh), b_strides=(Sk * d, dh),
+               out=p, ldd=Skp, d_strides=(n_head * Sq * Skp, Sq * Skp), impl=impl)
+        K.softmax_fwd(p, B, n_head, Sq, Sk, scale, key_len=key_len, causal=1 if causal else 0, ld=Skp)
+        o = torch.empty((B, Sq, d), dtype=dt, device=q.device)
+        K.gemm(p, v, M=Sq, N=dh, K=Sk, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=(n_head * Sq * Skp, Sq * Skp),
+               b_strides=(Sk * d, dh), out=o, ldd=d, d_strides=(Sq * d, dh), impl=impl)
+        ctx.save_for_backward(q, k, v, p)
+        ctx.n_head, ctx.scale = n_head, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, do: Tensor):
+        q, k, v, p = ctx.saved_tensors
+        n_head, scale = ctx.n_head, ctx.scale
+        B, Sq, d = q.shape
+        Sk = k.shape[1]
+        dh = d // n_head
+        Skp = p.shape[-1]
+        dt = q.dtype
+        impl = _impl_for(dt)
+        do = do.contiguous()
+        bs_p = (n_head * Sq * Skp, Sq * Skp)
+        dv = torch.empty_like(v)
+        # dV = P^T dO : A = P stored [Sq][Skp] (MN-major for an (Sk x Sq) operand), B = dO stored [Sq][dh] (MN-major)
+        K.gemm(p, do, M=Sk, N=dh, K=Sq, a_mn=True, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sq * d, dh),
+               out=dv, ldd=d, d_strides=(Sk * d, dh), impl=impl)
+        dp = torch.empty_like(p)
+        if Skp != Sk:
+            dp[..., Sk:].zero_()
+        K.gemm(do, v, M=Sq, N=Sk, K=dh, lda=d, ldb=d, batch=(B, n_head), a_strides=(Sq * d, dh), b_strides=(Sk * d, dh),
+               out=dp, ldd=Skp, d_strides=bs_p, impl=impl)
+        K.softmax_bwd(p, dp, B * n_head * Sq, Sk, scale, ld=Skp)  # dp <- dS (in place)
+        dq = torch.empty_like(q)
+        K.gemm(dp, k, M=Sq, N=dh, K=Sk, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sk * d, dh),
+               out=dq, ldd=d, d_strides=(Sq * d, dh), impl=impl)
+        dk = torch.empty_like(k)
+        K.gemm(dp, q, M=Sk, N=dh, K=Sq, a_mn=True, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sq * d, dh),
+               out=dk, ldd=d, d_strides=(Sk * d, dh), impl=impl)
+        return dq, dk, dv, None, None, None, None
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False) -> Tensor:
+    return _Attention.apply(q, k, v, n_head, scale, key_len, causal)
+
+
+# ------------------------------------------------------------------------------------------------ conv stem (k=3, pad=1) as im2col + GEMM
+class _ConvK3Gelu(Function):
+    """GELU(conv1d(x, w, b, stride, padding=1)) in time-major layout, optional positional table added after the GELU
+    (whisper_encoder.py:446-452).  x: (B, C, T) if channels_first else (B, T, C); out (B, T_out, D)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor, stride: int, channels_first: bool, pos: Optional[Tensor]):
+        dt = x.dtype
+        impl = _impl_for(dt)
+        if channels_first:
+            B, C, T = x.shape
+        else:
+            B, T, C = x.shape
+        D = w.shape[0]
+        col = K.im2col_k3(x, channels_first, stride)
+        rows = col.shape[0]
+        To = rows // B
+        pre = torch.empty((rows, D), dtype=dt, device=x.device)
+        w2 = shadow(w, dt).view(D, 3 * C)
+        posq = None
+        if pos is not None:
+            posq = shadow(pos, dt)[:To].contiguous()
+        y = K.gemm(col, w2, M=rows, N=D, K=3 * C, bias=b.detach(), aux_out=pre, epilogue=_C.EPI_GELU, residual=posq,
+                   res_row_mod=To if pos is not None else 0, out_dtype=dt, impl=impl)
+        ctx.save_for_backward(col, pre, w)
+        ctx.meta = (B, C, T, To, D, stride, channels_first)
+        return y.view(B, To, D)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        col, pre, w = ctx.saved_tensors
+        B, C, T, To, D, stride, channels_first = ctx.meta
+        dt = col.dtype
+        impl = _impl_for(dt)
+        rows = B * To
+        dpre = K.gelu_bwd(pre, dy.reshape(rows, D))
+        dw = K.gemm(dpre, col, M=D, N=3 * C, K=rows, a_mn=True, b_mn=True, lda=D, ldb=3 * C, out_dtype=torch.float32, impl=impl).view(D, C, 3)
+        db = K.colsum(dpre, rows, D)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            assert not channels_first, "input gradient is only needed for the time-major (second) conv"
+            dcol = K.gemm(dpre, shadow(w, dt).view(D, 3 * C), M=rows, N=3 * C, K=D, b_mn=True, ldb=3 * C, out_dtype=dt, impl=impl)
+            dx = K.col2im_k3(dcol, B, C, T, stride)
+        return dx, dw, db, None, None, None
+
+
+def conv_k3_gelu(x: Tensor, w: Tensor, b: Tensor, stride: int, channels_first: bool, pos: Optional[Tensor] = None) -> Tensor:
+    return _ConvK3Gelu.apply(x, w, b, stride, channels_first, pos)
+
+
+# ------------------------------------------------------------------------------------------------ decoder input embedding
+class _DecoderEmbed(Function):
+    @staticmethod
+    def forward(ctx, E: Tensor, pos: Tensor, prompt: Tensor, ids: Tensor, sop: int, dtype: torch.dtype):
+        out = K.decoder_embed(E.detach(), pos.detach(), prompt.to(dtype) if prompt.dtype != dtype else prompt, ids, sop, dtype)
+        ctx.save_for_backward(ids)
+        ctx.meta = (prompt.shape[1], sop, E.shape[0], pos.shape[0], prompt.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout: Tensor):
+        (ids,) = ctx.saved_tensors
+        q, sop, V, n_pos, pdt = ctx.meta
+        dE, dpos, dprompt = K.decoder_embed_bwd(dout, ids, q, sop, V, n_pos)
+        return dE, dpos, dprompt.to(pdt), None, None, None
+
+
+def decoder_embed(E: Tensor, pos: Tensor, prompt: Tensor, ids: Tensor, sop: int, dtype: torch.dtype) -> Tensor:
+    return _DecoderEmbed.apply(E, pos, prompt, ids, sop, dtype)
+
+
+# ------------------------------------------------------------------------------------------------ K7 ASP pooling + projection + L2 norm
+class _AspPool(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, gamma: float):
+        x = x.contiguous()
+        ms, ptil, var, saved = K.asp_pool_fwd(x, gamma)
+        ctx.save_for_backward(x, ms, ptil, var, saved)
+        ctx.gamma = gamma
+        return ms
+
+    @staticmethod
+    def backward(ctx, g_ms: Tensor):
+        x, ms, ptil, var, saved = ctx.saved_tensors
+        return K.asp_pool_bwd(x, ctx.gamma, ms, ptil, var, saved, g_ms), None
+
+
+class _L2Norm(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, eps: float):
+        y, norm = K.l2norm_fwd(x, eps)
+        ctx.save_for_backward(y, norm)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        y, norm = ctx.saved_tensors
+        return K.l2norm_bwd(y, norm, gy, ctx.eps), None
+
+
+def l2norm(x: Tensor, eps: float = 1e-12) -> Tensor:
+    return _L2Norm.apply(x, eps)
+
+
+class _LinearF32(Function):
+    """fp32 projection on the SIMT kernel (ASP projection: B x 2d x d, negligible work, exact arithmetic)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor):
+        ctx.save_for_backward(x, w)
+        return K.gemm(x, w.detach(), M=x.shape[0], N=w.shape[0], K=x.shape[1], bias=b.detach(), impl=_C.GEMM_SIMT)
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        x, w = ctx.saved_tensors
+        gy = gy.contiguous()
+        rows, Kd = x.shape
+        N = w.shape[0]
+        gx = K.gemm(gy, w.detach(), M=rows, N=Kd, K=N, b_mn=True, ldb=Kd, impl=_C.GEMM_SIMT)
+        gw = K.gemm(gy, x, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, impl=_C.GEMM_SIMT)
+        return gx, gw, K.colsum(gy, rows, N)
+
+
+def asp_pool(x: Tensor, gamma: float, proj_w: Tensor, proj_b: Tensor) -> Tensor:
+    """AttentiveStatisticsPooling.forward with lengths=None and use_projection=True (ts_qformer_espnet_model.py:780-857)."""
+    ms = _AspPool.apply(x, float(gamma))
+    return l2norm(_LinearF32.apply(ms, proj_w, proj_b), 1e-12)
+
+
+# ------------------------------------------------------------------------------------------------ K8 / K9 losses
+class _AamSoftmax(Function):
+    @staticmethod
+    def forward(ctx, f: Tensor, w: Tensor, labels: Tensor, margin: float, temp: float):
+        loss, nc, gf, gw = K.aam_softmax_fwd_bwd(f.float(), w.detach(), labels, margin, temp)
+        ctx.save_for_backward(gf, gw)
+        ctx.mark_non_differentiable(nc)
+        return loss, nc
+
+    @staticmethod
+    def backward(ctx, gloss: Tensor, _gnc):
+        gf, gw = ctx.saved_tensors
+        return K.scale(gf, 1.0, gloss), K.scale(gw, 1.0, gloss), None, None, None
+
+
+def aam_softmax(f: Tensor, w: Tensor, labels: Tensor, margin: float, temp: float) -> Tuple[Tensor, Tensor]:
+    """-> (mean CE loss (1,), #correct (1,) int32); ts_qformer_espnet_model.py:370-403."""
+    return _AamSoftmax.apply(f, w, labels, margin, temp)
+
+
+class _ArcInfoNCE(Function):
+    @staticmethod
+    def forward(ctx, prompt: Tensor, z: Tensor, pos_index: Tensor, neg_idx: Tensor, margin: float, temp: float):
+        loss, nc, gprompt, gz = K.arc_infonce_fwd_bwd(prompt, z.float(), pos_index, neg_idx, margin, temp)
+        ctx.save_for_backward(gprompt, gz)
+        ctx.mark_non_differentiable(nc)
+        return loss, nc
+
+    @staticmethod
+    def backward(ctx, gloss: Tensor, _gnc):
+        gprompt, gz = ctx.saved_tensors
+        return K.scale(gprompt, 1.0, gloss), K.scale(gz, 1.0, gloss), None, None, None, None
+
+
+def arc_infonce(prompt: Tensor, z: Tensor, pos_index: Tensor, neg_idx: Tensor, margin: float, temp: float) -> Tuple[Tensor, Tensor]:
+    """-> (mean CE loss (1,), #correct (1,)); ts_qformer_espnet_model.py:687-734 given the sampled negatives."""
+    return _ArcInfoNCE.apply(prompt, z, pos_index, neg_idx, margin, temp)
+
+
+# ------------------------------------------------------------------------------------------------ K10 tied logits + label-smoothed CE
+class _TiedLogitsLSCE(Function):
+    """loss_sum = sum over valid rows of KL(smoothed one-hot || softmax(x E^T)) — logits live only as a (rows, V) scratch
+    in the compute dtype that is overwritten in place by their gradient (whisper_decoder.py:287-289 +
+    ts_qformer_espnet_model.py:321-326)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, E: Tensor, targets: Tensor, ignore_id: int, smoothing: float):
+        dt = x.dtype
+        impl = _impl_for(dt)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        rows, d = x2.shape
+        V = E.shape[0]
+        Vp = _pad8(V)
+        logits = torch.empty((rows, Vp), dtype=dt, device=x.device)
+        K.gemm(x2, shadow(E, dt), M=rows, N=V, K=d, out=logits, ldd=Vp, impl=impl)
+        loss, counts = K.lsce_fwd_bwd(logits, rows, V, Vp, targets.reshape(-1), ignore_id, smoothing, 1.0, logits, Vp)
+        ctx.save_for_backward(x2, logits, E)
+        ctx.in_shape = x.shape
+        ctx.mark_non_differentiable(counts)
+        return loss, counts
+
+    @staticmethod
+    def backward(ctx, gloss: Tensor, _gc):
+        x2, dlog, E = ctx.saved_tensors
+        dt = x2.dtype
+        impl = _impl_for(dt)
+        rows, d = x2.shape
+        V = E.shape[0]
+        Vp = dlog.shape[1]
+        g = gloss.reshape(-1)[:1].float().contiguous()  # upstream scalar stays on the device (no sync): GEMM alpha_dev
+        dx = K.gemm(dlog, shadow(E, dt), M=rows, N=d, K=V, lda=Vp, b_mn=True, ldb=d, out_dtype=dt, impl=impl, alpha_dev=g)
+        dE = K.gemm(dlog, x2, M=V, N=d, K=rows, a_mn=True, lda=Vp, b_mn=True, ldb=d, out_dtype=torch.float32, impl=impl, alpha_dev=g)
+        return dx.view(ctx.in_shape), dE, None, None, None
+
+
+def tied_logits_lsce(x: Tensor, E: Tensor, targets: Tensor, ignore_id: int, smoothing: float) -> Tuple[Tensor, Tensor]:
+    return _TiedLogitsLSCE.apply(x, E, targets, ignore_id, smoothing)
+
+
+class _TiedLogits(Function):
+    """logits = x E^T as fp32 (B, U, V) — the plugin-surface output of the decoder (whisper_decoder.py:287-289)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, E: Tensor):
+        dt = x.dtype
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        rows, d = x2.shape
+        V = E.shape[0]
+        logits = K.gemm(x2, shadow(E, dt), M=rows, N=V, K=d, out_dtype=torch.float32, impl=_impl_for(dt))
+        ctx.save_for_backward(x2, E)
+        ctx.in_shape = x.shape
+        return logits.view(*x.shape[:-1], V)
+
+    @staticmethod
+    def backward(ctx, dl: Tensor):
+        x2, E = ctx.saved_tensors
+        dt = x2.dtype
+        rows, d = x2.shape
+        V = E.shape[0]
+        dl2 = dl.reshape(rows, V).contiguous()
+        dx = K.gemm(dl2, E.detach(), M=rows, N=d, K=V, b_mn=True, ldb=d, out_dtype=dt, impl=_C.GEMM_SIMT)
+        dE = K.gemm(dl2, x2, M=V, N=d, K=rows, a_mn=True, lda=V, b_mn=True, ldb=d, out_dtype=torch.float32, impl=_C.GEMM_SIMT)
+        return dx.view(ctx.in_shape), dE
+
+
+def tied_logits(x: Tensor, E: Tensor) -> Tensor:
+    return _TiedLogits.apply(x, E)

@@ -83,7 +83,7 @@ def gemm(
     bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, ldres: Optional[int] = None,
     res_strides: Tuple[int, int] = (0, 0), res_row_mod: int = 0,
     aux_in: Optional[Tensor] = None, aux_out: Optional[Tensor] = None, epilogue: int = _C.EPI_NONE,
-    alpha: float = 1.0, beta: float = 0.0, impl: int = _C.GEMM_AUTO,
+    alpha: float = 1.0, beta: float = 0.0, impl: int = _C.GEMM_AUTO, alpha_dev: Optional[Tensor] = None,
 ) -> Tensor:
     """D = epilogue(alpha * A @ B) with the operand layouts of include/tsw.h.  ``a``/``b`` are only used for their
     storage (data_ptr, dtype): the logical shapes come from M/N/K, the majors and the leading dimensions.
@@ -117,6 +117,9 @@ def gemm(
     g.aux_in, g.aux_out = ptr(aux_in), ptr(aux_out)
     g.epilogue, g.impl = epilogue, impl
     g.alpha, g.beta = alpha, beta
+    if alpha_dev is not None and (alpha_dev.dtype != torch.float32 or not alpha_dev.is_cuda):
+        raise _C.TswError("gemm: alpha_dev must be a float32 cuda scalar")
+    g.alpha_dev = ptr(alpha_dev)
     check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
     return out
 
@@ -170,6 +173,17 @@ def colsum(x: Tensor, rows: int, n: int, ld: Optional[int] = None) -> Tensor:
     ws = _ws(lib.tsw_colsum_workspace_bytes(rows, n), x.device)
     check(lib.tsw_colsum(ptr(x), dtype_code(x.dtype), rows, n, ld if ld is not None else n, ptr(out), ptr(ws), ws.numel(), stream()), "tsw_colsum")
     return out
+
+
+def scale(x: Tensor, s_host: float = 1.0, s_dev: Optional[Tensor] = None, inplace: bool = False) -> Tensor:
+    """y = x * s_host * s_dev (device scalar, e.g. the upstream loss gradient) without a host sync."""
+    lib = _C.load()
+    x = x.contiguous()
+    y = x if inplace else torch.empty_like(x)
+    if s_dev is not None:
+        s_dev = s_dev.reshape(-1)[:1].float().contiguous()
+    check(lib.tsw_scale(ptr(x), ptr(y), dtype_code(x.dtype), x.numel(), s_host, ptr(s_dev), stream()), "tsw_scale")
+    return y
 
 
 def add(a: Tensor, b: Tensor, out: Optional[Tensor] = None) -> Tensor:

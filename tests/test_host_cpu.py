@@ -1,0 +1,133 @@
+"""CPU: host-side logic of the product package (parsers, add_sos_eos, negative sampling, state-dict surface, the
+world_size-2 gloo path of the data-parallel helpers)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import harness, port, synth, upstream
+
+
+def test_parsers_match_reference_fixture(golden_dir):
+    from robustsq_whisper_b200 import ts_qformer_espnet_model as M
+    gold = np.load(os.path.join(golden_dir, "parsers.npz"))
+    utt = [str(u) for u in gold["utt"]]
+    assert np.array_equal(M.get_similarity_weight(utt).numpy(), gold["sim"])
+    assert np.array_equal(M.get_speaker_labels(utt).numpy(), gold["labels"])
+    assert np.array_equal(M.get_similarity_weight_wsj2mix([str(u) for u in gold["wsj_utt"]]).numpy(), gold["wsj_sim"])
+    assert np.array_equal(M.get_similarity_weight_ami([str(u) for u in gold["ami_utt"]]).numpy(), gold["ami_sim"])
+    big = synth.make_utt_ids(64)
+    assert torch.equal(M.get_similarity_weight(big), port.similarity_weight(big))
+    assert torch.equal(M.get_speaker_labels(big), port.speaker_labels(big))
+
+
+def test_add_sos_eos_matches_espnet_restatement():
+    from robustsq_whisper_b200.ts_qformer_espnet_model import add_sos_eos
+    g = torch.Generator().manual_seed(0)
+    ys = torch.randint(0, 100, (5, 9), generator=g)
+    ys[1, 6:] = -1
+    ys[3, 2:] = -1
+    a_in, a_out = add_sos_eos(ys, 777, 778, -1)
+    b_in, b_out = upstream.add_sos_eos(ys, 777, 778, -1)
+    assert torch.equal(a_in, b_in) and torch.equal(a_out, b_out)
+
+
+def test_batched_multinomial_equals_per_row_loop():
+    """The reference draws negatives row by row (ts_qformer_espnet_model.py:693-697); one batched CPU call consumes the
+    generator identically."""
+    utt = synth.make_utt_ids(16)
+    negw = port.negative_weight(port.similarity_weight(utt))
+    torch.manual_seed(7)
+    loop = port.sample_negatives(negw, 20)
+    torch.manual_seed(7)
+    batched = torch.multinomial(negw, 20, replacement=True)
+    assert torch.equal(loop, batched)
+    for b in range(16):  # no same-speaker negatives
+        assert all(negw[b, j] > 0 for j in loop[b].tolist())
+
+
+def _build(name="tiny", **kw):
+    from robustsq_whisper_b200.ts_qformer_espnet_model import TgtSpkQformerESPnetASRModel_V4
+    from robustsq_whisper_b200.whisper_decoder import QFormerTgtSpkWhisperDecoder_V2
+    from robustsq_whisper_b200.whisper_encoder import QFormerTgtSpkWhisperEncoder_V2
+    enc = QFormerTgtSpkWhisperEncoder_V2(whisper_model=name, num_query_tokens=16, num_hidden_layers=2)
+    dec = QFormerTgtSpkWhisperDecoder_V2(vocab_size=51865, encoder_output_size=enc.output_size(), whisper_model=name)
+    return TgtSpkQformerESPnetASRModel_V4(vocab_size=51865, token_list=[str(i) for i in range(51865)], frontend=None, specaug=None,
+                                          normalize=None, preencoder=None, encoder=enc, postencoder=None, decoder=dec, ctc=None,
+                                          joint_network=None, ctc_weight=0.0, lsm_weight=0.1, **kw)
+
+
+def test_state_dict_surface_matches_the_oracle_weights():
+    m = _build("tiny")
+    m.materialize_heads(device="cpu")
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    want = {k: tuple(v.shape) for k, v in port.init_state_dict(port.TSConfig(whisper_model="tiny")).items()}
+    assert set(want) <= set(mine), sorted(set(want) - set(mine))
+    assert all(".cls." in k for k in set(mine) - set(want)), sorted(set(mine) - set(want))
+    for k, shp in want.items():
+        assert mine[k] == shp, (k, mine[k], shp)
+    assert m.encoder.output_size() == 384 and m.sos == m.eos == 51864
+    # warm-ups (ts_qformer_espnet_model.py:738-750)
+    m.set_epoch(3)
+    assert m.get_current_asp_gamma() == pytest.approx(1.0 + 0.5 * 5.0)
+    m.set_epoch(9)
+    assert m.get_current_asp_gamma() == 6.0
+
+
+@pytest.mark.skipif(not harness.reference_available(), reason="reference checkout not present")
+def test_state_dict_keys_equal_the_reference_model():
+    ref = harness.build_reference_model("tiny", 16, 2)
+    ref.encoder.qformer.eval()
+    with torch.no_grad():
+        ref(**synth.make_batch(2, 1.0, 1.0, text_len=4))  # materialise the lazy heads
+    m = _build("tiny")
+    m.materialize_heads(device="cpu")
+    a = {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert a == b, (sorted(set(a) ^ set(b)))
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        _build("tiny", **{}).__class__(vocab_size=10, token_list=["a"], frontend=None, specaug=None, normalize=None, preencoder=None,
+                                       encoder=None, postencoder=None, decoder=None, ctc=None, joint_network=None, ctc_weight=0.3)
+    from robustsq_whisper_b200.whisper_encoder import QFormerTgtSpkWhisperEncoder_V2
+    with pytest.raises(NotImplementedError):
+        QFormerTgtSpkWhisperEncoder_V2(whisper_model="tiny", use_specaug=True)
+
+
+def _gloo_worker(rank, world, port_no, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port_no)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from robustsq_whisper_b200.parallel import GradientAllReducer, all_gather_with_grad
+    torch.manual_seed(rank)
+    x = torch.randn(3, 4, requires_grad=True)
+    pool = all_gather_with_grad(x)
+    w = torch.arange(world * 3 * 4, dtype=torch.float32).view(world * 3, 4)
+    (pool * w).sum().backward()
+    # every rank contributes the same w, so the reduce-scattered gradient is world * w[rank block]
+    ok_gather = pool.shape == (world * 3, 4) and torch.allclose(x.grad, world * w[rank * 3:(rank + 1) * 3])
+    p = torch.nn.Parameter(torch.zeros(5))
+    p.grad = torch.full((5,), float(rank + 1))
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    GradientAllReducer([p, frozen], bucket_bytes=8).reduce()
+    ok_reduce = torch.allclose(p.grad, torch.full((5,), sum(range(1, world + 1)) / world))
+    q.put((rank, bool(ok_gather), bool(ok_reduce)))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_helpers_world_size_2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True, True), (1, True, True)]

@@ -1,0 +1,153 @@
+"""GPU parity of the assembled TS-ASR path through the plugin classes: fp32 regime against the fixture the REAL
+reference produced (tests/golden/tiny_model.npz) and against the CPU port; bf16 regime within the 1e-2 relative
+budget of BASELINE.json's north_star."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import make_golden, port, synth  # noqa: E402
+
+
+def build_model(name, weight_seed=0, dtype=torch.float32, **kw):
+    from robustsq_whisper_b200.ts_qformer_espnet_model import TgtSpkQformerESPnetASRModel_V4
+    from robustsq_whisper_b200.whisper_decoder import QFormerTgtSpkWhisperDecoder_V2
+    from robustsq_whisper_b200.whisper_encoder import QFormerTgtSpkWhisperEncoder_V2
+    enc = QFormerTgtSpkWhisperEncoder_V2(whisper_model=name, num_query_tokens=16, num_hidden_layers=2)
+    dec = QFormerTgtSpkWhisperDecoder_V2(vocab_size=51865, encoder_output_size=enc.output_size(), whisper_model=name)
+    m = TgtSpkQformerESPnetASRModel_V4(vocab_size=51865, token_list=[str(i) for i in range(51865)], frontend=None, specaug=None,
+                                       normalize=None, preencoder=None, encoder=enc, postencoder=None, decoder=dec, ctc=None,
+                                       joint_network=None, ctc_weight=0.0, lsm_weight=0.1, **kw)
+    m.materialize_heads(device="cpu")
+    cfg = port.TSConfig(whisper_model=name, num_negatives=kw.get("num_negatives", 10))
+    sd = port.init_state_dict(cfg, weight_seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(".cls." in k for k in missing)
+    m = m.cuda()
+    m.encoder.compute_dtype = dtype
+    m.decoder.compute_dtype = dtype
+    return m, cfg, sd
+
+
+def to_cuda(batch):
+    return {k: (v.clone().cuda() if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def tiny_case():
+    c = make_golden.TINY_CASE
+    batch = synth.make_batch(c["batch"], c["mix_s"], c["enr_s"], text_len=c["text_len"], seed=c["seed"])
+    return c, batch
+
+
+def test_tiny_fp32_matches_reference_fixture(golden_dir, tiny_case):
+    c, batch = tiny_case
+    gold = np.load(os.path.join(golden_dir, "tiny_model.npz"))
+    m, cfg, sd = build_model("tiny", c["weight_seed"], torch.float32, num_negatives=c["num_negatives"])
+    m.set_epoch(c["epoch"])
+    torch.manual_seed(c["rng_seed"])
+    loss, stats, weight = m(**to_cuda(batch))
+    assert loss.shape == (1,) and int(weight.item()) == c["batch"]
+    assert loss.item() == pytest.approx(gold["loss"].item(), rel=1e-4)
+    for k in ("loss_con", "loss_aam", "loss_att", "acc", "acc_con", "acc_aam"):
+        assert stats[k].item() == pytest.approx(gold["stat_" + k].item(), rel=1e-4, abs=1e-6), k
+    loss.backward()
+    params = dict(m.named_parameters())
+    for k in make_golden.GRAD_KEYS:
+        got = make_golden.GRAD_SLICE(params[k].grad).cpu().numpy()
+        ref = gold["grad_" + k]
+        assert np.abs(got - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1e-6) + 1e-7, k
+        assert params[k].grad.norm().item() == pytest.approx(gold["gnorm_" + k].item(), rel=2e-3), k
+    # activations through the plugin surface
+    with torch.no_grad():
+        b = to_cuda(batch)
+        feats, _ = m.encoder.log_mel_spectrogram(b["speech"], b["speech_lengths"])
+        xs, olens, prompt, enr = m.encode(b["speech"], b["speech_lengths"], b["enroll"], b["enroll_lengths"])
+        assert np.array_equal(olens.cpu().numpy(), gold["enc_lens"])
+        from robustsq_whisper_b200.ts_qformer_espnet_model import add_sos_eos
+        ys_in, _ = add_sos_eos(b["text"], m.sos, m.eos, m.ignore_id)
+        logits, _ = m.decoder(xs, olens, ys_in, b["text_lengths"] + 1, prompt)
+        assert logits.dtype == torch.float32
+        named = dict(mel=feats, enc_out=xs, spk_prompt=prompt, enroll_emb=enr, dec_logits=logits)
+        for k, sl in make_golden.SLICES.items():
+            if k == "enroll_mel":
+                continue
+            got = named[k][sl].cpu().numpy()
+            ref = gold["act_" + k]
+            assert got.shape == ref.shape, k
+            tol = 1e-4 if k == "mel" else 5e-4
+            assert np.abs(got - ref).max() <= tol * max(1.0, np.abs(ref).max()), (k, np.abs(got - ref).max())
+        # greedy decode through batch_score: token ids identical in fp32
+        ys = torch.full((xs.size(0), 1), m.sos, dtype=torch.long, device="cuda")
+        for _ in range(6):
+            logp, _ = m.decoder.batch_score(ys, None, xs, prompt)
+            ys = torch.cat([ys, logp.argmax(-1, keepdim=True)], dim=1)
+        assert np.array_equal(ys[:, 1:].cpu().numpy(), gold["greedy_ids"])
+        assert np.abs(logp.max(-1)[0].cpu().numpy() - gold["greedy_last_logp_max"]).max() < 1e-3
+
+
+def test_tiny_bf16_within_budget(golden_dir, tiny_case):
+    c, batch = tiny_case
+    gold = np.load(os.path.join(golden_dir, "tiny_model.npz"))
+    m, cfg, sd = build_model("tiny", c["weight_seed"], torch.bfloat16, num_negatives=c["num_negatives"])
+    m.set_epoch(c["epoch"])
+    torch.manual_seed(c["rng_seed"])
+    loss, stats, weight = m(**to_cuda(batch))
+    for k in ("loss_con", "loss_aam", "loss_att", "loss"):
+        assert stats[k].item() == pytest.approx(gold["stat_" + k].item(), rel=1e-2), k
+    loss.backward()
+    params = dict(m.named_parameters())
+    worst = 0.0
+    for k in make_golden.GRAD_KEYS:
+        g = params[k].grad
+        assert g is not None and torch.isfinite(g).all(), k
+        worst = max(worst, abs(g.norm().item() / gold["gnorm_" + k].item() - 1.0))
+    assert worst < 5e-2, worst  # gradient norms: bf16 rounding accumulates over the backward chain
+    with torch.no_grad():
+        b = to_cuda(batch)
+        xs, olens, prompt, enr = m.encode(b["speech"], b["speech_lengths"], b["enroll"], b["enroll_lengths"])
+        named = dict(enc_out=xs, spk_prompt=prompt, enroll_emb=enr)
+        for k in named:
+            got = named[k][make_golden.SLICES[k]].float().cpu().numpy()
+            ref = gold["act_" + k]
+            assert np.abs(got - ref).max() <= 2e-2 * np.abs(ref).max(), (k, np.abs(got - ref).max(), np.abs(ref).max())
+
+
+def test_cfg1_tiny_forward_fp32_vs_port():
+    """BASELINE.json configs[0]: Whisper-tiny TS-ASR forward, batch 4 x 10 s + 3 s enrollment, fp32."""
+    batch = synth.make_batch(4, 10.0, 3.0)
+    m, cfg, sd = build_model("tiny", 0, torch.float32)
+    with torch.no_grad():
+        ref = port.encoder_forward(sd, cfg, batch["speech"], batch["speech_lengths"], batch["enroll"], batch["enroll_lengths"])
+        b = to_cuda(batch)
+        got = m.encode(b["speech"], b["speech_lengths"], b["enroll"], b["enroll_lengths"])
+    assert got[0].shape == (4, 516, 384) and got[2].shape == (4, 16, 384) and got[3].shape == (4, 150, 384)
+    assert torch.equal(got[1].cpu(), ref[1])
+    for g, r, n in zip((got[0], got[2], got[3]), (ref[0], ref[2], ref[3]), ("enc", "prompt", "enroll")):
+        assert rel(g, r) < 5e-4, (n, rel(g, r))
+
+
+def test_base_bf16_training_step_runs_and_matches_port_losses():
+    """BASELINE.json configs[1] shape family at a size the CPU oracle finishes in seconds: Whisper-base, bf16."""
+    batch = synth.make_batch(4, 6.0, 3.0, text_len=18)
+    m, cfg, sd = build_model("base", 0, torch.bfloat16, num_negatives=10)
+    m.set_epoch(6)
+    torch.manual_seed(7)
+    neg_idx = torch.multinomial(port.negative_weight(port.similarity_weight(batch["utt_id"])), 10, replacement=True)
+    with torch.no_grad():
+        rl, rs, _ = port.model_forward(sd, cfg, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}, epoch=6, neg_idx=neg_idx)
+    loss, stats, _ = m(**to_cuda(batch), neg_idx=neg_idx)
+    loss.backward()
+    for k in ("loss_con", "loss_aam", "loss_att", "loss"):
+        assert stats[k].item() == pytest.approx(float(rs[k]), rel=1e-2), k
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    n_with_grad = sum(p.grad is not None for p in m.parameters())
+    assert n_with_grad == sum(p.requires_grad for p in m.parameters()) - 0
