@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's headline metric on the B200-native TS-ASR hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...            # the reference algorithm on the box's host cores (oracle port)
+
+A "step" = one Whisper-medium TS-ASR training step (fwd + bwd; 30 s mixture + 10 s enrollment per utterance, bf16,
+SQ-Former q=16 / 2 layers, ASP + AAM-Softmax + Arc-InfoNCE (K=20) + label-smoothed attention loss) over one synthetic
+batch; at N > 1 every rank takes its own batch (weak scaling), Arc-InfoNCE negatives are all-gathered and gradients are
+all-reduced inside the timed region.  metric = mixture audio-seconds processed per wall-second, whole job.
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how each field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/sec, Whisper-medium TS fwd+bwd"
+UNIT = "audio-s/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="medium")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSW_BENCH_BATCH", "32")), help="utterances per GPU per step")
+    ap.add_argument("--mix-s", type=float, default=30.0)
+    ap.add_argument("--enr-s", type=float, default=10.0)
+    ap.add_argument("--negatives", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=1)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference algorithm on the host CPU (oracle/port.py, validated against the reference's own Python and the
+    committed fixtures).  /root/reference is not on the GPU box, so kind = "port".  Each step = fwd + bwd of a bounded
+    sample (cpu_batch utterances) of the workload, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import port, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = port.TSConfig(whisper_model=args.model, num_negatives=args.negatives)
+    sd = {k: v.requires_grad_(v.is_floating_point() and "position" not in k) for k, v in port.init_state_dict(cfg, 0).items()}
+    batch = synth.make_batch(args.cpu_batch, args.mix_s, args.enr_s, ragged=False)
+    neg_idx = torch.zeros(args.cpu_batch, args.negatives, dtype=torch.long)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        loss, _, _ = port.model_forward(sd, cfg, batch, epoch=6, neg_idx=neg_idx)
+        loss.backward()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = args.cpu_batch * args.mix_s / dt
+    sample = f"{args.cpu_batch} x ({args.mix_s:g} s + {args.enr_s:g} s) utterances per step, fwd+bwd, fp32, torch CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"whisper-{args.model} TS-ASR fwd+bwd, {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment", "batch_per_step": args.cpu_batch},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------- CUDA arm
+def cpu_baseline(args):
+    """Oracle port timed on this box's host cores on a bounded sample: 1 fwd+bwd step of cpu_batch utterances."""
+    import torch
+    from oracle import port, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = port.TSConfig(whisper_model=args.model, num_negatives=args.negatives)
+    sd = {k: v.requires_grad_(v.is_floating_point() and "position" not in k) for k, v in port.init_state_dict(cfg, 0).items()}
+    batch = synth.make_batch(args.cpu_batch, args.mix_s, args.enr_s, ragged=False)
+    neg_idx = torch.zeros(args.cpu_batch, args.negatives, dtype=torch.long)
+    t0 = time.perf_counter()
+    loss, _, _ = port.model_forward(sd, cfg, batch, epoch=6, neg_idx=neg_idx)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return {"value": args.cpu_batch * args.mix_s / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 un-warmed fwd+bwd step of {args.cpu_batch} x ({args.mix_s:g}+{args.enr_s:g}) s, fp32 torch CPU port of the reference, {dt:.1f} s"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import synth  # synthetic batch generator only (test infrastructure shared with the parity tests)
+    from robustsq_whisper_b200 import kernels as K
+    from robustsq_whisper_b200.factory import build_ts_model
+    from robustsq_whisper_b200.parallel import GradientAllReducer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    torch.manual_seed(0)
+    model = build_ts_model(args.model, 16, 2, num_negatives=args.negatives, gather_negatives=world > 1).to(dev)
+    model.encoder.compute_dtype = torch.bfloat16
+    model.decoder.compute_dtype = torch.bfloat16
+    model.materialize_heads()
+    model.set_epoch(6)
+    reducer = GradientAllReducer(model.parameters())
+
+    B = args.batch
+    batch = synth.make_batch(B, args.mix_s, args.enr_s, seed=1234 + rank, utt_offset=rank * B)
+    pinned = {k: v.pin_memory() for k, v in batch.items() if torch.is_tensor(v)}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    torch.manual_seed(7 + rank)
+    K_neg = args.negatives
+
+    def make_negatives():
+        P = B * world
+        # global pool: exclude same-speaker items; utt ids cycle through 8 speakers identically on every rank
+        ids = []
+        for r in range(world):
+            ids += synth.make_utt_ids(B, r * B)
+        from robustsq_whisper_b200.ts_qformer_espnet_model import get_similarity_weight
+        sim = get_similarity_weight(ids)[rank * B:(rank + 1) * B]
+        w = torch.softmax(torch.ones_like(sim).masked_fill_(sim == 1, -10000), dim=1)
+        return torch.multinomial(w, K_neg, replacement=True)
+
+    def step(inputs):
+        for p in model.parameters():
+            p.grad = None
+        loss, stats, weight = model(**inputs, utt_id=batch["utt_id"], neg_idx=make_negatives())
+        loss.backward()
+        reducer.reduce()
+        return loss
+
+    def resident_inputs():
+        return {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- warm-up
+    res = resident_inputs()
+    for _ in range(max(args.warmup, 3)):
+        step({k: v.clone() for k, v in res.items()})
+    sync_all()
+
+    # ---------------- timed region 1: inputs resident in HBM (value), GEMM launches timed with CUDA events
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.GEMM_PROFILE = []
+    K.LAUNCHES["n"] = 0
+    staged = [{k: v.clone() for k, v in res.items()} for _ in range(args.steps)]
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(staged[i])
+    e1.record()
+    sync_all()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    launches = K.LAUNCHES["n"] // max(args.steps, 1)
+    prof = K.GEMM_PROFILE
+    K.GEMM_PROFILE = None
+    tc = [(a.elapsed_time(b), f) for a, b, f, impl, *_ in prof if impl == "tcgen05"]
+    tc_ms = sum(t for t, _ in tc)
+    tc_flops = sum(f for _, f in tc)
+    gemm_share = tc_ms / (ms_dev * args.steps) if tc else 0.0
+
+    # ---------------- timed region 2: end to end through the public API with host buffers (e2e)
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    last = None
+    for i in range(args.steps):
+        loss = step(resident_inputs())
+        last = loss.detach().float().cpu()  # device -> host read of the step's result
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    audio_s = B * world * args.mix_s
+    value = audio_s / (ms_dev * 1e-3)
+    e2e_value = audio_s / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        print(f"[bench] peak HBM allocated {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB; tcgen05 GEMM {tc_ms / args.steps:.1f} ms of {ms_dev:.1f} ms/step", file=sys.stderr)
+        pk = peaks()
+        achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"whisper-{args.model} TS-ASR training step (fwd+bwd), {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment, "
+                                   f"q=16, SQ-Former L=2, K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2_policy": "per-step inputs and activations (>10 GB) exceed the 126 MB L2; fresh input copies each step",
+                       "loss_last": None if last is None else float(last)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM, all launches of the timed steps)", "bound": "tensor",
+                         "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None, "traffic": None,
+                         "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                         "launches_timed": len(tc), "share_of_step": gemm_share},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(args)
+            except Exception as ex:  # pragma: no cover
+                out["cpu_baseline"] = {"error": repr(ex)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

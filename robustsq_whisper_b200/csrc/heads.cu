@@ -555,6 +555,7 @@ lsce_kernel(const T* __restrict__ logits, int64_t V, int64_t ld, const int64_t* 
     if (g) for (int64_t j = tid; j < ld_dl; j += blockDim.x) g[j] = from_f32<GT>(0.f);
     return;
   }
+  const float ly = to_f32(l[y]);  // read before the in-place gradient write (dl may alias logits)
   // online max / sum-exp and the plain sum of logits in one pass
   float m = -INFINITY, z = 0.f, sl = 0.f;
   for (int64_t j = tid; j < V; j += blockDim.x) {
@@ -577,7 +578,6 @@ lsce_kernel(const T* __restrict__ logits, int64_t V, int64_t ld, const int64_t* 
   if (g) for (int64_t j = V + tid; j < ld_dl; j += blockDim.x) g[j] = from_f32<GT>(0.f);
   __syncthreads();
   if (tid == 0) {
-    const float ly = to_f32(l[y]);
     // KL(t || softmax) = sum_j t_j (log t_j - logp_j), xlogy(0, .) = 0
     float kl = (conf > 0.f ? conf * logf(conf) : 0.f) - conf * (ly - lse);
     if (low > 0.f) kl += (float)(V - 1) * low * logf(low) - low * ((sl - ly) - (float)(V - 1) * lse);

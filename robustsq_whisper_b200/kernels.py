@@ -17,6 +17,14 @@ from ._C import BF16, F32, GemmDesc, check, dtype_code, ptr, require_cuda, strea
 
 _logmel_ready = set()
 
+# launch accounting (bench.py's "gpu_launches") and optional per-launch CUDA-event timing of the GEMM kernels
+LAUNCHES = {"n": 0}
+GEMM_PROFILE = None  # when a list: (start_event, end_event, flops, impl, M, N, K, batches) appended per tsw_gemm call
+
+
+def _count(n: int = 1) -> None:
+    LAUNCHES["n"] += n
+
 
 def _ws(nbytes: int, device) -> Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
@@ -69,6 +77,7 @@ def logmel(audio: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
     code = dtype_code(out_dtype)
     ws = _ws(lib.tsw_logmel_workspace_bytes(B, N, code), audio.device)
     check(lib.tsw_logmel_fwd(ptr(audio), B, N, audio.stride(0), ptr(out), code, ptr(ws), ws.numel(), stream()), "tsw_logmel_fwd")
+    _count(2)
     return out
 
 
@@ -120,7 +129,16 @@ def gemm(
     if alpha_dev is not None and (alpha_dev.dtype != torch.float32 or not alpha_dev.is_cuda):
         raise _C.TswError("gemm: alpha_dev must be a float32 cuda scalar")
     g.alpha_dev = ptr(alpha_dev)
-    check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
+    if GEMM_PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
+        e1.record()
+        tc = impl != _C.GEMM_SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K * bo * bi, "tcgen05" if tc else "simt", M, N, K, bo * bi))
+    else:
+        check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
+    _count(1)
     return out
 
 
@@ -139,6 +157,7 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optio
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     check(lib.tsw_layernorm_fwd(ptr(x), ptr(res), ptr(gamma), ptr(beta), ptr(y), ptr(sum_out), ptr(mean), ptr(rstd), rows, d,
                                 eps, dtype_code(x.dtype), stream()), "tsw_layernorm_fwd")
+    _count(1)
     return y, sum_out, mean, rstd
 
 
@@ -153,6 +172,7 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
     ws = _ws(lib.tsw_layernorm_bwd_workspace_bytes(rows, d), x.device)
     check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
                                 dtype_code(x.dtype), ptr(ws), ws.numel(), stream()), "tsw_layernorm_bwd")
+    _count(2)
     return dx, dgamma, dbeta
 
 
@@ -164,6 +184,7 @@ def cast(x: Tensor, dtype: torch.dtype, out: Optional[Tensor] = None) -> Tensor:
     if out is None:
         out = torch.empty(x.shape, dtype=dtype, device=x.device)
     check(lib.tsw_cast(ptr(x), dtype_code(x.dtype), ptr(out), dtype_code(dtype), x.numel(), stream()), "tsw_cast")
+    _count(1)
     return out
 
 
@@ -172,6 +193,7 @@ def colsum(x: Tensor, rows: int, n: int, ld: Optional[int] = None) -> Tensor:
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     ws = _ws(lib.tsw_colsum_workspace_bytes(rows, n), x.device)
     check(lib.tsw_colsum(ptr(x), dtype_code(x.dtype), rows, n, ld if ld is not None else n, ptr(out), ptr(ws), ws.numel(), stream()), "tsw_colsum")
+    _count(2)
     return out
 
 
@@ -183,6 +205,7 @@ def scale(x: Tensor, s_host: float = 1.0, s_dev: Optional[Tensor] = None, inplac
     if s_dev is not None:
         s_dev = s_dev.reshape(-1)[:1].float().contiguous()
     check(lib.tsw_scale(ptr(x), ptr(y), dtype_code(x.dtype), x.numel(), s_host, ptr(s_dev), stream()), "tsw_scale")
+    _count(1)
     return y
 
 
@@ -193,6 +216,7 @@ def add(a: Tensor, b: Tensor, out: Optional[Tensor] = None) -> Tensor:
     if out is None:
         out = torch.empty_like(a)
     check(lib.tsw_add(ptr(a), ptr(b), ptr(out), dtype_code(a.dtype), a.numel(), stream()), "tsw_add")
+    _count(1)
     return out
 
 
@@ -201,6 +225,7 @@ def gelu_fwd(x: Tensor) -> Tensor:
     x = x.contiguous()
     y = torch.empty_like(x)
     check(lib.tsw_gelu_fwd(ptr(x), ptr(y), dtype_code(x.dtype), x.numel(), stream()), "tsw_gelu_fwd")
+    _count(1)
     return y
 
 
@@ -209,6 +234,7 @@ def gelu_bwd(x: Tensor, dy: Tensor) -> Tensor:
     x, dy = x.contiguous(), dy.contiguous()
     dx = torch.empty_like(x)
     check(lib.tsw_gelu_bwd(ptr(x), ptr(dy), ptr(dx), dtype_code(x.dtype), x.numel(), stream()), "tsw_gelu_bwd")
+    _count(1)
     return dx
 
 
@@ -223,6 +249,7 @@ def im2col_k3(x: Tensor, channels_first: bool, stride: int) -> Tensor:
     To = (T + 2 - 3) // stride + 1
     out = torch.empty((B * To, 3 * C), dtype=x.dtype, device=x.device)
     check(lib.tsw_im2col_k3(ptr(x), dtype_code(x.dtype), int(channels_first), B, C, T, stride, ptr(out), stream()), "tsw_im2col_k3")
+    _count(1)
     return out
 
 
@@ -231,6 +258,7 @@ def col2im_k3(dcol: Tensor, B: int, C: int, T: int, stride: int) -> Tensor:
     dcol = dcol.contiguous()
     din = torch.empty((B, T, C), dtype=dcol.dtype, device=dcol.device)
     check(lib.tsw_col2im_k3(ptr(dcol), dtype_code(dcol.dtype), B, C, T, stride, ptr(din), stream()), "tsw_col2im_k3")
+    _count(1)
     return din
 
 
@@ -240,12 +268,14 @@ def softmax_fwd(s: Tensor, batch: int, heads: int, sq: int, sk: int, scale: floa
     p = s if inplace else torch.empty_like(s)
     check(lib.tsw_softmax_fwd(ptr(s), ptr(p), dtype_code(s.dtype), batch, heads, sq, sk, ld if ld is not None else sk, scale,
                               ptr(key_len), causal, stream()), "tsw_softmax_fwd")
+    _count(1)
     return p
 
 
 def softmax_bwd(p: Tensor, dp: Tensor, rows: int, sk: int, scale: float, ld: Optional[int] = None) -> Tensor:
     lib = _C.load()
     check(lib.tsw_softmax_bwd(ptr(p), ptr(dp), ptr(dp), dtype_code(p.dtype), rows, sk, ld if ld is not None else sk, scale, stream()), "tsw_softmax_bwd")
+    _count(1)
     return dp
 
 
@@ -258,6 +288,7 @@ def decoder_embed(E: Tensor, pos: Tensor, prompt: Tensor, ids: Tensor, sop: int,
     out = torch.empty((B, 1 + q + n_tok, d), dtype=dtype, device=E.device)
     check(lib.tsw_decoder_embed(ptr(E), ptr(pos), ptr(prompt), dtype_code(prompt.dtype), ptr(ids), B, n_tok, q, d, sop, ptr(out),
                                 dtype_code(dtype), stream()), "tsw_decoder_embed")
+    _count(1)
     return out
 
 
@@ -271,6 +302,7 @@ def decoder_embed_bwd(dout: Tensor, ids: Tensor, q: int, sop: int, vocab: int, n
     dprompt = torch.empty((B, q, d), dtype=dout.dtype, device=dout.device)
     check(lib.tsw_decoder_embed_bwd(ptr(dout), dtype_code(dout.dtype), ptr(ids), B, n_tok, q, d, sop, ptr(dE), ptr(dpos), ptr(dprompt),
                                     dtype_code(dout.dtype), stream()), "tsw_decoder_embed_bwd")
+    _count(1)
     return dE, dpos, dprompt
 
 
@@ -283,6 +315,7 @@ def asp_pool_fwd(x: Tensor, gamma: float):
     f32 = dict(dtype=torch.float32, device=x.device)
     ms, ptil, var, saved = torch.empty((B, 2 * d), **f32), torch.empty((B, d), **f32), torch.empty((B, d), **f32), torch.empty((B, 4), **f32)
     check(lib.tsw_asp_pool_fwd(ptr(x), dtype_code(x.dtype), B, T, d, gamma, ptr(ms), ptr(ptil), ptr(var), ptr(saved), stream()), "tsw_asp_pool_fwd")
+    _count(1)
     return ms, ptil, var, saved
 
 
@@ -292,6 +325,7 @@ def asp_pool_bwd(x: Tensor, gamma: float, ms: Tensor, ptil: Tensor, var: Tensor,
     gx = torch.empty_like(x)
     g_ms = g_ms.contiguous().float()
     check(lib.tsw_asp_pool_bwd(ptr(x), dtype_code(x.dtype), B, T, d, gamma, ptr(ms), ptr(ptil), ptr(var), ptr(saved), ptr(g_ms), ptr(gx), stream()), "tsw_asp_pool_bwd")
+    _count(1)
     return gx
 
 
@@ -302,6 +336,7 @@ def l2norm_fwd(x: Tensor, eps: float):
     y = torch.empty_like(x)
     norm = torch.empty(rows, dtype=torch.float32, device=x.device)
     check(lib.tsw_l2norm_fwd(ptr(x), ptr(y), ptr(norm), rows, d, eps, stream()), "tsw_l2norm_fwd")
+    _count(1)
     return y, norm
 
 
@@ -311,6 +346,7 @@ def l2norm_bwd(y: Tensor, norm: Tensor, gy: Tensor, eps: float) -> Tensor:
     rows, d = y.shape
     gx = torch.empty_like(y)
     check(lib.tsw_l2norm_bwd(ptr(y), ptr(norm), ptr(gy), ptr(gx), rows, d, eps, stream()), "tsw_l2norm_bwd")
+    _count(1)
     return gx
 
 
@@ -328,6 +364,7 @@ def aam_softmax_fwd_bwd(f: Tensor, w: Tensor, labels: Tensor, margin: float, tem
     ws = _ws(lib.tsw_aam_workspace_bytes(B, C, d), f.device)
     check(lib.tsw_aam_softmax_fwd_bwd(ptr(f), ptr(w), ptr(labels), B, C, d, margin, temp, ptr(loss), ptr(nc), ptr(gf), ptr(gw),
                                       ptr(ws), ws.numel(), stream()), "tsw_aam_softmax_fwd_bwd")
+    _count(6)
     return loss, nc, gf, gw
 
 
@@ -346,6 +383,7 @@ def arc_infonce_fwd_bwd(prompt: Tensor, z: Tensor, pos_index: Tensor, neg_idx: T
     ws = _ws(lib.tsw_infonce_workspace_bytes(B, K, d), z.device)
     check(lib.tsw_arc_infonce_fwd_bwd(ptr(prompt), dtype_code(prompt.dtype), B, q, d, ptr(z), P, ptr(pos_index), ptr(neg_idx), K, margin,
                                       temp, ptr(loss), ptr(nc), ptr(gprompt), ptr(gz), ptr(ws), ws.numel(), stream()), "tsw_arc_infonce_fwd_bwd")
+    _count(1)
     return loss, nc, gprompt, gz
 
 
@@ -359,6 +397,7 @@ def lsce_fwd_bwd(logits: Tensor, rows: int, V: int, ld: int, targets: Tensor, ig
     check(lib.tsw_lsce_fwd_bwd(ptr(logits), dtype_code(logits.dtype), rows, V, ld, ptr(targets), ignore_id, smoothing, grad_scale,
                                ptr(loss), ptr(counts), ptr(dlogits), dtype_code(dlogits.dtype) if dlogits is not None else 0, ld_dl,
                                stream()), "tsw_lsce_fwd_bwd")
+    _count(1)
     return loss, counts
 
 
@@ -366,4 +405,5 @@ def log_softmax(logits: Tensor, rows: int, V: int, ld: int) -> Tensor:
     lib = _C.load()
     out = torch.empty((rows, V), dtype=torch.float32, device=logits.device)
     check(lib.tsw_log_softmax(ptr(logits), dtype_code(logits.dtype), rows, V, ld, ptr(out), stream()), "tsw_log_softmax")
+    _count(1)
     return out
