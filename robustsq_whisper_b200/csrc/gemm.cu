@@ -34,6 +34,13 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   ep.vec_ok = ok(g.D, g.ldd, g.d_stride_outer, g.d_stride_inner) && ok(g.aux_in, g.ldd, 0, 0) && ok(g.aux_out, g.ldd, 0, 0) &&
               ok(g.residual, g.ldres, g.res_stride_outer, g.res_stride_inner) && (!g.bias || aligned16(g.bias));
 
+  auto ok4 = [&](const void* p, int64_t ld, int64_t so, int64_t si) {
+    const uintptr_t al = g.d_dtype == TSW_F32 ? 15u : 7u;
+    return !p || ((reinterpret_cast<uintptr_t>(p) & al) == 0 && ld % 4 == 0 && so % 4 == 0 && si % 4 == 0);
+  };
+  ep.vec4_ok = ok4(g.D, g.ldd, g.d_stride_outer, g.d_stride_inner) && ok4(g.aux_in, g.ldd, 0, 0) && ok4(g.aux_out, g.ldd, 0, 0) &&
+               ok4(g.residual, g.ldres, g.res_stride_outer, g.res_stride_inner) && (!g.bias || aligned16(g.bias));
+
   cudaStream_t st = as_stream(stream);
   if (g.impl == TSW_GEMM_SIMT) return gemm_simt_launch(g, ep, st);
   if (g.impl == TSW_GEMM_TCGEN05) return gemm_tc_launch(g, ep, st);

@@ -22,7 +22,8 @@ namespace tsw {
 
 constexpr int TBM = 128;       // tile rows  (UMMA M, cta_group::1)
 constexpr int TBK = 64;        // K per stage = one 128-byte swizzle row of bf16
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue (two per TMEM lane quarter)
+constexpr int TC_EPI_WARPS = 8;
 constexpr uint32_t kPanelBytes = 64 * 128;  // one MN-major panel: 64 K-rows x 128 B
 
 struct TcParams {
@@ -31,7 +32,9 @@ struct TcParams {
   int a_mn, b_mn;
   int64_t d_so, d_si, r_so, r_si;
   int tiles_m, tiles_n;
-  int64_t total_tiles;
+  int64_t total_tiles;   // output tiles
+  int splits, kb_per_split;  // split-K: work item = (tile, split); partial sums are atomically added into fp32 D
+  int64_t total_work;    // total_tiles * splits
 };
 
 // ----------------------------------------------------------------------------------------------- PTX wrappers
@@ -116,6 +119,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+template <typename T> struct RawVec;
+template <> struct RawVec<float> {
+  using type = float4;
+  __device__ static float4 ldg(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static void unpack(const float4& r, float* o) { o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w; }
+};
+template <> struct RawVec<__nv_bfloat16> {
+  using type = uint2;
+  __device__ static uint2 ldg(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ static uint2 ld(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  __device__ static void unpack(const uint2& r, float* o) {
+    uint2 t = r;
+    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&t.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+};
+
 // shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version 1); offsets in bytes
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -144,10 +165,11 @@ struct TcSmem {
   static constexpr uint32_t kABytes = TBM * TBK * 2;
   static constexpr uint32_t kBBytes = BN * TBK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256;
+  static constexpr uint32_t kStgFloats = 32 * 32;  // per-epilogue-warp transpose staging: 32 rows x 32 fp32, XOR-swizzled 16-byte units
+  static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256 + TC_EPI_WARPS * kStgFloats * 4;
 };
 
-template <int BN, int STAGES, typename DT>
+template <int BN, int STAGES, typename DT, bool GENERIC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p, const EpiParams ep) {
   using S = TcSmem<BN, STAGES>;
@@ -160,6 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stg_base = reinterpret_cast<float*>(smem + (size_t)STAGES * S::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
@@ -167,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -183,13 +206,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int64_t t = w / p.splits;
+        const int sp = (int)(w - t * p.splits);
+        const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int bt = (int)(t / tiles_per_batch);
         const int64_t r = t - (int64_t)bt * tiles_per_batch;
         const int mt = (int)(r / p.tiles_n), nt = (int)(r - (int64_t)mt * p.tiles_n);
         const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
         const int m0 = mt * TBM, n0 = nt * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = tiles + (size_t)stage * S::kStageBytes;
           unsigned char* sb = sa + S::kABytes;
@@ -219,11 +245,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;  // bytes per UMMA_K = 16
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+        const int sp = (int)(w % p.splits);
+        const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * S::kStageBytes);
@@ -232,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < TBK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -243,24 +271,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (TMEM -> registers -> global)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's 32-column chunks this warp drains
+    float* stg = stg_base + (warp - 4) * S::kStgFloats;
+    const float alpha = ep.alpha_dev ? ep.alpha * __ldg(ep.alpha_dev) : ep.alpha;
+    const int u = lane & 7, rsub = lane >> 3;  // phase 2: 8 lanes x 4 columns cover a 32-column row segment, 4 rows / instruction
+    DT* const Dp = reinterpret_cast<DT*>(ep.D);
+    const DT* const Rp = reinterpret_cast<const DT*>(ep.residual);
+    const DT* const AIp = reinterpret_cast<const DT*>(ep.aux_in);
+    DT* const AOp = reinterpret_cast<DT*>(ep.aux_out);
+    const int64_t row4 = 4 * ep.ldd;
     int as = 0; uint32_t aphase = 0;
-    for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      const int64_t t = w / p.splits;
+      const bool first_split = (w - t * p.splits) == 0;
       const int bt = (int)(t / tiles_per_batch);
       const int64_t r = t - (int64_t)bt * tiles_per_batch;
       const int mt = (int)(r / p.tiles_n), nt = (int)(r - (int64_t)mt * p.tiles_n);
       const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
       const int64_t d_off = bo * p.d_so + bi * p.d_si, r_off = bo * p.r_so + bi * p.r_si;
-      const int64_t m = (int64_t)mt * TBM + q * 32 + lane;
-      const int64_t n0 = (int64_t)nt * BN;
+      const int64_t m_first = (int64_t)mt * TBM + q * 32 + rsub;  // this lane's rows: m_first + 4 i, i < 8
+      const int n_first = nt * BN + u * 4;                        // + c per chunk
+      const int64_t off0 = d_off + m_first * ep.ldd + n_first;
+      int rows_ok = 0;                                            // how many of the lane's 8 rows are inside M
+      if (m_first < p.M) rows_ok = (int)min((int64_t)8, (p.M - m_first + 3) / 4);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = half * 32; c < BN; c += 64) {
+        if (nt * BN + c >= p.N) break;  // warp-uniform
         float v[32];
-        tmem_ld32(taddr + c, v);  // warp-collective: executed by all lanes even for rows/columns out of range
-        if (n0 + c < p.N) epi_store<DT, 32>(ep, v, m, n0 + c, d_off, r_off);
+        tmem_ld32(taddr + c, v);        // lane = tile row, 32 consecutive columns
+        // transpose through shared memory so global accesses run along rows; 16-byte unit j of row r lives at unit
+        // j ^ (r & 7), which keeps both the row-wise writes and the 8-lanes-per-row reads bank-conflict free
+        float4* dst = reinterpret_cast<float4*>(stg + lane * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j ^ (lane & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int n = n_first + c;
+        const bool vec = ep.vec4_ok && (n + 4 <= p.N);
+        if (vec) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ep.bias && first_split) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
+          int64_t off = off0 + c;
+          int64_t roff = 0;
+          if (GENERIC && Rp) roff = r_off + (ep.res_row_mod > 0 ? (m_first % ep.res_row_mod) : m_first) * ep.ldres + n;
+          // The extra operand of the fused epilogue (residual | GELU' input | old D) is fetched for all 8 rows up front
+          // as raw 8/16-byte words through the read-only path, so the loads overlap instead of queueing behind stores.
+          typename RawVec<DT>::type pre[8];
+          const int which = !GENERIC ? 0 : Rp ? 1 : (ep.epilogue == TSW_EPI_MUL_DGELU) ? 2 : (ep.beta != 0.f) ? 3 : 0;
+          if (GENERIC && which != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < rows_ok) {
+                const DT* src;
+                if (which == 1) src = (ep.res_row_mod > 0) ? Rp + r_off + ((m_first + 4 * i) % ep.res_row_mod) * ep.ldres + n
+                                                           : Rp + roff + (int64_t)i * 4 * ep.ldres;
+                else src = (which == 2 ? AIp : Dp) + off + (int64_t)i * row4;
+                pre[i] = which == 3 ? RawVec<DT>::ld(src) : RawVec<DT>::ldg(src);  // D itself is written below: no read-only path
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (i < rows_ok) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * 32 + ((u ^ ((i * 4 + rsub) & 7)) * 4));
+              float o[4] = {fmaf(alpha, a.x, b4.x), fmaf(alpha, a.y, b4.y), fmaf(alpha, a.z, b4.z), fmaf(alpha, a.w, b4.w)};
+              if (GENERIC) {
+                float ex[4] = {0.f, 0.f, 0.f, 0.f};
+                if (which != 0) RawVec<DT>::unpack(pre[i], ex);
+                if (AOp) store4(AOp + off, o);
+                if (ep.epilogue == TSW_EPI_GELU) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) o[j] = gelu_fast(o[j]);
+                } else if (ep.epilogue == TSW_EPI_MUL_DGELU) {
+                  float ai[4];
+                  if (which == 2) { ai[0] = ex[0]; ai[1] = ex[1]; ai[2] = ex[2]; ai[3] = ex[3]; } else load4(AIp + off, ai);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) o[j] *= dgelu_fast(ai[j]);
+                }
+                if (which == 1) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) o[j] += ex[j];
+                }
+                if (ep.beta != 0.f) {
+                  float od[4];
+                  if (which == 3) { od[0] = ex[0]; od[1] = ex[1]; od[2] = ex[2]; od[3] = ex[3]; } else load4(Dp + off, od);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) o[j] += ep.beta * od[j];
+                }
+              }
+              if constexpr (sizeof(DT) == 4) {
+                if (p.splits > 1) atomicAdd(reinterpret_cast<float4*>(Dp + off), make_float4(o[0], o[1], o[2], o[3]));
+                else store4(Dp + off, o);
+              } else {
+                store4(Dp + off, o);
+              }
+              off += row4;
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < rows_ok; ++i) {
+            const float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * 32 + ((u ^ ((i * 4 + rsub) & 7)) * 4));
+            epi_store4<DT>(ep, a, m_first + 4 * i, n, d_off, r_off, alpha);
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -323,7 +441,7 @@ bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
   return true;
 }
 
-template <int BN, int STAGES, typename DT>
+template <int BN, int STAGES, typename DT, bool GENERIC>
 static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
   CUtensorMap tmA, tmB;
@@ -338,13 +456,25 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   p.d_so = g.d_stride_outer; p.d_si = g.d_stride_inner; p.r_so = g.res_stride_outer; p.r_si = g.res_stride_inner;
   p.tiles_m = (int)((g.M + TBM - 1) / TBM); p.tiles_n = (int)((g.N + BN - 1) / BN);
   p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * p.batches;
-  auto kern = gemm_tc_kernel<BN, STAGES, DT>;
+  const int num_kb = (int)((g.K + TBK - 1) / TBK);
+  p.splits = 1;
+  // split-K when the output has too few tiles to occupy the machine (weight gradients: M, N ~ 1e3, K ~ 5e4): fp32 output,
+  // plain epilogue, whole rows 16-byte aligned (vector atomics), one batch
+  if (!GENERIC && sizeof(DT) == 4 && p.batches == 1 && ep.vec4_ok && g.N % 4 == 0 && p.total_tiles * 2 <= sm_count() && num_kb >= 16) {
+    p.splits = (int)std::min<int64_t>(sm_count() / p.total_tiles, num_kb / 8);
+    if (p.splits < 1) p.splits = 1;
+  }
+  p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
+  p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.total_work = p.total_tiles * p.splits;
+  if (p.splits > 1) TSW_CUDA(cudaMemset2DAsync(g.D, (size_t)g.ldd * 4, 0, (size_t)g.N * 4, (size_t)g.M, st));
+  auto kern = gemm_tc_kernel<BN, STAGES, DT, GENERIC>;
   static bool attr_done = false;
   if (!attr_done) {
     TSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done = true;
   }
-  const int grid = (int)std::min<int64_t>(p.total_tiles, sm_count());
+  const int grid = (int)std::min<int64_t>(p.total_work, sm_count());
   kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, p, ep);
   TSW_LAUNCH_CHECK();
   return TSW_OK;
@@ -355,8 +485,15 @@ int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st)
   if (!gemm_tc_supported(g, &why)) { set_error("gemm(tcgen05): %s", why); return TSW_E_UNSUPPORTED; }
   // wide tiles when N is large enough to fill them; narrow tiles keep more CTAs busy on small N
   const bool wide = g.N > 128;
-  if (g.d_dtype == TSW_BF16) return wide ? tc_go<256, 4, __nv_bfloat16>(g, ep, st) : tc_go<128, 6, __nv_bfloat16>(g, ep, st);
-  if (g.d_dtype == TSW_F32) return wide ? tc_go<256, 4, float>(g, ep, st) : tc_go<128, 6, float>(g, ep, st);
+  const bool generic = ep.epilogue != TSW_EPI_NONE || ep.residual || ep.aux_out || ep.beta != 0.f;
+#define TC_DISPATCH(DT)                                                                                   \
+  do {                                                                                                    \
+    if (wide) return generic ? tc_go<256, 4, DT, true>(g, ep, st) : tc_go<256, 4, DT, false>(g, ep, st);  \
+    return generic ? tc_go<128, 6, DT, true>(g, ep, st) : tc_go<128, 6, DT, false>(g, ep, st);            \
+  } while (0)
+  if (g.d_dtype == TSW_BF16) TC_DISPATCH(__nv_bfloat16);
+  if (g.d_dtype == TSW_F32) TC_DISPATCH(float);
+#undef TC_DISPATCH
   set_error("gemm(tcgen05): bad output dtype");
   return TSW_E_INVALID;
 }

@@ -414,3 +414,27 @@ def test_gemm_auto_falls_back_to_simt_for_unaligned(K):
     from robustsq_whisper_b200._C import TswError
     with pytest.raises(TswError):
         K.gemm(a.cuda(), b.cuda(), M=33, N=21, K=45, out_dtype=torch.float32, impl=2)
+
+
+def test_gemm_tcgen05_split_k_weight_gradient_shape(K):
+    """dW = dY^T X with few output tiles and a long reduction takes the split-K path (vector atomics into fp32)."""
+    torch.manual_seed(16)
+    M, N, Kd = 384, 264, 8200
+    dy = (torch.randn(Kd, M) * 0.3).bfloat16()   # stored [K][M]  (MN-major A)
+    x = (torch.randn(Kd, N) * 0.3).bfloat16()    # stored [K][N]  (MN-major B)
+    bias = torch.randn(N)
+    ref = dy.float().t() @ x.float() + bias
+    out = K.gemm(dy.cuda(), x.cuda(), M=M, N=N, K=Kd, a_mn=True, b_mn=True, lda=M, ldb=N, bias=bias.cuda(), out_dtype=torch.float32, impl=2)
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_lsce_in_place_gradient(K):
+    """dlogits may alias logits (the fused tied-logits path): loss must be read before the overwrite."""
+    torch.manual_seed(17)
+    V, rows = 1000, 9
+    logits = torch.randn(rows, V)
+    tgt = torch.randint(0, V, (rows,))
+    ref = upstream.LabelSmoothingLoss(V, -1, 0.1)(logits.view(1, rows, V), tgt.view(1, rows))
+    buf = logits.clone().cuda()
+    ls, counts = K.lsce_fwd_bwd(buf, rows, V, V, tgt.cuda(), -1, 0.1, 1.0, buf, V)
+    assert ls.item() == pytest.approx(ref.item(), rel=1e-5)
