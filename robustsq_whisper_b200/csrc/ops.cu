@@ -54,9 +54,11 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
   for (int c = 0; c < kLnChunks; ++c) {
     const int i = lane + 32 * c;
     if (i < nvec) {
-      float o[VN];
+      float o[VN], gv[VN], bv[VN];
 #pragma unroll
-      for (int j = 0; j < VN; ++j) o[j] = (v[c][j] - mu) * rs * gamma[i * VN + j] + beta[i * VN + j];
+      for (int j = 0; j < VN; j += 4) { Vec<float>::load(gamma + i * VN + j, gv + j); Vec<float>::load(beta + i * VN + j, bv + j); }
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o[j] = (v[c][j] - mu) * rs * gv[j] + bv[j];
       Vec<T>::store(y + row * d + (int64_t)i * VN, o);
     }
   }
@@ -90,13 +92,15 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
     for (int c = 0; c < NC; ++c) {
       const int i = lane + 32 * c;
       if (i < nvec) {
-        float xv[VN], dv[VN];
+        float xv[VN], dv[VN], gv[VN];
         Vec<T>::load(x + row * d + (int64_t)i * VN, xv);
         Vec<T>::load(dy + row * d + (int64_t)i * VN, dv);
 #pragma unroll
+        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+#pragma unroll
         for (int j = 0; j < VN; ++j) {
           xh[c][j] = (xv[j] - mu) * rs;
-          g[c][j] = dv[j] * gamma[i * VN + j];
+          g[c][j] = dv[j] * gv[j];
           s1 += g[c][j];
           s2 += g[c][j] * xh[c][j];
           dg[c][j] += dv[j] * xh[c][j];
@@ -143,20 +147,54 @@ __global__ void colreduce_kernel(const float* __restrict__ partial, int nparts, 
 }
 
 // ============================================================================================ column sums (bias grads)
+// CTA = 32 column groups (one 16-byte vector each) x 8 row lanes: a warp reads 512 contiguous bytes of one row per
+// instruction; the 8 row lanes are folded through shared memory and the CTA writes one partial row.
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t n, int64_t ld, int64_t rows_per_chunk,
-                                      float* __restrict__ partial) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t n, int64_t ld, int64_t rows_per_chunk,
+                      float* __restrict__ partial, int vec_ok) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float sm[8][32 * VN + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = ((int64_t)blockIdx.x * 32 + tx) * VN;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int64_t r = r0;
-  for (; r + 3 < r1; r += 4) {
-    s0 += to_f32(x[r * ld + c]); s1 += to_f32(x[(r + 1) * ld + c]);
-    s2 += to_f32(x[(r + 2) * ld + c]); s3 += to_f32(x[(r + 3) * ld + c]);
+  float acc[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) acc[j] = 0.f;
+  if (c0 < n) {
+    if (vec_ok && c0 + VN <= n) {
+      int64_t r = r0 + ty;
+      for (; r + 8 < r1; r += 16) {  // two independent loads in flight
+        float a[VN], b[VN];
+        Vec<T>::load(x + r * ld + c0, a);
+        Vec<T>::load(x + (r + 8) * ld + c0, b);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += a[j] + b[j];
+      }
+      for (; r < r1; r += 8) {
+        float a[VN];
+        Vec<T>::load(x + r * ld + c0, a);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) acc[j] += a[j];
+      }
+    } else {
+      for (int64_t r = r0 + ty; r < r1; r += 8)
+#pragma unroll
+        for (int j = 0; j < VN; ++j) if (c0 + j < n) acc[j] += to_f32(x[r * ld + c0 + j]);
+    }
   }
-  for (; r < r1; ++r) s0 += to_f32(x[r * ld + c]);
-  partial[(int64_t)blockIdx.y * n + c] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int j = 0; j < VN; ++j) sm[ty][tx * VN + j] = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VN; c += 256) {
+    const int64_t col = (int64_t)blockIdx.x * 32 * VN + c;
+    if (col < n) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[k][c];
+      partial[(int64_t)blockIdx.y * n + col] = t;
+    }
+  }
 }
 
 // ============================================================================================ elementwise
@@ -363,7 +401,7 @@ extern "C" int tsw_layernorm_fwd(const void* x, const void* res, const float* ga
   const int vn = dtype == TSW_F32 ? 4 : 8;
   TSW_CHECK_ARG(d % vn == 0 && d / vn <= 32 * kLnChunks, "layernorm_fwd: d=%lld unsupported (need d %% %d == 0, d <= %d)",
                 (long long)d, vn, 32 * kLnChunks * vn);
-  TSW_CHECK_ARG(aligned16(x) && aligned16(y) && (!res || aligned16(res)) && (!sum_out || aligned16(sum_out)), "layernorm_fwd: pointers must be 16-byte aligned");
+  TSW_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!res || aligned16(res)) && (!sum_out || aligned16(sum_out)), "layernorm_fwd: pointers must be 16-byte aligned");
   const unsigned grid = (unsigned)((rows + 7) / 8);
   DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)res, gamma, beta, (T*)y,
                                                                                  (T*)sum_out, mean, rstd, rows, (int)d, eps)));
@@ -381,6 +419,7 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   TSW_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "layernorm_bwd: null/empty argument");
   const int vn = dtype == TSW_F32 ? 4 : 8;
   TSW_CHECK_ARG(d % vn == 0 && d <= 1024, "layernorm_bwd: d=%lld unsupported (d %% %d == 0, d <= 1024)", (long long)d, vn);
+  TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), "layernorm_bwd: pointers must be 16-byte aligned");
   if (!workspace || workspace_bytes < tsw_layernorm_bwd_workspace_bytes(rows, d)) { set_error("layernorm_bwd: workspace too small"); return TSW_E_WORKSPACE; }
   const int grid = (int)std::min<int64_t>(ln_bwd_grid(), (rows + 7) / 8);
   float* partial = (float*)workspace;
@@ -407,23 +446,25 @@ extern "C" int tsw_cast(const void* src, int src_dtype, void* dst, int dst_dtype
   return TSW_OK;
 }
 
-static int64_t colsum_chunks(int64_t rows, int64_t n) {
-  const int64_t col_blocks = (n + 255) / 256;
+static int64_t colsum_chunks(int64_t rows, int64_t n, int vn) {
+  const int64_t col_blocks = (n + 32 * vn - 1) / (32 * vn);
   int64_t chunks = std::max<int64_t>(1, ((int64_t)sm_count() * 8) / col_blocks);
-  chunks = std::min<int64_t>(chunks, (rows + 15) / 16);
+  chunks = std::min<int64_t>(chunks, (rows + 63) / 64);
   return std::max<int64_t>(1, std::min<int64_t>(chunks, 65535));
 }
-extern "C" size_t tsw_colsum_workspace_bytes(int64_t rows, int64_t n) { return sizeof(float) * (size_t)n * colsum_chunks(rows, n); }
+extern "C" size_t tsw_colsum_workspace_bytes(int64_t rows, int64_t n) { return sizeof(float) * (size_t)n * std::max(colsum_chunks(rows, n, 4), colsum_chunks(rows, n, 8)); }
 
 extern "C" int tsw_colsum(const void* x, int dtype, int64_t rows, int64_t n, int64_t ld, float* out, void* workspace,
                           size_t workspace_bytes, tsw_stream_t stream) {
   TSW_CHECK_ARG(x && out && rows > 0 && n > 0 && ld >= n, "colsum: bad argument");
   if (!workspace || workspace_bytes < tsw_colsum_workspace_bytes(rows, n)) { set_error("colsum: workspace too small"); return TSW_E_WORKSPACE; }
-  const int64_t chunks = colsum_chunks(rows, n);
+  const int vn = dtype == TSW_F32 ? 4 : 8;
+  const int64_t chunks = colsum_chunks(rows, n, vn);
   const int64_t rpc = (rows + chunks - 1) / chunks;
-  dim3 grid((unsigned)((n + 255) / 256), (unsigned)chunks);
+  dim3 grid((unsigned)((n + 32 * vn - 1) / (32 * vn)), (unsigned)chunks);
   float* partial = (float*)workspace;
-  DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, rows, n, ld, rpc, partial)));
+  const int vec_ok = aligned16(x) && ld % vn == 0;
+  DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, rows, n, ld, rpc, partial, vec_ok)));
   TSW_LAUNCH_CHECK();
   colreduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, (int)chunks, n, out, out, n);
   TSW_LAUNCH_CHECK();
