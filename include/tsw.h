@@ -137,6 +137,25 @@ int tsw_softmax_fwd(const void* s, void* p, int dtype, int64_t batch, int64_t he
 int tsw_softmax_bwd(const void* p, const void* dp, void* ds, int dtype, int64_t rows, int64_t sk, int64_t ld, float scale,
                     tsw_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ K3 fused attention
+ * Replaces the matmul -> scale -> (+mask) -> softmax -> matmul chains of openai-whisper MultiHeadAttention.qkv_attention
+ * (behind whisper_encoder.py:497-500, whisper_decoder.py:281-284) and BertSelfAttention.forward (Qformer.py:183-247):
+ * o[b, i, h*64:(h+1)*64] = softmax_k(scale * <q_i, k_k> + mask) v_k, head dim 64, bf16 in/out, fp32 statistics.
+ * q (B, Sq, ldq), k/v (B, Sk, ld*), o (B, Sq, ldo): heads are 64-wide column slices; lse (B, H, Sq) fp32 = log-sum-exp of
+ * the scaled, masked scores (saved for backward).  key_len (B) int32 or NULL masks keys >= key_len[b]; causal != 0 keeps
+ * key k for query i iff k <= i + (Sk - Sq).  Scores are never written to HBM. */
+int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t H, int64_t Sq, int64_t Sk,
+                 int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, const int32_t* key_len, int causal,
+                 tsw_stream_t stream);
+
+/* Backward of tsw_fmha_fwd: recomputes the probabilities from lse; dq (B, Sq, H*64 contiguous), dk/dv laid out like k/v.
+ * workspace holds the fp32 dQ accumulator (filled by bulk tensor reduce-adds) and delta = rowsum(dO * O). */
+size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq);
+int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
+                 void* dv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                 int64_t lddo, float scale, const int32_t* key_len, int causal, void* workspace, size_t workspace_bytes,
+                 tsw_stream_t stream);
+
 /* Token embedding gather + learned positions (whisper_decoder.py:267-279):
  * out[b, u, :] = (u == 0 ? E[sop] : u <= q ? prompt[b, u-1] : E[ids[b, u-1-q]]) + pos[u], out dtype `dtype`. */
 int tsw_decoder_embed(const float* E, const float* pos, const void* prompt, int prompt_dtype, const int64_t* ids,

@@ -1,0 +1,570 @@
+// K3 — fused multi-head attention (flash-style, head dim 64) on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Replaces the unfused  matmul -> scale -> (+mask) -> softmax(fp32) -> matmul  chains of the reference path:
+//   openai-whisper MultiHeadAttention.qkv_attention behind whisper_encoder.py:497-500 and whisper_decoder.py:281-284
+//   (no mask / causal mask), and BertSelfAttention.forward, Qformer.py:183-247 (key-padding masks, self and cross).
+// Scores are never written to HBM: per (batch, head, 128-query tile) a CTA streams 128-key tiles of K and V through a TMA
+// ring, S = Q K^T lands in TMEM, four softmax warps (thread = query row) turn it into bf16 probabilities in 128B-swizzled
+// shared memory, P V accumulates through TMEM into fp32 registers with the usual running-max rescale.  Forward saves
+// only the log-sum-exp per row; backward (fmha_bwd_kernel) recomputes P from it.
+//
+//   warp 0      TMA producer (Q once, K/V ring)
+//   warp 1      TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-5   softmax / output (each owns the 32 TMEM lanes its index allows)
+// Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+#include <mutex>
+
+#include "tc_ptx.cuh"
+
+namespace tsw {
+
+constexpr int FQ = 128;   // queries per CTA (UMMA M)
+constexpr int FK = 128;   // keys per tile
+constexpr int FD = 64;    // head dim
+constexpr int F_THREADS = 192;
+constexpr uint32_t kTileBytes = 128 * 128;  // 128 rows x 64 bf16 = 16 KB (one SW128 panel)
+
+struct FmhaParams {
+  int B, H, Sq, Sk;
+  float scale_log2;       // scale * log2(e)
+  const int32_t* key_len; // (B) or null
+  int causal;             // 0 | 1: key k visible to query i iff k <= i + (Sk - Sq)
+  __nv_bfloat16* o; int64_t ldo;
+  float* lse;             // (B, H, Sq) natural-log LSE of the scaled scores
+};
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t idesc_bf16(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ int fmha_kv_limit(const FmhaParams& p, int b, int q0) {
+  int limit = p.Sk;
+  if (p.key_len) limit = min(limit, p.key_len[b]);
+  if (p.causal) limit = min(limit, q0 + FQ + (p.Sk - p.Sq));  // last row of the tile sees keys < q0 + 128 + offset
+  return max(limit, 0);
+}
+
+struct FmhaFwdSmem {
+  unsigned char q[kTileBytes];
+  unsigned char k[2][kTileBytes];
+  unsigned char v[2][kTileBytes];
+  unsigned char p[2 * kTileBytes];  // 128 x 128 bf16 probabilities: two 64-key panels
+  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, p_full, o_full;
+  uint32_t tmem_slot;
+};
+
+__global__ void __launch_bounds__(F_THREADS, 2)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                const FmhaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  FmhaFwdSmem& s = *reinterpret_cast<FmhaFwdSmem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FQ, h = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_fwd: dynamic smem not 1024-aligned\n"); __trap(); }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(&s.q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.k_full[i], 1); mbar_init(&s.k_empty[i], 1); mbar_init(&s.v_full[i], 1); mbar_init(&s.v_empty[i], 1); }
+    mbar_init(&s.s_full, 1); mbar_init(&s.p_full, 4); mbar_init(&s.o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(&s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_s = s.tmem_slot;          // 128 columns: S
+  const uint32_t tmem_pv = s.tmem_slot + 128;   // 64 columns: P V of the current tile
+
+  const int limit = fmha_kv_limit(p, b, q0);
+  const int n_kv = (limit + FK - 1) / FK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&s.q_full, kTileBytes);
+      tma_load_4d(&tmQ, &s.q_full, s.q, h * FD, q0, b, 0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&s.k_empty[st], ph ^ 1);
+        mbar_expect_tx(&s.k_full[st], kTileBytes);
+        tma_load_4d(&tmK, &s.k_full[st], s.k[st], h * FD, j * FK, b, 0);
+        mbar_wait(&s.v_empty[st], ph ^ 1);
+        mbar_expect_tx(&s.v_full[st], kTileBytes);
+        tma_load_4d(&tmV, &s.v_full[st], s.v[st], h * FD, j * FK, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      const uint32_t id_s = idesc_bf16(FQ, FK, 0, 0);    // S = Q K^T : both K-major, N = 128
+      const uint32_t id_pv = idesc_bf16(FQ, FD, 0, 1);   // PV       : P K-major, V MN-major ([key][dh]), N = 64
+      const uint32_t qa = smem_u32(s.q), pa = smem_u32(s.p);
+      auto issue_s = [&](int j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&s.k_full[st], ph);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(s.k[st]);
+#pragma unroll
+        for (int k = 0; k < FD / 16; ++k)
+          umma_bf16(tmem_s, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), id_s, k > 0);
+        umma_commit(&s.s_full);
+        umma_commit(&s.k_empty[st]);
+      };
+      mbar_wait(&s.q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&s.p_full, j & 1);   // probabilities of tile j are in smem; S and PV TMEM have been drained
+        mbar_wait(&s.v_full[st], ph);
+        tc_fence_after();
+        const uint32_t va = smem_u32(s.v[st]);
+#pragma unroll
+        for (int k = 0; k < FK / 16; ++k)
+          umma_bf16(tmem_pv, make_smem_desc(pa + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
+                    make_smem_desc(va + k * 2048, kTileBytes, 1024), id_pv, k > 0);
+        umma_commit(&s.o_full);
+        umma_commit(&s.v_empty[st]);
+        if (j + 1 < n_kv) issue_s(j + 1);  // next S overlaps the softmax warps' output update
+      }
+    }
+  } else {
+    // ===================================================== softmax + output, thread = query row
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float o[FD];
+#pragma unroll
+    for (int i = 0; i < FD; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    int row_limit = limit;
+    if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s.s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * FK;
+      // pass 1: row maximum of the visible scores of this tile
+      float mx = m_run;
+#pragma unroll 1
+      for (int c = 0; c < FK; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (kbase + c + i < row_limit) mx = fmaxf(mx, v[i] * p.scale_log2);
+      }
+      const float m_new = mx;
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = exp2f(m_run - m_use);   // m_run = -inf on the first tile -> 0
+      float lsum = 0.f;
+      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
+#pragma unroll 1
+      for (int c = 0; c < FK; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_s + lane_off + c, v);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = (kbase + c + i < row_limit) ? exp2f(fmaf(v[i], p.scale_log2, -m_use)) : 0.f;
+          const float p1 = (kbase + c + i + 1 < row_limit) ? exp2f(fmaf(v[i + 1], p.scale_log2, -m_use)) : 0.f;
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          // accumulate the row sum from the ROUNDED probabilities so that P V / l is a true convex combination
+          const float2 pr = __bfloat1622float2(pb);
+          lsum += pr.x + pr.y;
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+        }
+        unsigned char* panel = s.p + (c >> 6) * kTileBytes + r * 128;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int u = ((c & 63) >> 3) + t;  // 16-byte unit inside the 128-byte row of this panel
+          *reinterpret_cast<uint4*>(panel + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      // fold the previous tiles' rescale into o BEFORE handing P to the tensor core? no: o holds tiles < j, rescale now
+#pragma unroll
+      for (int i = 0; i < FD; ++i) o[i] *= alpha;
+      fence_async_smem();     // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.p_full);
+      // accumulate P V of this tile
+      mbar_wait(&s.o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < FD; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_pv + lane_off + c, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c + i] += v[i];
+      }
+    }
+    if (qi < p.Sq) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = p.o + ((int64_t)b * p.Sq + qi) * p.ldo + h * FD;
+#pragma unroll
+      for (int c = 0; c < FD; c += 8) {
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = o[c + i] * inv;
+        Vec<__nv_bfloat16>::store(orow + c, t);
+      }
+      p.lse[((int64_t)b * p.H + h) * p.Sq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.69314718055994530942f : -INFINITY;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(s.tmem_slot); }
+}
+
+
+// ================================================================================================ backward
+// One CTA per (batch, head, 128-key tile); loop over the 128-query tiles that can see it.  Per iteration five MMAs:
+//   S = Q K^T, dP = dO V^T            -> TMEM (lanes = queries)
+//   P = exp2(S*c - lse), dS = P (dP - delta) * scale   (8 warps; thread = query row x 64-key half) -> bf16 in smem, [q][key]
+//   dV += P^T dO, dK += dS^T Q        -> TMEM accumulators over the whole loop (lanes = keys); P / dS are MN-major A operands
+//   dQ_i = dS K                       -> TMEM, staged to smem as fp32 and added into the fp32 dQ buffer with one
+//                                        cp.reduce.async.bulk.tensor (.add) per 32-column panel — no per-thread atomics.
+constexpr int FB_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax/gradient
+
+struct FmhaBwdParams {
+  int B, H, Sq, Sk;
+  float scale, scale_log2;
+  const int32_t* key_len;
+  int causal;
+  const float* lse;    // (B, H, Sq)
+  const float* delta;  // (B, H, Sq) rowsum(dO * O)
+  __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
+};
+
+struct FmhaBwdSmem {
+  unsigned char k[kTileBytes];
+  unsigned char v[kTileBytes];
+  unsigned char q[2][kTileBytes];
+  unsigned char dO[2][kTileBytes];
+  unsigned char p[2 * kTileBytes];    // [q][key] bf16, two 64-key panels
+  unsigned char ds[2 * kTileBytes];
+  unsigned char dq[2 * kTileBytes];   // fp32 staging: two 32-column panels of [128][128 B], SW128
+  uint64_t kv_full, q_full[2], q_empty[2], s_full, pds_full, dq_full;
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// first / one-past-last query tile that can see key tile kv0 (causal) 
+__device__ __forceinline__ void fmha_q_range(const FmhaBwdParams& p, int kv0, int* qt0, int* qt1) {
+  const int n_q = (p.Sq + FQ - 1) / FQ;
+  int lo = 0;
+  if (p.causal) {  // query i sees key k iff k <= i + off  ->  i >= kv0 - off
+    const int off = p.Sk - p.Sq;
+    lo = max(0, kv0 - off) / FQ;
+  }
+  *qt0 = min(lo, n_q); *qt1 = n_q;
+}
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ, const FmhaBwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  FmhaBwdSmem& s = *reinterpret_cast<FmhaBwdSmem*>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * FK, h = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_bwd: dynamic smem not 1024-aligned\n"); __trap(); }
+
+  int klimit = p.Sk;
+  if (p.key_len) klimit = min(klimit, p.key_len[b]);
+  int qt0, qt1;
+  fmha_q_range(p, kv0, &qt0, &qt1);
+  const bool active = kv0 < klimit && qt0 < qt1;   // otherwise this key tile receives no gradient
+  const int n_it = active ? qt1 - qt0 : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
+    mbar_init(&s.kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
+    mbar_init(&s.s_full, 1); mbar_init(&s.pds_full, 8); mbar_init(&s.dq_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t_s = s.tmem_slot, t_dp = t_s + 128, t_dv = t_s + 256, t_dk = t_s + 320, t_dq = t_s + 384;
+
+  if (warp == 0) {
+    if (lane == 0 && active) {
+      mbar_expect_tx(&s.kv_full, 2 * kTileBytes);
+      tma_load_4d(&tmK, &s.kv_full, s.k, h * FD, kv0, b, 0);
+      tma_load_4d(&tmV, &s.kv_full, s.v, h * FD, kv0, b, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&s.q_empty[st], ph ^ 1);
+        mbar_expect_tx(&s.q_full[st], 2 * kTileBytes);
+        tma_load_4d(&tmQ, &s.q_full[st], s.q[st], h * FD, (qt0 + it) * FQ, b, 0);
+        tma_load_4d(&tmdO, &s.q_full[st], s.dO[st], h * FD, (qt0 + it) * FQ, b, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && active) {
+      const uint32_t id_s = idesc_bf16(128, 128, 0, 0);   // S, dP: K-major x K-major, N = 128 keys
+      const uint32_t id_g = idesc_bf16(128, 64, 1, 1);    // dV, dK: A = P^T / dS^T (MN-major), B = dO / Q (MN-major), N = 64
+      const uint32_t id_q = idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major over keys), B = K tile (MN-major), N = 64
+      const uint32_t ka = smem_u32(s.k), va = smem_u32(s.v), pa = smem_u32(s.p), dsa = smem_u32(s.ds);
+      auto issue_scores = [&](int it) {
+        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&s.q_full[st], ph);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(s.q[st]), doa = smem_u32(s.dO[st]);
+#pragma unroll
+        for (int k = 0; k < FD / 16; ++k)
+          umma_bf16(t_s, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < FD / 16; ++k)
+          umma_bf16(t_dp, make_smem_desc(doa + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), id_s, k > 0);
+        umma_commit(&s.s_full);
+      };
+      mbar_wait(&s.kv_full, 0);
+      issue_scores(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        mbar_wait(&s.pds_full, it & 1);   // P, dS in smem; S, dP and dQ TMEM drained
+        tc_fence_after();
+        const uint32_t qa = smem_u32(s.q[st]), doa = smem_u32(s.dO[st]);
+#pragma unroll
+        for (int k = 0; k < FQ / 16; ++k) {  // reduction over the 128 queries, 16 per instruction
+          // A (MN-major): [q][key] rows of 128 B per 64-key panel -> LBO = panel stride, 16 q-rows = 2048 B per step
+          umma_bf16(t_dv, make_smem_desc(pa + k * 2048, kTileBytes, 1024), make_smem_desc(doa + k * 2048, kTileBytes, 1024), id_g, (it | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < FQ / 16; ++k)
+          umma_bf16(t_dk, make_smem_desc(dsa + k * 2048, kTileBytes, 1024), make_smem_desc(qa + k * 2048, kTileBytes, 1024), id_g, (it | k) != 0);
+#pragma unroll
+        for (int k = 0; k < FK / 16; ++k)    // reduction over the 128 keys
+          umma_bf16(t_dq, make_smem_desc(dsa + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024), make_smem_desc(ka + k * 2048, kTileBytes, 1024), id_q, k > 0);
+        umma_commit(&s.dq_full);
+        umma_commit(&s.q_empty[st]);
+        if (it + 1 < n_it) issue_scores(it + 1);
+      }
+    }
+  } else {
+    // ===================================================== P / dS, dQ staging, final dK / dV   (warps 2..9)
+    const int quarter = warp & 3;          // TMEM lane quarter
+    const int half = (warp - 2) >> 2;      // which 64-key (and 32-dQ-column) half this warp handles
+    const int r = quarter * 32 + lane;     // row inside the tile (query row in the loop, key row at the end)
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const bool leader = (warp == 2 && lane == 0);
+    for (int it = 0; it < n_it; ++it) {
+      const int q0 = (qt0 + it) * FQ;
+      const int qi = q0 + r;
+      float lse2 = 0.f, dlt = 0.f;
+      int row_limit = 0;
+      if (qi < p.Sq) {
+        const int64_t idx = ((int64_t)b * p.H + h) * p.Sq + qi;
+        lse2 = p.lse[idx] * 1.44269504088896340736f;
+        dlt = p.delta[idx];
+        row_limit = klimit;
+        if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
+        if (!(lse2 > -INFINITY)) row_limit = 0;
+      }
+      mbar_wait(&s.s_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half * 64; c < half * 64 + 64; c += 32) {
+        float sv[32], dpv[32];
+        tmem_ld32(t_s + lane_off + c, sv);
+        tmem_ld32(t_dp + lane_off + c, dpv);
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const bool ok0 = kv0 + c + i < row_limit, ok1 = kv0 + c + i + 1 < row_limit;
+          const float p0 = ok0 ? exp2f(fmaf(sv[i], p.scale_log2, -lse2)) : 0.f;
+          const float p1 = ok1 ? exp2f(fmaf(sv[i + 1], p.scale_log2, -lse2)) : 0.f;
+          const float d0 = p0 * (dpv[i] - dlt) * p.scale, d1 = p1 * (dpv[i + 1] - dlt) * p.scale;
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1), db = __floats2bfloat162_rn(d0, d1);
+          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+          dk_[i >> 1] = *reinterpret_cast<const uint32_t*>(&db);
+        }
+        const int off = (c >> 6) * kTileBytes + r * 128;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int u = (((c & 63) >> 3) + t) ^ (r & 7);
+          *reinterpret_cast<uint4*>(s.p + off + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          *reinterpret_cast<uint4*>(s.ds + off + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.pds_full);
+      // dQ tile of this iteration -> fp32 smem panels -> TMA reduce-add into the global fp32 dQ
+      mbar_wait(&s.dq_full, it & 1);
+      tc_fence_after();
+      if (leader) bulk_wait_read0();            // the previous reduce has finished reading the staging buffer
+      named_bar_sync(1, 256);
+      {
+        float v[32];
+        tmem_ld32(t_dq + lane_off + half * 32, v);
+        unsigned char* row = s.dq + half * kTileBytes + r * 128;
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          *reinterpret_cast<float4*>(row + ((t ^ (r & 7)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, 256);
+      if (leader) {
+        tma_reduce_add_4d(&tmdQ, s.dq, h * FD, q0, b, 0);
+        tma_reduce_add_4d(&tmdQ, s.dq + kTileBytes, h * FD + 32, q0, b, 0);
+        bulk_commit();
+      }
+    }
+    // ---- dK, dV of this key tile (lanes = keys); inactive tiles write zeros
+    const int key = kv0 + r;
+    if (active) { mbar_wait(&s.dq_full, (n_it - 1) & 1); tc_fence_after(); }  // all MMAs of the last iteration have completed
+    float gv[32], gk[32];
+    if (active) {
+      tmem_ld32(t_dv + lane_off + half * 32, gv);
+      tmem_ld32(t_dk + lane_off + half * 32, gk);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) gv[i] = gk[i] = 0.f;
+    }
+    if (key < p.Sk) {
+      __nv_bfloat16* dvrow = p.dv + ((int64_t)b * p.Sk + key) * p.lddv + h * FD + half * 32;
+      __nv_bfloat16* dkrow = p.dk + ((int64_t)b * p.Sk + key) * p.lddk + h * FD + half * 32;
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
+    }
+    if (leader) bulk_wait0();   // the last reduce must be complete before the CTA (and its smem) goes away
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(s.tmem_slot); }
+}
+
+// delta[b,h,i] = sum_c dO[b,i,h*64+c] * O[b,i,h*64+c]; one warp per (row, head)
+__global__ void __launch_bounds__(256)
+fmha_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, int64_t ldo, int64_t lddo, int B, int H, int Sq,
+                  float* __restrict__ delta) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b, i, h)
+  if (w >= (int64_t)B * Sq * H) return;
+  const int h = (int)(w % H);
+  const int64_t bi = w / H;
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + bi * ldo + h * FD + lane * 2);
+  const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(dO + bi * lddo + h * FD + lane * 2);
+  const float2 af = __bfloat1622float2(a), gf = __bfloat1622float2(g);
+  const float sum = warp_sum(af.x * gf.x + af.y * gf.y);
+  if (lane == 0) { const int64_t b = bi / Sq, i = bi - b * Sq; delta[(b * H + h) * Sq + i] = sum; }
+}
+
+// (B, S, d) bf16 tensor -> 4-D map {d, S, B, 1}, box {64, 128, 1, 1}, SWIZZLE_128B
+static int make_bsd_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t d_cols, int64_t ld, bool f32 = false) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("fmha: cuTensorMapEncodeTiled entry point unavailable"); return TSW_E_CUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)d_cols, (cuuint64_t)S, (cuuint64_t)B, 1};
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)S * ld * es, (cuuint64_t)B * S * ld * es};
+  cuuint32_t box[4] = {f32 ? 32u : 64u, 128u, 1u, 1u};  // 128-byte inner box either way
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("fmha: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSW_E_CUDA; }
+  return TSW_OK;
+}
+
+}  // namespace tsw
+
+using namespace tsw;
+
+extern "C" int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int64_t B, int64_t H, int64_t Sq, int64_t Sk,
+                            int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, const int32_t* key_len, int causal,
+                            tsw_stream_t stream) {
+  TSW_CHECK_ARG(q && k && v && o && lse, "fmha_fwd: null argument");
+  TSW_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0 && B <= 65535 && H <= 65535, "fmha_fwd: bad sizes");
+  TSW_CHECK_ARG(ldq >= H * FD && ldk >= H * FD && ldv >= H * FD && ldo >= H * FD, "fmha_fwd: leading dimension smaller than H * 64");
+  TSW_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o),
+                "fmha_fwd: pointers / leading dimensions must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_bsd_map(&tq, q, B, Sq, H * FD, ldq))) return rc;
+  if ((rc = make_bsd_map(&tk, k, B, Sk, H * FD, ldk))) return rc;
+  if ((rc = make_bsd_map(&tv, v, B, Sk, H * FD, ldv))) return rc;
+  FmhaParams p;
+  p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
+  p.scale_log2 = scale * 1.44269504088896340736f;
+  p.key_len = key_len; p.causal = causal ? 1 : 0;
+  p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.lse = lse;
+  static bool attr_done = false;
+  const size_t smem = sizeof(FmhaFwdSmem);
+  if (!attr_done) {
+    TSW_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((Sq + FQ - 1) / FQ), (unsigned)H, (unsigned)B);
+  fmha_fwd_kernel<<<grid, F_THREADS, smem, as_stream(stream)>>>(tq, tk, tv, p);
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
+
+extern "C" int tsw_cast(const void*, int, void*, int, int64_t, tsw_stream_t);
+
+extern "C" size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq) {
+  return (size_t)(B * Sq * H * FD) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256);
+}
+
+extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
+                            void* dv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                            int64_t lddo, float scale, const int32_t* key_len, int causal, void* workspace, size_t workspace_bytes,
+                            tsw_stream_t stream) {
+  TSW_CHECK_ARG(q && k && v && o && dO && lse && dq && dk && dv, "fmha_bwd: null argument");
+  TSW_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0 && B <= 65535 && H <= 65535, "fmha_bwd: bad sizes");
+  TSW_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0, "fmha_bwd: leading dimensions must be multiples of 8");
+  TSW_CHECK_ARG(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(dO) && aligned16(dq) && aligned16(dk) && aligned16(dv),
+                "fmha_bwd: pointers must be 16-byte aligned");
+  if (!workspace || workspace_bytes < tsw_fmha_bwd_workspace_bytes(B, H, Sq)) { set_error("fmha_bwd: workspace too small"); return TSW_E_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  const int64_t dcols = H * FD;
+  float* dq32 = (float*)workspace;                       // (B, Sq, H*64) fp32 accumulator
+  float* delta = (float*)((char*)workspace + (size_t)(B * Sq * dcols) * 4);
+  TSW_CUDA(cudaMemsetAsync(dq32, 0, (size_t)(B * Sq * dcols) * 4, st));
+  {
+    const int64_t warps = B * Sq * H;
+    fmha_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, ldo, lddo, (int)B, (int)H, (int)Sq, delta);
+    TSW_LAUNCH_CHECK();
+  }
+  CUtensorMap tq, tk, tv, tdo, tdq;
+  int rc;
+  if ((rc = make_bsd_map(&tq, q, B, Sq, dcols, ldq))) return rc;
+  if ((rc = make_bsd_map(&tk, k, B, Sk, dcols, ldk))) return rc;
+  if ((rc = make_bsd_map(&tv, v, B, Sk, dcols, ldv))) return rc;
+  if ((rc = make_bsd_map(&tdo, dO, B, Sq, dcols, lddo))) return rc;
+  if ((rc = make_bsd_map(&tdq, dq32, B, Sq, dcols, dcols, true))) return rc;
+  FmhaBwdParams p;
+  p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
+  p.scale = scale; p.scale_log2 = scale * 1.44269504088896340736f;
+  p.key_len = key_len; p.causal = causal ? 1 : 0;
+  p.lse = lse; p.delta = delta;
+  p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddk = ldk; p.lddv = ldv;
+  static bool attr_done = false;
+  const size_t smem = sizeof(FmhaBwdSmem);
+  if (!attr_done) {
+    TSW_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((Sk + FK - 1) / FK), (unsigned)H, (unsigned)B);
+  fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+  TSW_LAUNCH_CHECK();
+  // dq (B, Sq, ldq) bf16 <- fp32 accumulator (contiguous when ldq == H*64, the only layout the host side uses)
+  TSW_CHECK_ARG(ldq == dcols, "fmha_bwd: dq must be contiguous (ldq == H * 64)");
+  return tsw_cast(dq32, TSW_F32, dq, TSW_BF16, B * Sq * dcols, stream);
+}

@@ -282,7 +282,29 @@ class _Attention(Function):
         return dq, dk, dv, None, None, None, None
 
 
+class _FusedAttention(Function):
+    """Flash-style attention on tcgen05 (K3, fmha.cu): scores never reach HBM; backward recomputes them from the saved
+    log-sum-exp.  bf16, head dim 64 — every attention of the training path."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor], causal: bool):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        o, lse = K.fmha_fwd(q, k, v, n_head, scale, key_len=key_len, causal=causal)
+        ctx.save_for_backward(q, k, v, o, lse, key_len if key_len is not None else q.new_empty(0))
+        ctx.meta = (n_head, scale, causal, key_len is not None)
+        return o
+
+    @staticmethod
+    def backward(ctx, do: Tensor):
+        q, k, v, o, lse, key_len = ctx.saved_tensors
+        n_head, scale, causal, has_len = ctx.meta
+        dq, dk, dv = K.fmha_bwd(q, k, v, o, do, lse, n_head, scale, key_len=key_len if has_len else None, causal=causal)
+        return dq, dk, dv, None, None, None, None
+
+
 def attention(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False) -> Tensor:
+    if q.dtype == torch.bfloat16 and q.shape[-1] == n_head * 64:
+        return _FusedAttention.apply(q, k, v, n_head, scale, key_len, causal)
     return _Attention.apply(q, k, v, n_head, scale, key_len, causal)
 
 

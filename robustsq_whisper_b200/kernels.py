@@ -279,6 +279,38 @@ def softmax_bwd(p: Tensor, dp: Tensor, rows: int, sk: int, scale: float, ld: Opt
     return dp
 
 
+def fmha_fwd(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False):
+    """Fused attention forward (bf16, head dim 64). q (B,Sq,d), k/v (B,Sk,d) contiguous -> o (B,Sq,d), lse (B,H,Sq) fp32."""
+    require_cuda(q, k, v, key_len)
+    lib = _C.load()
+    B, Sq, d = q.shape
+    Sk = k.shape[1]
+    if q.dtype != torch.bfloat16 or d != n_head * 64:
+        raise _C.TswError("fmha_fwd: bf16 and head dim 64 only")
+    o = torch.empty_like(q)
+    lse = torch.empty((B, n_head, Sq), dtype=torch.float32, device=q.device)
+    check(lib.tsw_fmha_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), B, n_head, Sq, Sk, q.stride(1), k.stride(1), v.stride(1), o.stride(1),
+                           scale, ptr(key_len), int(causal), stream()), "tsw_fmha_fwd")
+    _count(1)
+    return o, lse
+
+
+def fmha_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, do: Tensor, lse: Tensor, n_head: int, scale: float,
+             key_len: Optional[Tensor] = None, causal: bool = False):
+    """-> dq, dk, dv (bf16, shapes of q, k, v)."""
+    lib = _C.load()
+    B, Sq, d = q.shape
+    Sk = k.shape[1]
+    do = do.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ws = _ws(lib.tsw_fmha_bwd_workspace_bytes(B, n_head, Sq), q.device)
+    check(lib.tsw_fmha_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dq), ptr(dk), ptr(dv), B, n_head, Sq, Sk, q.stride(1),
+                           k.stride(1), v.stride(1), o.stride(1), do.stride(1), scale, ptr(key_len), int(causal), ptr(ws), ws.numel(),
+                           stream()), "tsw_fmha_bwd")
+    _count(4)
+    return dq, dk, dv
+
+
 def decoder_embed(E: Tensor, pos: Tensor, prompt: Tensor, ids: Tensor, sop: int, dtype: torch.dtype) -> Tensor:
     lib = _C.load()
     B, n_tok = ids.shape

@@ -438,3 +438,62 @@ def test_lsce_in_place_gradient(K):
     buf = logits.clone().cuda()
     ls, counts = K.lsce_fwd_bwd(buf, rows, V, V, tgt.cuda(), -1, 0.1, 1.0, buf, V)
     assert ls.item() == pytest.approx(ref.item(), rel=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ K3 fused attention
+def _attn_ref(q, k, v, H, scale, key_len=None, causal=False):
+    B, Sq, d = q.shape
+    Sk = k.shape[1]
+    qh, kh, vh = (t.float().view(B, -1, H, d // H).permute(0, 2, 1, 3) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2) * scale
+    if key_len is not None:
+        s = s.masked_fill(torch.arange(Sk)[None, None, None, :] >= key_len[:, None, None, None], float("-inf"))
+    if causal:
+        i = torch.arange(Sq)[:, None]
+        s = s.masked_fill(torch.arange(Sk)[None, :] > i + (Sk - Sq), float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    o = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B, Sq, d)
+    return o, lse
+
+
+FMHA_CASES = [
+    (2, 3, 150, 150, False, False),   # ragged single tile + tail
+    (2, 2, 300, 300, True, False),    # key padding
+    (2, 2, 260, 260, False, True),    # causal (decoder self-attention)
+    (3, 2, 16, 333, True, False),     # SQ-Former cross-attention: 16 queries
+    (2, 2, 107, 1516, False, False),  # decoder cross-attention
+    (1, 2, 1516, 1516, False, False), # encoder self-attention length
+]
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,use_len,causal", FMHA_CASES)
+def test_fmha_fwd(K, B, H, Sq, Sk, use_len, causal):
+    torch.manual_seed(18)
+    d = H * 64
+    q, k, v = ((torch.randn(B, S, d) * 0.8).bfloat16() for S in (Sq, Sk, Sk))
+    key_len = torch.tensor([Sk, max(1, Sk // 2 + 3), 7][:B], dtype=torch.int32) if use_len else None
+    scale = 0.125
+    o_ref, lse_ref = _attn_ref(q, k, v, H, scale, key_len, causal)
+    o, lse = K.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), H, scale, key_len=None if key_len is None else key_len.cuda(), causal=causal)
+    torch.cuda.synchronize()
+    assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
+    assert rel_err(o.float(), o_ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,use_len,causal", FMHA_CASES)
+def test_fmha_bwd(K, B, H, Sq, Sk, use_len, causal):
+    torch.manual_seed(19)
+    d = H * 64
+    q, k, v = ((torch.randn(B, S, d) * 0.8).bfloat16() for S in (Sq, Sk, Sk))
+    do = (torch.randn(B, Sq, d) * 0.5).bfloat16()
+    key_len = torch.tensor([Sk, max(1, Sk // 2 + 3), 7][:B], dtype=torch.int32) if use_len else None
+    scale = 0.125
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _attn_ref(qr, kr, vr, H, scale, key_len, causal)
+    o_ref.backward(do.float())
+    kl = None if key_len is None else key_len.cuda()
+    o, lse = K.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), H, scale, key_len=kl, causal=causal)
+    dq, dk, dv = K.fmha_bwd(q.cuda(), k.cuda(), v.cuda(), o, do.cuda(), lse, H, scale, key_len=kl, causal=causal)
+    torch.cuda.synchronize()
+    for got, ref, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
+        assert rel_err(got.float(), ref) < 2e-2, (name, rel_err(got.float(), ref))
