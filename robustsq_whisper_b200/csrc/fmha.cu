@@ -21,7 +21,7 @@ namespace tsw {
 constexpr int FQ = 128;   // queries per CTA (UMMA M)
 constexpr int FK = 128;   // keys per tile
 constexpr int FD = 64;    // head dim
-constexpr int F_THREADS = 192;
+constexpr int F_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two per TMEM lane quarter: 64 keys each)
 constexpr uint32_t kTileBytes = 128 * 128;  // 128 rows x 64 bf16 = 16 KB (one SW128 panel)
 
 struct FmhaParams {
@@ -33,6 +33,8 @@ struct FmhaParams {
   float* lse;             // (B, H, Sq) natural-log LSE of the scaled scores
 };
 
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t idesc_bf16(int m, int n, int a_mn, int b_mn) {
@@ -47,6 +49,29 @@ __device__ __forceinline__ int fmha_kv_limit(const FmhaParams& p, int b, int q0)
   return max(limit, 0);
 }
 
+
+// 32 scores of one row -> probabilities against the fixed reference: bf16 pairs for the P operand, running sum, raw max.
+template <bool MASKED>
+__device__ __forceinline__ void fwd_chunk(const float* v, float scale_log2, float m_ref, int first_key, int row_limit, uint32_t* pk,
+                                          float& lsum, float& tmax) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float a = v[i], b = v[i + 1];
+    float p0 = ex2_approx(fmaf(a, scale_log2, -m_ref));
+    float p1 = ex2_approx(fmaf(b, scale_log2, -m_ref));
+    if (MASKED) {
+      if (first_key + i >= row_limit) { p0 = 0.f; a = -INFINITY; }
+      if (first_key + i + 1 >= row_limit) { p1 = 0.f; b = -INFINITY; }
+    }
+    tmax = fmaxf(tmax, fmaxf(a, b));
+    s0 += p0; s1 += p1;
+    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+  }
+  lsum += s0 + s1;
+}
+
 struct FmhaFwdSmem {
   unsigned char q[kTileBytes];
   unsigned char k[2][kTileBytes];
@@ -54,6 +79,7 @@ struct FmhaFwdSmem {
   unsigned char p[2 * kTileBytes];  // 128 x 128 bf16 probabilities: two 64-key panels
   uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, p_full, o_full;
   uint32_t tmem_slot;
+  __nv_bfloat16 xmax[2][FQ];   // per-row partial maxima exchanged between the two threads of a row (rounded UP: any bound works)
 };
 
 __global__ void __launch_bounds__(F_THREADS, 2)
@@ -69,7 +95,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(&s.q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s.k_full[i], 1); mbar_init(&s.k_empty[i], 1); mbar_init(&s.v_full[i], 1); mbar_init(&s.v_empty[i], 1); }
-    mbar_init(&s.s_full, 1); mbar_init(&s.p_full, 4); mbar_init(&s.o_full, 1);
+    mbar_init(&s.s_full, 1); mbar_init(&s.p_full, 8); mbar_init(&s.o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(&s.tmem_slot);
@@ -100,15 +126,19 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0 && n_kv > 0) {
       const uint32_t id_s = idesc_bf16(FQ, FK, 0, 0);    // S = Q K^T : both K-major, N = 128
       const uint32_t id_pv = idesc_bf16(FQ, FD, 0, 1);   // PV       : P K-major, V MN-major ([key][dh]), N = 64
-      const uint32_t qa = smem_u32(s.q), pa = smem_u32(s.p);
+      // descriptors of the fixed buffers are built once; the issue loop only bumps their address field
+      const uint64_t dQ_ = make_smem_desc(smem_u32(s.q), 16, 1024);
+      const uint64_t dP0 = make_smem_desc(smem_u32(s.p), 16, 1024), dP1 = make_smem_desc(smem_u32(s.p) + kTileBytes, 16, 1024);
+      const uint64_t dK_[2] = {make_smem_desc(smem_u32(s.k[0]), 16, 1024), make_smem_desc(smem_u32(s.k[1]), 16, 1024)};
+      const uint64_t dV_[2] = {make_smem_desc(smem_u32(s.v[0]), kTileBytes, 1024), make_smem_desc(smem_u32(s.v[1]), kTileBytes, 1024)};
       auto issue_s = [&](int j) {
         const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
         mbar_wait(&s.k_full[st], ph);
         tc_fence_after();
-        const uint32_t ka = smem_u32(s.k[st]);
+        const uint64_t kd = dK_[st];
+        umma_bf16_c<false>(tmem_s, dQ_, kd, id_s);
 #pragma unroll
-        for (int k = 0; k < FD / 16; ++k)
-          umma_bf16(tmem_s, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), id_s, k > 0);
+        for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(tmem_s, desc_advance(dQ_, k * 32), desc_advance(kd, k * 32), id_s);
         umma_commit(&s.s_full);
         umma_commit(&s.k_empty[st]);
       };
@@ -119,99 +149,112 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s.p_full, j & 1);   // probabilities of tile j are in smem; S and PV TMEM have been drained
         mbar_wait(&s.v_full[st], ph);
         tc_fence_after();
-        const uint32_t va = smem_u32(s.v[st]);
+        const uint64_t vd = dV_[st];
+        umma_bf16_c<false>(tmem_pv, dP0, vd, id_pv);
 #pragma unroll
-        for (int k = 0; k < FK / 16; ++k)
-          umma_bf16(tmem_pv, make_smem_desc(pa + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024),
-                    make_smem_desc(va + k * 2048, kTileBytes, 1024), id_pv, k > 0);
+        for (int k = 1; k < FK / 16; ++k)
+          umma_bf16_c<true>(tmem_pv, desc_advance(k < 4 ? dP0 : dP1, (k & 3) * 32), desc_advance(vd, k * 2048), id_pv);
         umma_commit(&s.o_full);
         umma_commit(&s.v_empty[st]);
         if (j + 1 < n_kv) issue_s(j + 1);  // next S overlaps the softmax warps' output update
       }
     }
   } else {
-    // ===================================================== softmax + output, thread = query row
+    // ===================================================== softmax + output: thread = (query row, 64-key half)
     const int quarter = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float o[FD];
+    float o[32];   // output columns [hf*32, hf*32 + 32) of this row
 #pragma unroll
-    for (int i = 0; i < FD; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    // Lazy running maximum: tile j is exponentiated against the reference m_ref fixed BEFORE the tile (exact for tile 0,
+    // where S is read twice), so S leaves TMEM once per tile and no row-wide exchange sits between the MMA and the
+    // exponentials.  The reference moves (and o, l are rescaled) only after a tile whose maximum exceeded it by > 2^8 —
+    // probabilities up to 256 are harmless in bf16 / fp32; the final division by l removes the common factor.
+    float m_ref = -INFINITY, l_part = 0.f;
     int row_limit = limit;
     if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s.s_full, j & 1);
       tc_fence_after();
-      const int kbase = j * FK;
-      // pass 1: row maximum of the visible scores of this tile
-      float mx = m_run;
+      const int kb = j * FK + hf * 64;                 // first key of this thread's half
+      const bool full = kb + 64 <= row_limit;          // no masking needed
+      if (j == 0) {                                    // exact maximum of the first tile -> initial reference
+        float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < FK; c += 32) {
-        float v[32];
-        tmem_ld32(tmem_s + lane_off + c, v);
+        for (int c = 0; c < 64; c += 32) {
+          float v[32];
+          tmem_ld32(tmem_s + lane_off + hf * 64 + c, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (kbase + c + i < row_limit) mx = fmaxf(mx, v[i] * p.scale_log2);
-      }
-      const float m_new = mx;
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);   // m_run = -inf on the first tile -> 0
-      float lsum = 0.f;
-      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
-#pragma unroll 1
-      for (int c = 0; c < FK; c += 32) {
-        float v[32];
-        tmem_ld32(tmem_s + lane_off + c, v);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (kbase + c + i < row_limit) ? exp2f(fmaf(v[i], p.scale_log2, -m_use)) : 0.f;
-          const float p1 = (kbase + c + i + 1 < row_limit) ? exp2f(fmaf(v[i + 1], p.scale_log2, -m_use)) : 0.f;
-          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          // accumulate the row sum from the ROUNDED probabilities so that P V / l is a true convex combination
-          const float2 pr = __bfloat1622float2(pb);
-          lsum += pr.x + pr.y;
-          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+          for (int i = 0; i < 32; ++i) if (full || kb + c + i < row_limit) mx = fmaxf(mx, v[i]);
         }
-        unsigned char* panel = s.p + (c >> 6) * kTileBytes + r * 128;
+        const __nv_bfloat16 mxb = __float2bfloat16_ru(mx);   // both threads of the row must agree bit-for-bit
+        s.xmax[hf][r] = mxb;
+        named_bar_sync(1, 256);
+        m_ref = fmaxf(__bfloat162float(mxb), __bfloat162float(s.xmax[hf ^ 1][r])) * p.scale_log2;
+        if (m_ref == -INFINITY) m_ref = 0.f;
+      }
+      float lsum = 0.f, tmax = -INFINITY;
+      unsigned char* prow = s.p + hf * kTileBytes + r * 128;
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_s + lane_off + hf * 64 + c, v);
+        uint32_t pk[16];
+        if (full) fwd_chunk<false>(v, p.scale_log2, m_ref, kb + c, row_limit, pk, lsum, tmax);
+        else fwd_chunk<true>(v, p.scale_log2, m_ref, kb + c, row_limit, pk, lsum, tmax);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int u = ((c & 63) >> 3) + t;  // 16-byte unit inside the 128-byte row of this panel
-          *reinterpret_cast<uint4*>(panel + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          const int u = (c >> 3) + t;  // 16-byte unit inside this row of the panel
+          *reinterpret_cast<uint4*>(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
         }
       }
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      // fold the previous tiles' rescale into o BEFORE handing P to the tensor core? no: o holds tiles < j, rescale now
-#pragma unroll
-      for (int i = 0; i < FD; ++i) o[i] *= alpha;
+      l_part += lsum;
+      s.xmax[hf][r] = __float2bfloat16_ru(tmax);   // read by the partner after p_full / o_full below (ordered by the barriers)
       fence_async_smem();     // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s.p_full);
-      // accumulate P V of this tile
+      // accumulate P V of this tile (this thread's 32 output columns)
       mbar_wait(&s.o_full, j & 1);
       tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < FD; c += 32) {
+      {
         float v[32];
-        tmem_ld32(tmem_pv + lane_off + c, v);
+        tmem_ld32(tmem_pv + lane_off + hf * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] += v[i];
+        for (int i = 0; i < 32; ++i) o[i] += v[i];
+      }
+      // move the reference if this tile overshot it by more than 2^8 (both threads of the row take the same decision:
+      // o_full implies every softmax warp has passed p_full, i.e. has published its xmax)
+      const float m_tile = fmaxf(__bfloat162float(s.xmax[0][r]), __bfloat162float(s.xmax[1][r])) * p.scale_log2;
+      named_bar_sync(1, 256);                        // xmax is rewritten in the next tile
+      if (m_tile > m_ref + 8.f) {
+        const float alpha = ex2_approx(m_ref - m_tile);
+        l_part *= alpha;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= alpha;
+        m_ref = m_tile;
       }
     }
+    const float m_run = m_ref;
+    // total row sum = sum of the two halves (same running maximum on both sides)
+    float* lx = reinterpret_cast<float*>(s.p);   // the P buffer is free once the last P V has completed (o_full)
+    lx[hf * FQ + r] = l_part;
+    named_bar_sync(1, 256);
+    const float l_run = l_part + lx[(hf ^ 1) * FQ + r];
     if (qi < p.Sq) {
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* orow = p.o + ((int64_t)b * p.Sq + qi) * p.ldo + h * FD;
+      __nv_bfloat16* orow = p.o + ((int64_t)b * p.Sq + qi) * p.ldo + h * FD + hf * 32;
 #pragma unroll
-      for (int c = 0; c < FD; c += 8) {
+      for (int c = 0; c < 32; c += 8) {
         float t[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) t[i] = o[c + i] * inv;
         Vec<__nv_bfloat16>::store(orow + c, t);
       }
-      p.lse[((int64_t)b * p.H + h) * p.Sq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.69314718055994530942f : -INFINITY;
+      if (hf == 0) p.lse[((int64_t)b * p.H + h) * p.Sq + qi] = l_run > 0.f ? (m_run + log2f(l_run)) * 0.69314718055994530942f : -INFINITY;
     }
     tc_fence_before();
   }
@@ -227,7 +270,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 //   dV += P^T dO, dK += dS^T Q        -> TMEM accumulators over the whole loop (lanes = keys); P / dS are MN-major A operands
 //   dQ_i = dS K                       -> TMEM, staged to smem as fp32 and added into the fp32 dQ buffer with one
 //                                        cp.reduce.async.bulk.tensor (.add) per 32-column panel — no per-thread atomics.
-constexpr int FB_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax/gradient
+constexpr int FB_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2-17 softmax/gradient (four per TMEM lane quarter: 32 keys each)
 
 struct FmhaBwdParams {
   int B, H, Sq, Sk;
@@ -238,6 +281,22 @@ struct FmhaBwdParams {
   const float* delta;  // (B, H, Sq) rowsum(dO * O)
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
 };
+
+
+template <bool MASKED>
+__device__ __forceinline__ void bwd_chunk(const float* sv, const float* dpv, float scale_log2, float lse2, float scale, float dlt_s,
+                                          int first_key, int row_limit, uint32_t* pk, uint32_t* dk_) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float p0 = ex2_approx(fmaf(sv[i], scale_log2, -lse2));
+    float p1 = ex2_approx(fmaf(sv[i + 1], scale_log2, -lse2));
+    if (MASKED) { if (first_key + i >= row_limit) p0 = 0.f; if (first_key + i + 1 >= row_limit) p1 = 0.f; }
+    const float d0 = p0 * fmaf(dpv[i], scale, -dlt_s), d1 = p1 * fmaf(dpv[i + 1], scale, -dlt_s);   // P (dP - delta) scale
+    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1), db = __floats2bfloat162_rn(d0, d1);
+    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+    dk_[i >> 1] = *reinterpret_cast<const uint32_t*>(&db);
+  }
+}
 
 struct FmhaBwdSmem {
   unsigned char k[kTileBytes];
@@ -258,7 +317,6 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const v
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // first / one-past-last query tile that can see key tile kv0 (causal) 
 __device__ __forceinline__ void fmha_q_range(const FmhaBwdParams& p, int kv0, int* qt0, int* qt1) {
@@ -291,7 +349,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     mbar_init(&s.kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
-    mbar_init(&s.s_full, 1); mbar_init(&s.pds_full, 8); mbar_init(&s.dq_full, 1);
+    mbar_init(&s.s_full, 1); mbar_init(&s.pds_full, 16); mbar_init(&s.dq_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
@@ -319,17 +377,26 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t id_g = idesc_bf16(128, 64, 1, 1);    // dV, dK: A = P^T / dS^T (MN-major), B = dO / Q (MN-major), N = 64
       const uint32_t id_q = idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major over keys), B = K tile (MN-major), N = 64
       const uint32_t ka = smem_u32(s.k), va = smem_u32(s.v), pa = smem_u32(s.p), dsa = smem_u32(s.ds);
+      // descriptors built once; the issue loop only bumps the address field
+      const uint64_t dK_k = make_smem_desc(ka, 16, 1024), dV_k = make_smem_desc(va, 16, 1024);          // K-major views (S, dP)
+      const uint64_t dK_mn = make_smem_desc(ka, kTileBytes, 1024);                                        // MN-major view (dQ)
+      const uint64_t dP_mn = make_smem_desc(pa, kTileBytes, 1024), dS_mn = make_smem_desc(dsa, kTileBytes, 1024);
+      const uint64_t dS_k0 = make_smem_desc(dsa, 16, 1024), dS_k1 = make_smem_desc(dsa + kTileBytes, 16, 1024);
+      const uint64_t dQ_k[2] = {make_smem_desc(smem_u32(s.q[0]), 16, 1024), make_smem_desc(smem_u32(s.q[1]), 16, 1024)};
+      const uint64_t dQ_mn[2] = {make_smem_desc(smem_u32(s.q[0]), kTileBytes, 1024), make_smem_desc(smem_u32(s.q[1]), kTileBytes, 1024)};
+      const uint64_t dO_k[2] = {make_smem_desc(smem_u32(s.dO[0]), 16, 1024), make_smem_desc(smem_u32(s.dO[1]), 16, 1024)};
+      const uint64_t dO_mn[2] = {make_smem_desc(smem_u32(s.dO[0]), kTileBytes, 1024), make_smem_desc(smem_u32(s.dO[1]), kTileBytes, 1024)};
       auto issue_scores = [&](int it) {
         const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&s.q_full[st], ph);
         tc_fence_after();
-        const uint32_t qa = smem_u32(s.q[st]), doa = smem_u32(s.dO[st]);
+        const uint64_t qd = dQ_k[st], od = dO_k[st];
+        umma_bf16_c<false>(t_s, qd, dK_k, id_s);
 #pragma unroll
-        for (int k = 0; k < FD / 16; ++k)
-          umma_bf16(t_s, make_smem_desc(qa + k * 32, 16, 1024), make_smem_desc(ka + k * 32, 16, 1024), id_s, k > 0);
+        for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_s, desc_advance(qd, k * 32), desc_advance(dK_k, k * 32), id_s);
+        umma_bf16_c<false>(t_dp, od, dV_k, id_s);
 #pragma unroll
-        for (int k = 0; k < FD / 16; ++k)
-          umma_bf16(t_dp, make_smem_desc(doa + k * 32, 16, 1024), make_smem_desc(va + k * 32, 16, 1024), id_s, k > 0);
+        for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_dp, desc_advance(od, k * 32), desc_advance(dV_k, k * 32), id_s);
         umma_commit(&s.s_full);
       };
       mbar_wait(&s.kv_full, 0);
@@ -338,67 +405,69 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int st = it & 1;
         mbar_wait(&s.pds_full, it & 1);   // P, dS in smem; S, dP and dQ TMEM drained
         tc_fence_after();
-        const uint32_t qa = smem_u32(s.q[st]), doa = smem_u32(s.dO[st]);
+        const uint64_t qd = dQ_mn[st], od = dO_mn[st];
+        // dV += P^T dO, dK += dS^T Q: reduction over the 128 queries, 16 per instruction (2048 B per step in both operands)
+        if (it == 0) umma_bf16_c<false>(t_dv, dP_mn, od, id_g); else umma_bf16_c<true>(t_dv, dP_mn, od, id_g);
 #pragma unroll
-        for (int k = 0; k < FQ / 16; ++k) {  // reduction over the 128 queries, 16 per instruction
-          // A (MN-major): [q][key] rows of 128 B per 64-key panel -> LBO = panel stride, 16 q-rows = 2048 B per step
-          umma_bf16(t_dv, make_smem_desc(pa + k * 2048, kTileBytes, 1024), make_smem_desc(doa + k * 2048, kTileBytes, 1024), id_g, (it | k) != 0);
-        }
+        for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dv, desc_advance(dP_mn, k * 2048), desc_advance(od, k * 2048), id_g);
+        if (it == 0) umma_bf16_c<false>(t_dk, dS_mn, qd, id_g); else umma_bf16_c<true>(t_dk, dS_mn, qd, id_g);
 #pragma unroll
-        for (int k = 0; k < FQ / 16; ++k)
-          umma_bf16(t_dk, make_smem_desc(dsa + k * 2048, kTileBytes, 1024), make_smem_desc(qa + k * 2048, kTileBytes, 1024), id_g, (it | k) != 0);
+        for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dk, desc_advance(dS_mn, k * 2048), desc_advance(qd, k * 2048), id_g);
+        // dQ_i = dS K: reduction over the 128 keys
+        umma_bf16_c<false>(t_dq, dS_k0, dK_mn, id_q);
 #pragma unroll
-        for (int k = 0; k < FK / 16; ++k)    // reduction over the 128 keys
-          umma_bf16(t_dq, make_smem_desc(dsa + (k >> 2) * kTileBytes + (k & 3) * 32, 16, 1024), make_smem_desc(ka + k * 2048, kTileBytes, 1024), id_q, k > 0);
+        for (int k = 1; k < FK / 16; ++k)
+          umma_bf16_c<true>(t_dq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
         umma_commit(&s.dq_full);
         umma_commit(&s.q_empty[st]);
         if (it + 1 < n_it) issue_scores(it + 1);
       }
     }
   } else {
-    // ===================================================== P / dS, dQ staging, final dK / dV   (warps 2..9)
+    // ===================================================== P / dS, dQ staging, final dK / dV   (warps 2..17)
     const int quarter = warp & 3;          // TMEM lane quarter
-    const int half = (warp - 2) >> 2;      // which 64-key (and 32-dQ-column) half this warp handles
+    const int part = (warp - 2) >> 2;      // which 32-key slice (and 16-column slice of dQ / dK / dV) this warp handles
     const int r = quarter * 32 + lane;     // row inside the tile (query row in the loop, key row at the end)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     const bool leader = (warp == 2 && lane == 0);
+    const int c0 = part * 32;              // first key column of the slice
+    const int poff = (part >> 1) * kTileBytes + r * 128;   // 64-key panel + row
+    const int ubase = (part & 1) * 4;      // first 16-byte unit of the slice inside the 128-byte panel row
+    auto load_stats = [&](int it, float& lse_nat, float& dl) {
+      const int qn = (qt0 + it) * FQ + r;
+      lse_nat = -INFINITY; dl = 0.f;
+      if (it < n_it && qn < p.Sq) {
+        const int64_t idx = ((int64_t)b * p.H + h) * p.Sq + qn;
+        lse_nat = __ldg(p.lse + idx); dl = __ldg(p.delta + idx);
+      }
+    };
+    float lse_next, dlt_next;
+    load_stats(0, lse_next, dlt_next);
     for (int it = 0; it < n_it; ++it) {
       const int q0 = (qt0 + it) * FQ;
       const int qi = q0 + r;
-      float lse2 = 0.f, dlt = 0.f;
+      const float lse2 = lse_next * 1.44269504088896340736f, dlt = dlt_next;
+      load_stats(it + 1, lse_next, dlt_next);   // in flight during this iteration
       int row_limit = 0;
-      if (qi < p.Sq) {
-        const int64_t idx = ((int64_t)b * p.H + h) * p.Sq + qi;
-        lse2 = p.lse[idx] * 1.44269504088896340736f;
-        dlt = p.delta[idx];
+      if (qi < p.Sq && lse2 > -INFINITY) {
         row_limit = klimit;
         if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
-        if (!(lse2 > -INFINITY)) row_limit = 0;
       }
+      const bool full = kv0 + c0 + 32 <= row_limit;
       mbar_wait(&s.s_full, it & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = half * 64; c < half * 64 + 64; c += 32) {
+      {
         float sv[32], dpv[32];
-        tmem_ld32(t_s + lane_off + c, sv);
-        tmem_ld32(t_dp + lane_off + c, dpv);
+        tmem_ld32(t_s + lane_off + c0, sv);
+        tmem_ld32(t_dp + lane_off + c0, dpv);
         uint32_t pk[16], dk_[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const bool ok0 = kv0 + c + i < row_limit, ok1 = kv0 + c + i + 1 < row_limit;
-          const float p0 = ok0 ? exp2f(fmaf(sv[i], p.scale_log2, -lse2)) : 0.f;
-          const float p1 = ok1 ? exp2f(fmaf(sv[i + 1], p.scale_log2, -lse2)) : 0.f;
-          const float d0 = p0 * (dpv[i] - dlt) * p.scale, d1 = p1 * (dpv[i + 1] - dlt) * p.scale;
-          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1), db = __floats2bfloat162_rn(d0, d1);
-          pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-          dk_[i >> 1] = *reinterpret_cast<const uint32_t*>(&db);
-        }
-        const int off = (c >> 6) * kTileBytes + r * 128;
+        if (full) bwd_chunk<false>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
+        else bwd_chunk<true>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          const int u = (((c & 63) >> 3) + t) ^ (r & 7);
-          *reinterpret_cast<uint4*>(s.p + off + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-          *reinterpret_cast<uint4*>(s.ds + off + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
+          const int u = (ubase + t) ^ (r & 7);
+          *reinterpret_cast<uint4*>(s.p + poff + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          *reinterpret_cast<uint4*>(s.ds + poff + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
         }
       }
       fence_async_smem();
@@ -409,18 +478,18 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&s.dq_full, it & 1);
       tc_fence_after();
       if (leader) bulk_wait_read0();            // the previous reduce has finished reading the staging buffer
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       {
-        float v[32];
-        tmem_ld32(t_dq + lane_off + half * 32, v);
-        unsigned char* row = s.dq + half * kTileBytes + r * 128;
+        float v[16];
+        tmem_ld16(t_dq + lane_off + part * 16, v);
+        unsigned char* row = s.dq + poff;      // 32-column fp32 panel (part >> 1), this row
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          *reinterpret_cast<float4*>(row + ((t ^ (r & 7)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+        for (int t = 0; t < 4; ++t)
+          *reinterpret_cast<float4*>(row + (((ubase + t) ^ (r & 7)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
       }
       fence_async_smem();
       tc_fence_before();
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       if (leader) {
         tma_reduce_add_4d(&tmdQ, s.dq, h * FD, q0, b, 0);
         tma_reduce_add_4d(&tmdQ, s.dq + kTileBytes, h * FD + 32, q0, b, 0);
@@ -430,19 +499,19 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ---- dK, dV of this key tile (lanes = keys); inactive tiles write zeros
     const int key = kv0 + r;
     if (active) { mbar_wait(&s.dq_full, (n_it - 1) & 1); tc_fence_after(); }  // all MMAs of the last iteration have completed
-    float gv[32], gk[32];
+    float gv[16], gk[16];
     if (active) {
-      tmem_ld32(t_dv + lane_off + half * 32, gv);
-      tmem_ld32(t_dk + lane_off + half * 32, gk);
+      tmem_ld16(t_dv + lane_off + part * 16, gv);
+      tmem_ld16(t_dk + lane_off + part * 16, gk);
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) gv[i] = gk[i] = 0.f;
+      for (int i = 0; i < 16; ++i) gv[i] = gk[i] = 0.f;
     }
     if (key < p.Sk) {
-      __nv_bfloat16* dvrow = p.dv + ((int64_t)b * p.Sk + key) * p.lddv + h * FD + half * 32;
-      __nv_bfloat16* dkrow = p.dk + ((int64_t)b * p.Sk + key) * p.lddk + h * FD + half * 32;
+      __nv_bfloat16* dvrow = p.dv + ((int64_t)b * p.Sk + key) * p.lddv + h * FD + part * 16;
+      __nv_bfloat16* dkrow = p.dk + ((int64_t)b * p.Sk + key) * p.lddk + h * FD + part * 16;
 #pragma unroll
-      for (int c = 0; c < 32; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
+      for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
     }
     if (leader) bulk_wait0();   // the last reduce must be complete before the CTA (and its smem) goes away
     tc_fence_before();
