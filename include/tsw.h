@@ -67,11 +67,13 @@ int tsw_logmel_fwd(const float* audio, int64_t batch, int64_t n_samples, int64_t
  *
  * A is stored [M][K] (a_mn_major = 0, "K-major") or [K][M] (a_mn_major = 1); B is stored [N][K] (b_mn_major = 0,
  * the nn.Linear weight layout) or [K][N] (b_mn_major = 1).  D, residual and aux are stored [M][N].
- * Epilogue order: v = alpha*acc (+ bias[n]) ; if aux_out: aux_out = v ; v = act(v) | v * gelu'(aux_in) ;
+ * Epilogue order: v = alpha*acc (+ bias[n]) ; if aux_out: aux_out = v (gelu'(v) for GELU_SAVE_GRAD) ; v = act(v) | v * gelu'(aux_in) | v * aux_in ;
  * (+ residual[(m % res_row_mod)][n]) ; (+ D if beta != 0) ; D = v.
  * impl: 0 = auto (tcgen05 for bf16 operands that satisfy TMA alignment, else SIMT), 1 = SIMT fp32-accumulate
  * kernel, 2 = tcgen05/TMEM/TMA kernel (fails if unsupported). */
-enum { TSW_EPI_NONE = 0, TSW_EPI_GELU = 1, TSW_EPI_MUL_DGELU = 2 };
+enum { TSW_EPI_NONE = 0, TSW_EPI_GELU = 1, TSW_EPI_MUL_DGELU = 2,
+       TSW_EPI_GELU_SAVE_GRAD = 3, /* D = gelu(v), aux_out = gelu'(v)  (forward of an MLP that will be differentiated) */
+       TSW_EPI_MUL_AUX = 4         /* D = v * aux_in               (its backward: one multiply instead of erf/exp) */ };
 enum { TSW_GEMM_AUTO = 0, TSW_GEMM_SIMT = 1, TSW_GEMM_TCGEN05 = 2 };
 
 typedef struct {

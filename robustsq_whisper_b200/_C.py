@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtsw_sm100.so")
 
 F32, BF16 = 0, 1
-EPI_NONE, EPI_GELU, EPI_MUL_DGELU = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_MUL_DGELU, EPI_GELU_SAVE_GRAD, EPI_MUL_AUX = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 
 

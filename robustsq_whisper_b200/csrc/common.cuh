@@ -97,6 +97,21 @@ __device__ __forceinline__ float dgelu_fast(float x) {
   return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), cdf);
 }
 
+// gelu(x) and gelu'(x) from one erf evaluation: the exp(-x^2/2) inside erf_fast is the Gaussian density gelu' needs
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& dg) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float ex = __expf(-ax * ax);                 // exp(-x^2 / 2)
+  const float cdf = 0.5f * (1.f + copysignf(1.f - p * t * ex, x));
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, ex, cdf);
+}
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& dg) { g = gelu_f(x); dg = dgelu_f(x); }
+
 // 8 x bf16 <-> 8 x f32 through one 16-byte access
 struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
 

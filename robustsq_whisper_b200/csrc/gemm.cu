@@ -14,8 +14,8 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   TSW_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0 && g.batch_outer >= 1 && g.batch_inner >= 1, "gemm: bad sizes M=%lld N=%lld K=%lld", (long long)g.M, (long long)g.N, (long long)g.K);
   TSW_CHECK_ARG((g.a_dtype | 1) == 1 && (g.b_dtype | 1) == 1 && (g.d_dtype | 1) == 1, "gemm: bad dtype");
   TSW_CHECK_ARG(g.lda >= (g.a_mn_major ? g.M : g.K) && g.ldb >= (g.b_mn_major ? g.N : g.K) && g.ldd >= g.N, "gemm: leading dimension too small");
-  TSW_CHECK_ARG(g.epilogue >= TSW_EPI_NONE && g.epilogue <= TSW_EPI_MUL_DGELU, "gemm: bad epilogue");
-  TSW_CHECK_ARG(g.epilogue != TSW_EPI_MUL_DGELU || g.aux_in, "gemm: MUL_DGELU needs aux_in");
+  TSW_CHECK_ARG(g.epilogue >= TSW_EPI_NONE && g.epilogue <= TSW_EPI_MUL_AUX, "gemm: bad epilogue");
+  TSW_CHECK_ARG((g.epilogue != TSW_EPI_MUL_DGELU && g.epilogue != TSW_EPI_MUL_AUX) || g.aux_in, "gemm: MUL_DGELU / MUL_AUX need aux_in");
   TSW_CHECK_ARG(!g.residual || (g.res_dtype == g.d_dtype && g.ldres >= g.N), "gemm: residual must have the output dtype");
   TSW_CHECK_ARG(g.beta == 0.f || g.beta == 1.f, "gemm: beta must be 0 or 1");
 

@@ -43,10 +43,22 @@ __device__ __forceinline__ void epi_store4(const EpiParams& p, float4 acc, int64
   float v[4] = {alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w};
   if (p.vec4_ok && n + 4 <= p.N) {
     if (p.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n)); v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w; }
-    if (aout) store4(aout + n, v);
+    if (p.epilogue == TSW_EPI_GELU_SAVE_GRAD) {
+      float dg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gelu_and_grad(v[j], v[j], dg[j]);
+      if (aout) store4(aout + n, dg);
+    } else if (aout) {
+      store4(aout + n, v);
+    }
     if (p.epilogue == TSW_EPI_GELU) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = gelu_f(v[j]);
+    } else if (p.epilogue == TSW_EPI_MUL_AUX) {
+      float a[4];
+      load4(ain + n, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] *= a[j];
     } else if (p.epilogue == TSW_EPI_MUL_DGELU) {
       float a[4];
       load4(ain + n, a);
@@ -72,8 +84,10 @@ __device__ __forceinline__ void epi_store4(const EpiParams& p, float4 acc, int64
       if (n + j < p.N) {
         float x = v[j];
         if (p.bias) x += p.bias[n + j];
-        if (aout) aout[n + j] = from_f32<DT>(x);
+        if (p.epilogue == TSW_EPI_GELU_SAVE_GRAD) { float dg; gelu_and_grad(x, x, dg); if (aout) aout[n + j] = from_f32<DT>(dg); }
+        else if (aout) aout[n + j] = from_f32<DT>(x);
         if (p.epilogue == TSW_EPI_GELU) x = gelu_f(x);
+        else if (p.epilogue == TSW_EPI_MUL_AUX) x *= to_f32(ain[n + j]);
         else if (p.epilogue == TSW_EPI_MUL_DGELU) x *= dgelu_f(to_f32(ain[n + j]));
         if (rrowp) x += to_f32(rrowp[n + j]);
         if (p.beta != 0.f) x += p.beta * to_f32(drow[n + j]);
@@ -108,10 +122,22 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, const float* acc, 
 #pragma unroll
         for (int j = 0; j < VN; ++j) v[j] += __ldg(p.bias + n + j);
       }
-      if (aout) Vec<DT>::store(aout + n, v);
+      if (p.epilogue == TSW_EPI_GELU_SAVE_GRAD) {
+        float dg[VN];
+#pragma unroll
+        for (int j = 0; j < VN; ++j) gelu_and_grad(v[j], v[j], dg[j]);
+        if (aout) Vec<DT>::store(aout + n, dg);
+      } else if (aout) {
+        Vec<DT>::store(aout + n, v);
+      }
       if (p.epilogue == TSW_EPI_GELU) {
 #pragma unroll
         for (int j = 0; j < VN; ++j) v[j] = gelu_f(v[j]);
+      } else if (p.epilogue == TSW_EPI_MUL_AUX) {
+        float a[VN];
+        Vec<DT>::load(ain + n, a);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) v[j] *= a[j];
       } else if (p.epilogue == TSW_EPI_MUL_DGELU) {
         float a[VN];
         Vec<DT>::load(ain + n, a);
@@ -137,8 +163,10 @@ __device__ __forceinline__ void epi_store(const EpiParams& p, const float* acc, 
         if (n + j < p.N) {
           float x = v[j];
           if (p.bias) x += p.bias[n + j];
-          if (aout) aout[n + j] = from_f32<DT>(x);
+          if (p.epilogue == TSW_EPI_GELU_SAVE_GRAD) { float dg; gelu_and_grad(x, x, dg); if (aout) aout[n + j] = from_f32<DT>(dg); }
+          else if (aout) aout[n + j] = from_f32<DT>(x);
           if (p.epilogue == TSW_EPI_GELU) x = gelu_f(x);
+          else if (p.epilogue == TSW_EPI_MUL_AUX) x *= to_f32(ain[n + j]);
           else if (p.epilogue == TSW_EPI_MUL_DGELU) x *= dgelu_f(to_f32(ain[n + j]));
           if (rrowp) x += to_f32(rrowp[n + j]);
           if (p.beta != 0.f) x += p.beta * to_f32(drow[n + j]);

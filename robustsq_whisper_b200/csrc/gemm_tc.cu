@@ -227,7 +227,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // The extra operand of the fused epilogue (residual | GELU' input | old D) is fetched for all 8 rows up front
           // as raw 8/16-byte words through the read-only path, so the loads overlap instead of queueing behind stores.
           typename RawVec<DT>::type pre[8];
-          const int which = !GENERIC ? 0 : Rp ? 1 : (ep.epilogue == TSW_EPI_MUL_DGELU) ? 2 : (ep.beta != 0.f) ? 3 : 0;
+          const bool mul_in = ep.epilogue == TSW_EPI_MUL_DGELU || ep.epilogue == TSW_EPI_MUL_AUX;
+          const int which = !GENERIC ? 0 : Rp ? 1 : mul_in ? 2 : (ep.beta != 0.f) ? 3 : 0;
           if (GENERIC && which != 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -248,15 +249,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (GENERIC) {
                 float ex[4] = {0.f, 0.f, 0.f, 0.f};
                 if (which != 0) RawVec<DT>::unpack(pre[i], ex);
-                if (AOp) store4(AOp + off, o);
+                if (ep.epilogue == TSW_EPI_GELU_SAVE_GRAD) {
+                  float dg[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) gelu_and_grad_fast(o[j], o[j], dg[j]);
+                  if (AOp) store4(AOp + off, dg);
+                } else if (AOp) {
+                  store4(AOp + off, o);
+                }
                 if (ep.epilogue == TSW_EPI_GELU) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) o[j] = gelu_fast(o[j]);
-                } else if (ep.epilogue == TSW_EPI_MUL_DGELU) {
+                } else if (mul_in) {
                   float ai[4];
                   if (which == 2) { ai[0] = ex[0]; ai[1] = ex[1]; ai[2] = ex[2]; ai[3] = ex[3]; } else load4(AIp + off, ai);
+                  if (ep.epilogue == TSW_EPI_MUL_AUX) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) o[j] *= dgelu_fast(ai[j]);
+                    for (int j = 0; j < 4; ++j) o[j] *= ai[j];
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] *= dgelu_fast(ai[j]);
+                  }
                 }
                 if (which == 1) {
 #pragma unroll

@@ -152,7 +152,7 @@ __global__ void colreduce_kernel(const float* __restrict__ partial, int nparts, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t n, int64_t ld, int64_t rows_per_chunk,
-                      float* __restrict__ partial, int vec_ok) {
+                      float* __restrict__ partial, int vec_ok, float* __restrict__ out, unsigned int* __restrict__ counters) {
   constexpr int VN = Vec<T>::N;
   __shared__ float sm[8][32 * VN + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -194,6 +194,24 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t n, int64_t 
       for (int k = 0; k < 8; ++k) t += sm[k][c];
       partial[(int64_t)blockIdx.y * n + col] = t;
     }
+  }
+  // the last CTA of this column block to finish folds the row-chunk partials (fixed order -> deterministic sums)
+  __shared__ unsigned int ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(&counters[blockIdx.x], 1u);
+  __syncthreads();
+  if (ticket == gridDim.y - 1) {
+    __threadfence();
+    for (int c = threadIdx.x; c < 32 * VN; c += 256) {
+      const int64_t col = (int64_t)blockIdx.x * 32 * VN + c;
+      if (col < n) {
+        float t = 0.f;
+        for (unsigned int k = 0; k < gridDim.y; ++k) t += __ldcg(partial + (int64_t)k * n + col);
+        out[col] = t;
+      }
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;  // self-resetting for the next call
   }
 }
 
@@ -446,6 +464,20 @@ extern "C" int tsw_cast(const void* src, int src_dtype, void* dst, int dst_dtype
   return TSW_OK;
 }
 
+constexpr int kMaxColBlocks = 8192;
+static unsigned int* colsum_counters() {  // one zero-initialised ticket array per device, reused (self-resetting) by every call
+  static unsigned int* ptrs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
+  if (!ptrs[dev]) {
+    unsigned int* p = nullptr;
+    if (cudaMalloc(&p, sizeof(unsigned int) * kMaxColBlocks) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(unsigned int) * kMaxColBlocks);
+    ptrs[dev] = p;
+  }
+  return ptrs[dev];
+}
+
 static int64_t colsum_chunks(int64_t rows, int64_t n, int vn) {
   const int64_t col_blocks = (n + 32 * vn - 1) / (32 * vn);
   int64_t chunks = std::max<int64_t>(1, ((int64_t)sm_count() * 8) / col_blocks);
@@ -464,9 +496,9 @@ extern "C" int tsw_colsum(const void* x, int dtype, int64_t rows, int64_t n, int
   dim3 grid((unsigned)((n + 32 * vn - 1) / (32 * vn)), (unsigned)chunks);
   float* partial = (float*)workspace;
   const int vec_ok = aligned16(x) && ld % vn == 0;
-  DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, rows, n, ld, rpc, partial, vec_ok)));
-  TSW_LAUNCH_CHECK();
-  colreduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(partial, (int)chunks, n, out, out, n);
+  unsigned int* counters = colsum_counters();
+  TSW_CHECK_ARG(counters && grid.x <= (unsigned)kMaxColBlocks, "colsum: ticket buffer unavailable / too many columns");
+  DISPATCH_T(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, rows, n, ld, rpc, partial, vec_ok, out, counters)));
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }

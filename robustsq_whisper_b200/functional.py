@@ -136,7 +136,8 @@ class _MLP(Function):
         dt = x.dtype
         impl = _impl_for(dt)
         h = torch.empty((rows, H), dtype=dt, device=x.device)
-        g = K.gemm(x2, shadow(w1, dt), M=rows, N=H, K=d, bias=b1.detach(), aux_out=h, epilogue=_C.EPI_GELU, out_dtype=dt, impl=impl)
+        # h receives gelu'(pre-activation): backward becomes one multiply in the dgrad epilogue
+        g = K.gemm(x2, shadow(w1, dt), M=rows, N=H, K=d, bias=b1.detach(), aux_out=h, epilogue=_C.EPI_GELU_SAVE_GRAD, out_dtype=dt, impl=impl)
         res2 = None if residual is None else residual.reshape(rows, N).contiguous()
         y = K.gemm(g, shadow(w2, dt), M=rows, N=N, K=H, bias=b2.detach(), residual=res2, out_dtype=dt, impl=impl)
         ctx.save_for_backward(x2, h, g, w1, w2)
@@ -156,7 +157,7 @@ class _MLP(Function):
             dy2 = dy2.contiguous()
         dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl)
         db2 = K.colsum(dy2, rows, N)
-        dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_DGELU, out_dtype=dt, impl=impl)
+        dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_AUX, out_dtype=dt, impl=impl)
         dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl)
         db1 = K.colsum(dh, rows, H)
         dx = None

@@ -193,7 +193,7 @@ def colsum(x: Tensor, rows: int, n: int, ld: Optional[int] = None) -> Tensor:
     out = torch.empty(n, dtype=torch.float32, device=x.device)
     ws = _ws(lib.tsw_colsum_workspace_bytes(rows, n), x.device)
     check(lib.tsw_colsum(ptr(x), dtype_code(x.dtype), rows, n, ld if ld is not None else n, ptr(out), ptr(ws), ws.numel(), stream()), "tsw_colsum")
-    _count(2)
+    _count(1)
     return out
 
 
