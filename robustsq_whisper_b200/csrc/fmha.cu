@@ -87,7 +87,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const FmhaParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FmhaFwdSmem& s = *reinterpret_cast<FmhaFwdSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FQ, h = blockIdx.y, b = blockIdx.z;
   if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_fwd: dynamic smem not 1024-aligned\n"); __trap(); }
 
@@ -123,7 +123,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n_kv > 0) {
+    if (n_kv > 0) {   // whole warp, uniform control flow; one elected lane issues MMAs / commits
+      const bool leader_lane = elect_one();
       const uint32_t id_s = idesc_bf16(FQ, FK, 0, 0);    // S = Q K^T : both K-major, N = 128
       const uint32_t id_pv = idesc_bf16(FQ, FD, 0, 1);   // PV       : P K-major, V MN-major ([key][dh]), N = 64
       // descriptors of the fixed buffers are built once; the issue loop only bumps their address field
@@ -136,11 +137,14 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s.k_full[st], ph);
         tc_fence_after();
         const uint64_t kd = dK_[st];
+        if (leader_lane) {
         umma_bf16_c<false>(tmem_s, dQ_, kd, id_s);
 #pragma unroll
         for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(tmem_s, desc_advance(dQ_, k * 32), desc_advance(kd, k * 32), id_s);
         umma_commit(&s.s_full);
         umma_commit(&s.k_empty[st]);
+        }
+        __syncwarp();
       };
       mbar_wait(&s.q_full, 0);
       issue_s(0);
@@ -150,12 +154,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s.v_full[st], ph);
         tc_fence_after();
         const uint64_t vd = dV_[st];
+        if (leader_lane) {
         umma_bf16_c<false>(tmem_pv, dP0, vd, id_pv);
 #pragma unroll
         for (int k = 1; k < FK / 16; ++k)
           umma_bf16_c<true>(tmem_pv, desc_advance(k < 4 ? dP0 : dP1, (k & 3) * 32), desc_advance(vd, k * 2048), id_pv);
         umma_commit(&s.o_full);
         umma_commit(&s.v_empty[st]);
+        }
+        __syncwarp();
         if (j + 1 < n_kv) issue_s(j + 1);  // next S overlaps the softmax warps' output update
       }
     }
@@ -306,7 +313,7 @@ struct FmhaBwdSmem {
   unsigned char p[2 * kTileBytes];    // [q][key] bf16, two 64-key panels
   unsigned char ds[2 * kTileBytes];
   unsigned char dq[2 * kTileBytes];   // fp32 staging: two 32-column panels of [128][128 B], SW128
-  uint64_t kv_full, q_full[2], q_empty[2], s_full, pds_full, dq_full;
+  uint64_t kv_full, q_full[2], q_empty[2], s_full, pds_full, dq_full, acc_full;
   uint32_t tmem_slot;
 };
 
@@ -334,7 +341,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ, const FmhaBwdParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FmhaBwdSmem& s = *reinterpret_cast<FmhaBwdSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * FK, h = blockIdx.y, b = blockIdx.z;
   if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_bwd: dynamic smem not 1024-aligned\n"); __trap(); }
 
@@ -349,7 +356,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     mbar_init(&s.kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
-    mbar_init(&s.s_full, 1); mbar_init(&s.pds_full, 16); mbar_init(&s.dq_full, 1);
+    mbar_init(&s.s_full, 1); mbar_init(&s.pds_full, 16); mbar_init(&s.dq_full, 1); mbar_init(&s.acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
@@ -372,7 +379,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && active) {
+    if (active) {   // the whole warp walks the loop (uniform control flow); one elected lane issues the MMAs / commits
+      const bool leader_lane = elect_one();
       const uint32_t id_s = idesc_bf16(128, 128, 0, 0);   // S, dP: K-major x K-major, N = 128 keys
       const uint32_t id_g = idesc_bf16(128, 64, 1, 1);    // dV, dK: A = P^T / dS^T (MN-major), B = dO / Q (MN-major), N = 64
       const uint32_t id_q = idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major over keys), B = K tile (MN-major), N = 64
@@ -391,6 +399,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s.q_full[st], ph);
         tc_fence_after();
         const uint64_t qd = dQ_k[st], od = dO_k[st];
+        if (leader_lane) {
         umma_bf16_c<false>(t_s, qd, dK_k, id_s);
 #pragma unroll
         for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_s, desc_advance(qd, k * 32), desc_advance(dK_k, k * 32), id_s);
@@ -398,6 +407,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_dp, desc_advance(od, k * 32), desc_advance(dV_k, k * 32), id_s);
         umma_commit(&s.s_full);
+        }
+        __syncwarp();
       };
       mbar_wait(&s.kv_full, 0);
       issue_scores(0);
@@ -406,6 +417,13 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(&s.pds_full, it & 1);   // P, dS in smem; S, dP and dQ TMEM drained
         tc_fence_after();
         const uint64_t qd = dQ_mn[st], od = dO_mn[st];
+        if (leader_lane) {
+        // dQ_i = dS K first (reduction over the 128 keys): its drain by the gradient warps then overlaps dV / dK below
+        umma_bf16_c<false>(t_dq, dS_k0, dK_mn, id_q);
+#pragma unroll
+        for (int k = 1; k < FK / 16; ++k)
+          umma_bf16_c<true>(t_dq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
+        umma_commit(&s.dq_full);
         // dV += P^T dO, dK += dS^T Q: reduction over the 128 queries, 16 per instruction (2048 B per step in both operands)
         if (it == 0) umma_bf16_c<false>(t_dv, dP_mn, od, id_g); else umma_bf16_c<true>(t_dv, dP_mn, od, id_g);
 #pragma unroll
@@ -413,13 +431,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (it == 0) umma_bf16_c<false>(t_dk, dS_mn, qd, id_g); else umma_bf16_c<true>(t_dk, dS_mn, qd, id_g);
 #pragma unroll
         for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dk, desc_advance(dS_mn, k * 2048), desc_advance(qd, k * 2048), id_g);
-        // dQ_i = dS K: reduction over the 128 keys
-        umma_bf16_c<false>(t_dq, dS_k0, dK_mn, id_q);
-#pragma unroll
-        for (int k = 1; k < FK / 16; ++k)
-          umma_bf16_c<true>(t_dq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
-        umma_commit(&s.dq_full);
         umma_commit(&s.q_empty[st]);
+        if (it + 1 == n_it) umma_commit(&s.acc_full);   // dK / dV accumulators final
+        }
+        __syncwarp();
         if (it + 1 < n_it) issue_scores(it + 1);
       }
     }
@@ -498,7 +513,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     // ---- dK, dV of this key tile (lanes = keys); inactive tiles write zeros
     const int key = kv0 + r;
-    if (active) { mbar_wait(&s.dq_full, (n_it - 1) & 1); tc_fence_after(); }  // all MMAs of the last iteration have completed
+    if (active) { mbar_wait(&s.acc_full, 0); tc_fence_after(); }  // all MMAs of the last iteration have completed
     float gv[16], gk[16];
     if (active) {
       tmem_ld16(t_dv + lane_off + part * 16, gv);

@@ -7,6 +7,15 @@
 namespace tsw {
 
 // ----------------------------------------------------------------------------------------------- PTX wrappers
+// true on exactly one (converged-warp) lane; keeps the surrounding control flow warp-uniform so operands of the
+// tcgen05 instructions stay in uniform registers (no per-issue R2UR / re-election sequences)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
