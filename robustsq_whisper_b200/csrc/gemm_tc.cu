@@ -67,6 +67,67 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
   return d;
 }
 
+
+// ---- fused-epilogue kinds with a dedicated row loop (anything else goes through the general epi_store4)
+enum { EK_PLAIN = 0, EK_RES = 1, EK_GELU = 2, EK_GELU_GRAD = 3, EK_MUL_AUX = 4, EK_MUL_DGELU = 5, EK_ANY = 6 };
+
+__device__ __forceinline__ int epi_kind_of(const EpiParams& ep) {
+  const bool has_res = ep.residual != nullptr, has_ao = ep.aux_out != nullptr, beta = ep.beta != 0.f;
+  if (beta || ep.res_row_mod > 0) return EK_ANY;
+  switch (ep.epilogue) {
+    case TSW_EPI_NONE: return (has_res && !has_ao) ? EK_RES : (!has_res && !has_ao) ? EK_PLAIN : EK_ANY;
+    case TSW_EPI_GELU: return !has_res ? EK_GELU : EK_ANY;
+    case TSW_EPI_GELU_SAVE_GRAD: return (!has_res && has_ao) ? EK_GELU_GRAD : EK_ANY;
+    case TSW_EPI_MUL_AUX: return (!has_res && !has_ao) ? EK_MUL_AUX : EK_ANY;
+    case TSW_EPI_MUL_DGELU: return (!has_res && !has_ao) ? EK_MUL_DGELU : EK_ANY;
+  }
+  return EK_ANY;
+}
+
+// The lane's up-to-8 rows (stride 4 rows) of one 32-column chunk: staged fp32 accumulators -> fused epilogue -> global.
+// srow = staging base + rsub*32 (row i lives 4*i rows further); extra operands are fetched for all rows first.
+template <typename DT, int KIND>
+__device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic, const float* srow, int u, int rsub, int rows_ok, float alpha,
+                                         float4 b4, DT* Dp, const DT* Rp, const DT* AIp, DT* AOp, int64_t off, int64_t row4, int64_t roff,
+                                         int64_t rrow4, int) {
+  typename RawVec<DT>::type pre[8];
+  if (KIND == EK_RES || KIND == EK_MUL_AUX || KIND == EK_MUL_DGELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < rows_ok) pre[i] = RawVec<DT>::ldg(KIND == EK_RES ? Rp + roff + (int64_t)i * rrow4 : AIp + off + (int64_t)i * row4);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < rows_ok) {
+      const int rl = i * 4 + rsub;
+      const float4 a = *reinterpret_cast<const float4*>(srow + i * 128 + ((u ^ (rl & 7)) * 4));
+      float o[4] = {fmaf(alpha, a.x, b4.x), fmaf(alpha, a.y, b4.y), fmaf(alpha, a.z, b4.z), fmaf(alpha, a.w, b4.w)};
+      if (KIND == EK_RES || KIND == EK_MUL_AUX || KIND == EK_MUL_DGELU) {
+        float ex[4];
+        RawVec<DT>::unpack(pre[i], ex);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = KIND == EK_RES ? o[j] + ex[j] : KIND == EK_MUL_AUX ? o[j] * ex[j] : o[j] * dgelu_fast(ex[j]);
+      } else if (KIND == EK_GELU) {
+        if (AOp) store4(AOp + off + (int64_t)i * row4, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = gelu_fast(o[j]);
+      } else if (KIND == EK_GELU_GRAD) {
+        float dg[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gelu_and_grad_fast(o[j], o[j], dg[j]);
+        store4(AOp + off + (int64_t)i * row4, dg);
+      }
+      DT* dst = Dp + off + (int64_t)i * row4;
+      if constexpr (sizeof(DT) == 4) {
+        if (KIND == EK_PLAIN && split_atomic) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
+        else store4(dst, o);
+      } else {
+        store4(dst, o);
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr uint32_t kABytes = TBM * TBK * 2;
@@ -182,6 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = (warp - 4) >> 2;  // which half of the tile's 32-column chunks this warp drains
     float* stg = stg_base + (warp - 4) * S::kStgFloats;
     const float alpha = ep.alpha_dev ? ep.alpha * __ldg(ep.alpha_dev) : ep.alpha;
+    const int epi_kind = epi_kind_of(ep);
     const int u = lane & 7, rsub = lane >> 3;  // phase 2: 8 lanes x 4 columns cover a 32-column row segment, 4 rows / instruction
     DT* const Dp = reinterpret_cast<DT*>(ep.D);
     const DT* const Rp = reinterpret_cast<const DT*>(ep.residual);
@@ -202,6 +264,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t off0 = d_off + m_first * ep.ldd + n_first;
       int rows_ok = 0;                                            // how many of the lane's 8 rows are inside M
       if (m_first < p.M) rows_ok = (int)min((int64_t)8, (p.M - m_first + 3) / 4);
+      if (GENERIC) {
+        // pull the NEXT tile's extra epilogue operand (residual | aux_in | old D) into L2 now: its loads then hit L2
+        // (~250 cycles) instead of DRAM (~800) when that tile's epilogue runs one main loop later
+        const int64_t wn = w + gridDim.x;
+        const DT* src = Rp ? Rp : ((ep.epilogue == TSW_EPI_MUL_DGELU || ep.epilogue == TSW_EPI_MUL_AUX) ? AIp : (ep.beta != 0.f ? Dp : nullptr));
+        if (src != nullptr && wn < p.total_work && ep.res_row_mod == 0) {
+          const int64_t tn = wn / p.splits;
+          const int btn = (int)(tn / tiles_per_batch);
+          const int64_t rn = tn - (int64_t)btn * tiles_per_batch;
+          const int mtn = (int)(rn / p.tiles_n), ntn = (int)(rn - (int64_t)mtn * p.tiles_n);
+          const int bon = btn / p.batch_inner, bin = btn - bon * p.batch_inner;
+          const int64_t ld = Rp ? ep.ldres : ep.ldd;
+          const int64_t boff = Rp ? (bon * p.r_so + bin * p.r_si) : (bon * p.d_so + bin * p.d_si);
+          // 128 rows x (BN * sizeof(DT)) bytes = rows of BN*sizeof(DT)/128 lines; 256 epilogue threads share them
+          constexpr int kLinesPerRow = BN * (int)sizeof(DT) / 128;
+          const int et = (warp - 4) * 32 + lane;
+          for (int i = et; i < TBM * kLinesPerRow; i += TC_EPI_WARPS * 32) {
+            const int row = i / kLinesPerRow, line = i - row * kLinesPerRow;
+            const int64_t m = (int64_t)mtn * TBM + row;
+            const int64_t n = (int64_t)ntn * BN + line * (128 / (int)sizeof(DT));
+            if (m < p.M && n < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + boff + m * ld + n));
+          }
+        }
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -221,74 +307,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (vec) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias && first_split) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
-          int64_t off = off0 + c;
-          int64_t roff = 0;
-          if (GENERIC && Rp) roff = r_off + (ep.res_row_mod > 0 ? (m_first % ep.res_row_mod) : m_first) * ep.ldres + n;
-          // The extra operand of the fused epilogue (residual | GELU' input | old D) is fetched for all 8 rows up front
-          // as raw 8/16-byte words through the read-only path, so the loads overlap instead of queueing behind stores.
-          typename RawVec<DT>::type pre[8];
-          const bool mul_in = ep.epilogue == TSW_EPI_MUL_DGELU || ep.epilogue == TSW_EPI_MUL_AUX;
-          const int which = !GENERIC ? 0 : Rp ? 1 : mul_in ? 2 : (ep.beta != 0.f) ? 3 : 0;
-          if (GENERIC && which != 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i < rows_ok) {
-                const DT* src;
-                if (which == 1) src = (ep.res_row_mod > 0) ? Rp + r_off + ((m_first + 4 * i) % ep.res_row_mod) * ep.ldres + n
-                                                           : Rp + roff + (int64_t)i * 4 * ep.ldres;
-                else src = (which == 2 ? AIp : Dp) + off + (int64_t)i * row4;
-                pre[i] = which == 3 ? RawVec<DT>::ld(src) : RawVec<DT>::ldg(src);  // D itself is written below: no read-only path
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (i < rows_ok) {
-              const float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * 32 + ((u ^ ((i * 4 + rsub) & 7)) * 4));
-              float o[4] = {fmaf(alpha, a.x, b4.x), fmaf(alpha, a.y, b4.y), fmaf(alpha, a.z, b4.z), fmaf(alpha, a.w, b4.w)};
-              if (GENERIC) {
-                float ex[4] = {0.f, 0.f, 0.f, 0.f};
-                if (which != 0) RawVec<DT>::unpack(pre[i], ex);
-                if (ep.epilogue == TSW_EPI_GELU_SAVE_GRAD) {
-                  float dg[4];
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) gelu_and_grad_fast(o[j], o[j], dg[j]);
-                  if (AOp) store4(AOp + off, dg);
-                } else if (AOp) {
-                  store4(AOp + off, o);
+          const int64_t off = off0 + c;
+          const float* srow = stg + rsub * 32;
+          if (!GENERIC) {
+            epi_rows<DT, EK_PLAIN>(ep, p.splits > 1, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, nullptr, off, row4, 0, 0, 0);
+          } else {
+            // one specialised, branch-free row loop per fused-epilogue kind: the kind is uniform for the whole launch, so
+            // only one compact loop is ever resident in the instruction cache
+            const int64_t roff = Rp ? r_off + m_first * ep.ldres + n : 0;
+            switch (epi_kind) {
+              case EK_RES: epi_rows<DT, EK_RES>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, Rp, nullptr, nullptr, off, row4, roff, 4 * ep.ldres, 0); break;
+              case EK_GELU: epi_rows<DT, EK_GELU>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, AOp, off, row4, 0, 0, 0); break;
+              case EK_GELU_GRAD: epi_rows<DT, EK_GELU_GRAD>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, AOp, off, row4, 0, 0, 0); break;
+              case EK_MUL_AUX: epi_rows<DT, EK_MUL_AUX>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, AIp, nullptr, off, row4, 0, 0, 0); break;
+              case EK_MUL_DGELU: epi_rows<DT, EK_MUL_DGELU>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, AIp, nullptr, off, row4, 0, 0, 0); break;
+              default:
+#pragma unroll 1
+                for (int i = 0; i < rows_ok; ++i) {
+                  const float4 a = *reinterpret_cast<const float4*>(stg + (i * 4 + rsub) * 32 + ((u ^ ((i * 4 + rsub) & 7)) * 4));
+                  epi_store4<DT>(ep, a, m_first + 4 * i, n, d_off, r_off, alpha);
                 }
-                if (ep.epilogue == TSW_EPI_GELU) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) o[j] = gelu_fast(o[j]);
-                } else if (mul_in) {
-                  float ai[4];
-                  if (which == 2) { ai[0] = ex[0]; ai[1] = ex[1]; ai[2] = ex[2]; ai[3] = ex[3]; } else load4(AIp + off, ai);
-                  if (ep.epilogue == TSW_EPI_MUL_AUX) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] *= ai[j];
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] *= dgelu_fast(ai[j]);
-                  }
-                }
-                if (which == 1) {
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) o[j] += ex[j];
-                }
-                if (ep.beta != 0.f) {
-                  float od[4];
-                  if (which == 3) { od[0] = ex[0]; od[1] = ex[1]; od[2] = ex[2]; od[3] = ex[3]; } else load4(Dp + off, od);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) o[j] += ep.beta * od[j];
-                }
-              }
-              if constexpr (sizeof(DT) == 4) {
-                if (p.splits > 1) atomicAdd(reinterpret_cast<float4*>(Dp + off), make_float4(o[0], o[1], o[2], o[3]));
-                else store4(Dp + off, o);
-              } else {
-                store4(Dp + off, o);
-              }
-              off += row4;
             }
           }
         } else {

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from robustsq_whisper_b200 import kernels as K, _C
 
-def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=False, aux=False, res=False, iters=10, batch=(1,1)):
+def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=False, aux=False, res=False, iters=10, batch=(1,1), rowmod=0):
     dev = "cuda"
     nb = batch[0] * batch[1]
     a = torch.randn((nb, Kd, M) if a_mn else (nb, M, Kd), device=dev).bfloat16()
@@ -14,8 +14,9 @@ def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=Fals
               d_strides=(batch[1] * M * N, M * N), epilogue=epi)
     if bias: kw["bias"] = torch.randn(N, device=dev)
     if aux: kw["aux_out"] = torch.empty_like(d)
-    if epi == 2: kw["aux_in"] = torch.randn_like(d)
+    if epi in (2, 4): kw["aux_in"] = torch.randn_like(d)
     if res: kw["residual"] = torch.randn_like(d)
+    if rowmod: kw["res_row_mod"] = rowmod
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(2): K.gemm(a, b, **kw)
     ts = []
@@ -29,14 +30,10 @@ def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=Fals
     print(f"M={M:6d} N={N:5d} K={Kd:6d} nb={nb:4d} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} bias={int(bias)} aux={int(aux)} res={int(res)} out={'bf16' if out==torch.bfloat16 else 'f32'}: {t:8.3f} ms  {fl / t / 1e9:8.1f} TF/s")
 
 S = 48512
-bench(S, 1024, 1024, bias=True)
+bench(S, 4096, 1024, b_mn=True)
+bench(S, 4096, 1024, b_mn=True, res=True)
+bench(S, 4096, 1024, b_mn=True, epi=4)
+bench(S, 4096, 1024, bias=True, epi=3, aux=True)
+bench(S, 4096, 1024, bias=True, epi=1)
 bench(S, 1024, 1024, bias=True, res=True)
-bench(S, 4096, 1024, bias=True, epi=1, aux=True)
 bench(S, 1024, 4096, bias=True, res=True)
-bench(S, 1024, 1024, b_mn=True)
-bench(S, 4096, 1024, b_mn=True, epi=2)
-bench(1024, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
-bench(1024, 4096, S, a_mn=True, b_mn=True, out=torch.float32)
-bench(8192, 8192, 8192)
-bench(1516, 1516, 64, batch=(32, 16))
-bench(1516, 64, 1520, b_mn=True, batch=(32, 16))
