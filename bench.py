@@ -197,8 +197,10 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---------------- warm-up
+    # ---------------- warm-up (inputs of every timed step are staged first, so the caching allocator reaches its steady
+    # state during warm-up and no cudaMalloc lands inside a timed region)
     res = resident_inputs()
+    staged = [{k: v.clone() for k, v in res.items()} for _ in range(args.steps)]
     for _ in range(max(args.warmup, 3)):
         step({k: v.clone() for k, v in res.items()})
     sync_all()
@@ -208,7 +210,6 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     K.LAUNCHES["n"] = 0
-    staged = [{k: v.clone() for k, v in res.items()} for _ in range(args.steps)]
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -237,7 +238,9 @@ def run_b200(args):
     # ---------------- region 3: the same steps again with every tsw_gemm launch bracketed by CUDA events (roofline of
     # the dominant kernel); kept out of regions 1-2 so the ~2.5k event records per step do not perturb `value` / `e2e`
     K.GEMM_PROFILE = []
-    staged = [{k: v.clone() for k, v in res.items()} for _ in range(args.steps)]
+    for d_ in staged:  # the model mutates `text` in place (ignore_id fill): restore pristine inputs
+        for k_ in d_:
+            d_[k_].copy_(res[k_])
     sync_all()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()

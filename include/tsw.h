@@ -103,9 +103,10 @@ int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspace_bytes, ts
 int tsw_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* sum_out,
                       float* mean, float* rstd, int64_t rows, int64_t d, float eps, int dtype, tsw_stream_t stream);
 size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d);
-/* dx = LN'(dy); dgamma/dbeta (d) fp32 are OVERWRITTEN. x is the LN input (x + res when fused). */
-int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
-                      float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
+/* dx = LN'(dy) (+ dres, the gradient arriving on the residual branch that bypasses the LN, or NULL); dgamma/dbeta (d) fp32
+ * are OVERWRITTEN. x is the LN input (x + res when fused). */
+int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
+                      void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
                       size_t workspace_bytes, tsw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ elementwise / reductions */

@@ -53,7 +53,7 @@ SIGNATURES = {
     "tsw_gemm": (c_int, [POINTER(GemmDesc), _P, _SZ, _P]),
     "tsw_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I, _P]),
     "tsw_layernorm_bwd_workspace_bytes": (_SZ, [_I64, _I64]),
-    "tsw_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _P, _SZ, _P]),
+    "tsw_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _P, _SZ, _P]),
     "tsw_cast": (c_int, [_P, _I, _P, _I, _I64, _P]),
     "tsw_colsum_workspace_bytes": (_SZ, [_I64, _I64]),
     "tsw_colsum": (c_int, [_P, _I, _I64, _I64, _I64, _P, _P, _SZ, _P]),

@@ -64,76 +64,114 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
   }
 }
 
-// Each warp walks rows (grid-stride), emits dx and keeps dgamma/dbeta for the columns its lanes own in registers;
-// CTA partials land in workspace [gridDim.x][2][d] and are reduced by colreduce_kernel.
+// LayerNorm backward in two HBM passes, both at high occupancy:
+//   ln_bwd_dx_kernel     one warp per row: dx = rstd (g - mean(g) - xhat mean(g xhat)) [+ dres], g = dy * gamma
+//   ln_bwd_dgb_kernel    column reductions dgamma = sum_rows dy * xhat, dbeta = sum_rows dy (32 column groups x 8 row lanes per
+//                        CTA, the last CTA of a column block folds the row-chunk partials in a fixed order)
 template <typename T>
 __global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, T* __restrict__ dx,
-                     float* __restrict__ partial, int64_t rows, int d) {
+ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+                 const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx, int64_t rows, int d) {
   constexpr int VN = Vec<T>::N;
-  constexpr int NC = 32 / VN;  // vectors per lane for d = 1024
-  extern __shared__ float sm[];  // [2][d]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
   const int nvec = d / VN;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  float dg[NC][VN], db[NC][VN];
+  const float mu = mean[row], rs = rstd[row];
+  float xh[kLnChunks][VN], g[kLnChunks][VN];
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-  for (int c = 0; c < NC; ++c)
-#pragma unroll
-    for (int j = 0; j < VN; ++j) dg[c][j] = db[c][j] = 0.f;
-
-  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
-    const float mu = mean[row], rs = rstd[row];
-    float xh[NC][VN], g[NC][VN];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int i = lane + 32 * c;
-      if (i < nvec) {
-        float xv[VN], dv[VN], gv[VN];
-        Vec<T>::load(x + row * d + (int64_t)i * VN, xv);
-        Vec<T>::load(dy + row * d + (int64_t)i * VN, dv);
-#pragma unroll
-        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
-#pragma unroll
-        for (int j = 0; j < VN; ++j) {
-          xh[c][j] = (xv[j] - mu) * rs;
-          g[c][j] = dv[j] * gv[j];
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
-          dg[c][j] += dv[j] * xh[c][j];
-          db[c][j] += dv[j];
-        }
-      }
-    }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int i = lane + 32 * c;
-      if (i < nvec) {
-        float o[VN];
-#pragma unroll
-        for (int j = 0; j < VN; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
-        Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
-      }
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
+  for (int c = 0; c < kLnChunks; ++c) {
     const int i = lane + 32 * c;
     if (i < nvec) {
+      float xv[VN], dv[VN], gv[VN];
+      Vec<T>::load(x + row * d + (int64_t)i * VN, xv);
+      Vec<T>::load(dy + row * d + (int64_t)i * VN, dv);
+#pragma unroll
+      for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
 #pragma unroll
       for (int j = 0; j < VN; ++j) {
-        atomicAdd(&sm[i * VN + j], dg[c][j]);
-        atomicAdd(&sm[d + i * VN + j], db[c][j]);
+        xh[c][j] = (xv[j] - mu) * rs;
+        g[c][j] = dv[j] * gv[j];
+        s1 += g[c][j];
+        s2 += g[c][j] * xh[c][j];
       }
     }
   }
+  s1 = warp_sum(s1) / d;
+  s2 = warp_sum(s2) / d;
+#pragma unroll
+  for (int c = 0; c < kLnChunks; ++c) {
+    const int i = lane + 32 * c;
+    if (i < nvec) {
+      float o[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
+      if (dres != nullptr) {
+        float r[VN];
+        Vec<T>::load(dres + row * d + (int64_t)i * VN, r);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] += r[j];
+      }
+      Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+ln_bwd_dgb_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  int64_t rows, int d, int64_t rows_per_chunk, float* __restrict__ partial, float* __restrict__ dgamma,
+                  float* __restrict__ dbeta, unsigned int* __restrict__ counters) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float sm[2][8][32 * VN + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + tx) * VN;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float ag[VN], ab[VN];
+#pragma unroll
+  for (int j = 0; j < VN; ++j) ag[j] = ab[j] = 0.f;
+  if (c0 < d) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float xv[VN], dv[VN];
+      Vec<T>::load(x + r * d + c0, xv);
+      Vec<T>::load(dy + r * d + c0, dv);
+      const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { ag[j] = fmaf(dv[j], (xv[j] - mu) * rs, ag[j]); ab[j] += dv[j]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < VN; ++j) { sm[0][ty][tx * VN + j] = ag[j]; sm[1][ty][tx * VN + j] = ab[j]; }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) partial[(int64_t)blockIdx.x * 2 * d + i] = sm[i];
+  for (int c = threadIdx.x; c < 2 * 32 * VN; c += 256) {
+    const int which = c / (32 * VN), cc = c - which * 32 * VN;
+    const int col = blockIdx.x * 32 * VN + cc;
+    if (col < d) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[which][k][cc];
+      partial[((int64_t)blockIdx.y * 2 + which) * d + col] = t;
+    }
+  }
+  __shared__ unsigned int ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(&counters[blockIdx.x], 1u);
+  __syncthreads();
+  if (ticket == gridDim.y - 1) {
+    __threadfence();
+    for (int c = threadIdx.x; c < 2 * 32 * VN; c += 256) {
+      const int which = c / (32 * VN), cc = c - which * 32 * VN;
+      const int col = blockIdx.x * 32 * VN + cc;
+      if (col < d) {
+        float t = 0.f;
+        for (unsigned int k = 0; k < gridDim.y; ++k) t += __ldcg(partial + ((int64_t)k * 2 + which) * d + col);
+        (which == 0 ? dgamma : dbeta)[col] = t;
+      }
+    }
+    if (threadIdx.x == 0) counters[blockIdx.x] = 0;
+  }
 }
 
 // out[c] = sum_p partial[p][c], c < n
@@ -427,25 +465,32 @@ extern "C" int tsw_layernorm_fwd(const void* x, const void* res, const float* ga
   return TSW_OK;
 }
 
-static int ln_bwd_grid() { return sm_count() * 2; }
+static unsigned int* colsum_counters();
+static int64_t colsum_chunks(int64_t rows, int64_t n, int vn);
 
-extern "C" size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d) { return sizeof(float) * 2 * (size_t)d * ln_bwd_grid(); }
+extern "C" size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d) {
+  return sizeof(float) * 2 * (size_t)d * (size_t)std::max(colsum_chunks(rows, d, 4), colsum_chunks(rows, d, 8));
+}
 
-extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, void* dx,
-                                 float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
+extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
+                                 void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
                                  size_t workspace_bytes, tsw_stream_t stream) {
   TSW_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "layernorm_bwd: null/empty argument");
   const int vn = dtype == TSW_F32 ? 4 : 8;
-  TSW_CHECK_ARG(d % vn == 0 && d <= 1024, "layernorm_bwd: d=%lld unsupported (d %% %d == 0, d <= 1024)", (long long)d, vn);
-  TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), "layernorm_bwd: pointers must be 16-byte aligned");
+  TSW_CHECK_ARG(d % vn == 0 && d / vn <= 32 * kLnChunks, "layernorm_bwd: d=%lld unsupported", (long long)d);
+  TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!dres || aligned16(dres)), "layernorm_bwd: pointers must be 16-byte aligned");
   if (!workspace || workspace_bytes < tsw_layernorm_bwd_workspace_bytes(rows, d)) { set_error("layernorm_bwd: workspace too small"); return TSW_E_WORKSPACE; }
-  const int grid = (int)std::min<int64_t>(ln_bwd_grid(), (rows + 7) / 8);
-  float* partial = (float*)workspace;
-  const size_t smem = sizeof(float) * 2 * d;
-  DISPATCH_T(dtype, (layernorm_bwd_kernel<T><<<grid, 256, smem, as_stream(stream)>>>((const T*)dy, (const T*)x, gamma, mean, rstd,
-                                                                                     (T*)dx, partial, rows, (int)d)));
+  cudaStream_t st = as_stream(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  DISPATCH_T(dtype, (ln_bwd_dx_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d)));
   TSW_LAUNCH_CHECK();
-  colreduce_kernel<<<(unsigned)((2 * d + 255) / 256), 256, 0, as_stream(stream)>>>(partial, grid, 2 * d, dgamma, dbeta, d);
+  const int64_t chunks = colsum_chunks(rows, d, vn);
+  const int64_t rpc = (rows + chunks - 1) / chunks;
+  dim3 g2((unsigned)((d + 32 * vn - 1) / (32 * vn)), (unsigned)chunks);
+  unsigned int* counters = colsum_counters();
+  TSW_CHECK_ARG(counters != nullptr, "layernorm_bwd: ticket buffer unavailable");
+  // the LN tickets live in the upper half of the per-device ticket array (colsum uses the lower half)
+  DISPATCH_T(dtype, (ln_bwd_dgb_kernel<T><<<g2, 256, 0, st>>>((const T*)dy, (const T*)x, mean, rstd, rows, (int)d, rpc, (float*)workspace, dgamma, dbeta, counters + 4096)));
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }
@@ -464,15 +509,16 @@ extern "C" int tsw_cast(const void* src, int src_dtype, void* dst, int dst_dtype
   return TSW_OK;
 }
 
-constexpr int kMaxColBlocks = 8192;
+constexpr int kMaxColBlocks = 4096;  // lower half: colsum tickets, upper half: LayerNorm-backward tickets
+constexpr int kTicketWords = 8192;
 static unsigned int* colsum_counters() {  // one zero-initialised ticket array per device, reused (self-resetting) by every call
   static unsigned int* ptrs[64] = {nullptr};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
   if (!ptrs[dev]) {
     unsigned int* p = nullptr;
-    if (cudaMalloc(&p, sizeof(unsigned int) * kMaxColBlocks) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, sizeof(unsigned int) * kMaxColBlocks);
+    if (cudaMalloc(&p, sizeof(unsigned int) * kTicketWords) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, sizeof(unsigned int) * kTicketWords);
     ptrs[dev] = p;
   }
   return ptrs[dev];

@@ -186,6 +186,31 @@ class _LayerNorm(Function):
         return dx, dg, db, None, (dx if ctx.has_res else None)
 
 
+class _LayerNormTap(Function):
+    """(x, LN(x)) for the pre-LN residual pattern  x + f(LN(x)): the first output is x itself (an alias that carries the
+    residual branch), so backward receives the residual-branch gradient and the LN gradient together and adds them inside
+    the LN-backward kernel instead of a separate full-tensor add."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, gamma: Tensor, beta: Tensor, eps: float):
+        x = x.contiguous()
+        y, _, mean, rstd = K.layernorm_fwd(x, gamma.detach(), beta.detach(), eps)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, g_skip: Optional[Tensor], gy: Optional[Tensor]):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        if gy is None:
+            return g_skip, None, None, None
+        dx, dg, db = K.layernorm_bwd(gy, x, gamma.detach(), mean, rstd, dres=g_skip)
+        return dx, dg, db, None
+
+
+def layernorm_tap(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
+    return _LayerNormTap.apply(x, gamma, beta, eps)
+
+
 def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, res: Optional[Tensor] = None) -> Tensor:
     """LN(x) or, with ``res``, LN(x + res) (the BertSelfOutput / BertOutput pattern, Qformer.py:264-268,351-355)."""
     return _LayerNorm.apply(x, gamma, beta, eps, res)

@@ -161,16 +161,18 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optio
     return y, sum_out, mean, rstd
 
 
-def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor):
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dres: Optional[Tensor] = None):
     lib = _C.load()
     d = x.shape[-1]
     rows = x.numel() // d
     dy = dy.contiguous()
+    if dres is not None:
+        dres = dres.contiguous()
     dx = torch.empty_like(x)
     dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
     dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
     ws = _ws(lib.tsw_layernorm_bwd_workspace_bytes(rows, d), x.device)
-    check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
+    check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
                                 dtype_code(x.dtype), ptr(ws), ws.numel(), stream()), "tsw_layernorm_bwd")
     _count(2)
     return dx, dgamma, dbeta

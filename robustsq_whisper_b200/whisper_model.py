@@ -124,8 +124,10 @@ def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool
 
 def residual_block(p: BlockParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False) -> Tensor:
     """openai-whisper ResidualAttentionBlock: x += attn(ln(x)); [x += cross_attn(ln(x), xa)]; x += mlp(ln(x))."""
-    x = mha(p.attn, F.layernorm(x, p.attn_ln.weight, p.attn_ln.bias, p.attn_ln.eps), causal=causal, residual=x)
+    x, h = F.layernorm_tap(x, p.attn_ln.weight, p.attn_ln.bias, p.attn_ln.eps)
+    x = mha(p.attn, h, causal=causal, residual=x)
     if xa is not None:
-        x = mha(p.cross_attn, F.layernorm(x, p.cross_attn_ln.weight, p.cross_attn_ln.bias, p.cross_attn_ln.eps), xa=xa, residual=x)
-    h = F.layernorm(x, p.mlp_ln.weight, p.mlp_ln.bias, p.mlp_ln.eps)
+        x, h = F.layernorm_tap(x, p.cross_attn_ln.weight, p.cross_attn_ln.bias, p.cross_attn_ln.eps)
+        x = mha(p.cross_attn, h, xa=xa, residual=x)
+    x, h = F.layernorm_tap(x, p.mlp_ln.weight, p.mlp_ln.bias, p.mlp_ln.eps)
     return F.mlp(h, p.mlp[0].weight, p.mlp[0].bias, p.mlp[2].weight, p.mlp[2].bias, residual=x)
