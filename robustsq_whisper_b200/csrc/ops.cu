@@ -7,60 +7,98 @@
 
 namespace tsw {
 
+// raw 16-byte vector <-> fp32 lanes (keeps prefetched rows compact in registers)
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& r, float* o);
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& r, float* o) {
+  o[0] = __uint_as_float(r.x); o[1] = __uint_as_float(r.y); o[2] = __uint_as_float(r.z); o[3] = __uint_as_float(r.w);
+}
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& r, float* o) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { o[2 * i] = __uint_as_float(w[i] << 16); o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <typename T> __device__ __forceinline__ uint4 ldg16(const T* p) { return *reinterpret_cast<const uint4*>(p); }
+
 // ============================================================================================ LayerNorm
 // One warp per row, the row kept in registers (d <= 32 lanes * kLnChunks vectors).
 constexpr int kLnChunks = 8;
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int NC>
+__global__ void __launch_bounds__(256, 4)
 layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const float* __restrict__ gamma,
                      const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ sum_out, float* __restrict__ mean,
                      float* __restrict__ rstd, int64_t rows, int d, float eps) {
+  // Warps walk rows grid-stride.  A row lives in registers as raw 16-byte vectors (unpacked on the fly in each of the
+  // three passes), and the next row's loads are issued before the current one is reduced: small register footprint ->
+  // four CTAs per SM, every warp with a row in flight.
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = d / VN;
-  float v[kLnChunks][VN];
-  float s = 0.f;
+  uint4 cx[NC], nx[NC];
+  auto load_row = [&](int64_t r, uint4* dst) {
 #pragma unroll
-  for (int c = 0; c < kLnChunks; ++c) {
-    const int i = lane + 32 * c;
-    if (i < nvec) {
-      Vec<T>::load(x + row * d + (int64_t)i * VN, v[c]);
-      if (res != nullptr) {
-        float r[VN];
-        Vec<T>::load(res + row * d + (int64_t)i * VN, r);
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        dst[c] = ldg16(x + r * d + (int64_t)i * VN);
+        if (res != nullptr) {  // fused residual: keep the ROUNDED sum (what the unfused path would have stored)
+          float a[VN], b[VN];
+          unpack16<T>(dst[c], a);
+          unpack16<T>(ldg16(res + r * d + (int64_t)i * VN), b);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) v[c][j] = to_f32(from_f32<T>(v[c][j] + r[j]));  // round like the unfused sum
-        if (sum_out != nullptr) Vec<T>::store(sum_out + row * d + (int64_t)i * VN, v[c]);
+          for (int j = 0; j < VN; ++j) a[j] = to_f32(from_f32<T>(a[j] + b[j]));
+          T tmp[VN];
+#pragma unroll
+          for (int j = 0; j < VN; ++j) tmp[j] = from_f32<T>(a[j]);
+          dst[c] = *reinterpret_cast<const uint4*>(tmp);
+        }
       }
-#pragma unroll
-      for (int j = 0; j < VN; ++j) s += v[c][j];
     }
-  }
-  const float mu = warp_sum(s) / d;
-  float q = 0.f;
+  };
+  load_row(row, cx);
+  for (; row < rows; row += stride) {
+    const bool more = row + stride < rows;
+    if (more) load_row(row + stride, nx);
+    float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < kLnChunks; ++c) {
-    if (lane + 32 * c < nvec) {
+    for (int c = 0; c < NC; ++c)
+      if (lane + 32 * c < nvec) {
+        if (res != nullptr && sum_out != nullptr) *reinterpret_cast<uint4*>(sum_out + row * d + (int64_t)(lane + 32 * c) * VN) = cx[c];
+        float v[VN];
+        unpack16<T>(cx[c], v);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) { const float t = v[c][j] - mu; q += t * t; }
+        for (int j = 0; j < VN; ++j) s += v[j];
+      }
+    const float mu = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (lane + 32 * c < nvec) {
+        float v[VN];
+        unpack16<T>(cx[c], v);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { const float t = v[j] - mu; q += t * t; }
+      }
+    const float rs = rsqrtf(warp_sum(q) / d + eps);
+    if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float v[VN], o[VN], gv[VN], bv[VN];
+        unpack16<T>(cx[c], v);
+#pragma unroll
+        for (int j = 0; j < VN; j += 4) { Vec<float>::load(gamma + i * VN + j, gv + j); Vec<float>::load(beta + i * VN + j, bv + j); }
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] = (v[j] - mu) * rs * gv[j] + bv[j];
+        Vec<T>::store(y + row * d + (int64_t)i * VN, o);
+      }
     }
-  }
-  const float rs = rsqrtf(warp_sum(q) / d + eps);
-  if (lane == 0) { if (mean) mean[row] = mu; if (rstd) rstd[row] = rs; }
 #pragma unroll
-  for (int c = 0; c < kLnChunks; ++c) {
-    const int i = lane + 32 * c;
-    if (i < nvec) {
-      float o[VN], gv[VN], bv[VN];
-#pragma unroll
-      for (int j = 0; j < VN; j += 4) { Vec<float>::load(gamma + i * VN + j, gv + j); Vec<float>::load(beta + i * VN + j, bv + j); }
-#pragma unroll
-      for (int j = 0; j < VN; ++j) o[j] = (v[c][j] - mu) * rs * gv[j] + bv[j];
-      Vec<T>::store(y + row * d + (int64_t)i * VN, o);
-    }
+    for (int c = 0; c < NC; ++c) cx[c] = nx[c];
   }
 }
 
@@ -68,53 +106,65 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
 //   ln_bwd_dx_kernel     one warp per row: dx = rstd (g - mean(g) - xhat mean(g xhat)) [+ dres], g = dy * gamma
 //   ln_bwd_dgb_kernel    column reductions dgamma = sum_rows dy * xhat, dbeta = sum_rows dy (32 column groups x 8 row lanes per
 //                        CTA, the last CTA of a column block folds the row-chunk partials in a fixed order)
-template <typename T>
-__global__ void __launch_bounds__(256)
+template <typename T, int NC>
+__global__ void __launch_bounds__(256, 3)
 ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx, int64_t rows, int d) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = d / VN;
-  const float mu = mean[row], rs = rstd[row];
-  float xh[kLnChunks][VN], g[kLnChunks][VN];
-  float s1 = 0.f, s2 = 0.f;
+  uint4 cx[NC], cd[NC], nx[NC], nd[NC];   // current / next row of x and dy, raw
+  auto load_row = [&](int64_t r, uint4* xd, uint4* dd) {
 #pragma unroll
-  for (int c = 0; c < kLnChunks; ++c) {
-    const int i = lane + 32 * c;
-    if (i < nvec) {
-      float xv[VN], dv[VN], gv[VN];
-      Vec<T>::load(x + row * d + (int64_t)i * VN, xv);
-      Vec<T>::load(dy + row * d + (int64_t)i * VN, dv);
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) { xd[c] = ldg16(x + r * d + (int64_t)i * VN); dd[c] = ldg16(dy + r * d + (int64_t)i * VN); }
+    }
+  };
+  load_row(row, cx, cd);
+  for (; row < rows; row += stride) {
+    const bool more = row + stride < rows;
+    if (more) load_row(row + stride, nx, nd);
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float xv[VN], dv[VN], gv[VN];
+        unpack16<T>(cx[c], xv); unpack16<T>(cd[c], dv);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) {
-        xh[c][j] = (xv[j] - mu) * rs;
-        g[c][j] = dv[j] * gv[j];
-        s1 += g[c][j];
-        s2 += g[c][j] * xh[c][j];
+        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { const float g = dv[j] * gv[j]; s1 += g; s2 += g * ((xv[j] - mu) * rs); }
       }
     }
-  }
-  s1 = warp_sum(s1) / d;
-  s2 = warp_sum(s2) / d;
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
 #pragma unroll
-  for (int c = 0; c < kLnChunks; ++c) {
-    const int i = lane + 32 * c;
-    if (i < nvec) {
-      float o[VN];
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float xv[VN], dv[VN], gv[VN], o[VN];
+        unpack16<T>(cx[c], xv); unpack16<T>(cd[c], dv);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) o[j] = rs * (g[c][j] - s1 - xh[c][j] * s2);
-      if (dres != nullptr) {
-        float r[VN];
-        Vec<T>::load(dres + row * d + (int64_t)i * VN, r);
+        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) o[j] += r[j];
+        for (int j = 0; j < VN; ++j) o[j] = rs * (dv[j] * gv[j] - s1 - (xv[j] - mu) * rs * s2);
+        if (dres != nullptr) {
+          float r[VN];
+          unpack16<T>(ldg16(dres + row * d + (int64_t)i * VN), r);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] += r[j];
+        }
+        Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
       }
-      Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
     }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { cx[c] = nx[c]; cd[c] = nd[c]; }
   }
 }
 
@@ -451,6 +501,17 @@ using namespace tsw;
   else if ((dtype) == TSW_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
   else { set_error("bad dtype %d", (int)(dtype)); return TSW_E_INVALID; }
 
+// chunk count = ceil(d / (32 lanes * VN)), rounded up to an instantiated value
+#define LN_DISPATCH_NC(nc, ...)                               \
+  do {                                                        \
+    if ((nc) <= 1) { constexpr int NC = 1; __VA_ARGS__; }      \
+    else if ((nc) <= 2) { constexpr int NC = 2; __VA_ARGS__; } \
+    else if ((nc) <= 3) { constexpr int NC = 3; __VA_ARGS__; } \
+    else if ((nc) <= 4) { constexpr int NC = 4; __VA_ARGS__; } \
+    else if ((nc) <= 6) { constexpr int NC = 6; __VA_ARGS__; } \
+    else { constexpr int NC = 8; __VA_ARGS__; }                \
+  } while (0)
+
 extern "C" int tsw_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y, void* sum_out,
                                  float* mean, float* rstd, int64_t rows, int64_t d, float eps, int dtype, tsw_stream_t stream) {
   TSW_CHECK_ARG(x && y && gamma && beta && rows > 0 && d > 0, "layernorm_fwd: null/empty argument");
@@ -458,9 +519,10 @@ extern "C" int tsw_layernorm_fwd(const void* x, const void* res, const float* ga
   TSW_CHECK_ARG(d % vn == 0 && d / vn <= 32 * kLnChunks, "layernorm_fwd: d=%lld unsupported (need d %% %d == 0, d <= %d)",
                 (long long)d, vn, 32 * kLnChunks * vn);
   TSW_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!res || aligned16(res)) && (!sum_out || aligned16(sum_out)), "layernorm_fwd: pointers must be 16-byte aligned");
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  DISPATCH_T(dtype, (layernorm_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)res, gamma, beta, (T*)y,
-                                                                                 (T*)sum_out, mean, rstd, rows, (int)d, eps)));
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 4);
+  const int nc = (int)((d / vn + 31) / 32);
+  DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (layernorm_fwd_kernel<T, NC><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)res, gamma, beta, (T*)y,
+                                                                                 (T*)sum_out, mean, rstd, rows, (int)d, eps))));
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }
@@ -481,8 +543,9 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!dres || aligned16(dres)), "layernorm_bwd: pointers must be 16-byte aligned");
   if (!workspace || workspace_bytes < tsw_layernorm_bwd_workspace_bytes(rows, d)) { set_error("layernorm_bwd: workspace too small"); return TSW_E_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
-  const unsigned grid = (unsigned)((rows + 7) / 8);
-  DISPATCH_T(dtype, (ln_bwd_dx_kernel<T><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d)));
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 3);
+  const int nc = (int)((d / vn + 31) / 32);
+  DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (ln_bwd_dx_kernel<T, NC><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d))));
   TSW_LAUNCH_CHECK();
   const int64_t chunks = colsum_chunks(rows, d, vn);
   const int64_t rpc = (rows + chunks - 1) / chunks;
