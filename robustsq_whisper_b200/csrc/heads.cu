@@ -12,10 +12,17 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace tsw {
+
+// one bulk asynchronous copy (TMA, non-tensor form) of a contiguous slab into shared memory, completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 constexpr int kAspThreads = 256;
 constexpr int kMaxCPT = 2;  // vector chunks per thread along d (d <= 256 * kMaxCPT * VN)
@@ -58,18 +65,30 @@ asp_fwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, float* __r
   const T* xb = x + (int64_t)b * Tlen * d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* colA = reinterpret_cast<float*>(smem_raw);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t slab_bytes = RESIDENT ? (((size_t)rows_per * d * sizeof(T) + 127) & ~(size_t)127) : 0;
+  T* slab = reinterpret_cast<T*>(smem_raw);
+  float* colA = reinterpret_cast<float*>(smem_raw + slab_bytes);
   float* muP = colA + d;
   float* m2P = muP + d;
   float* pvec = m2P + d;
   float* sc = pvec + d;                 // rows_per
   float* red = sc + ((rows_per + 3) & ~3);
   float* xchg = red + 40;               // 8 floats
-  T* slab = reinterpret_cast<T*>(xchg + 8);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xchg + 8);
 
+  if (RESIDENT) {   // the CTA's slab of frames is contiguous in HBM: one bulk copy brings it in, x is read exactly once
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0 && nrows > 0) {
+      const uint32_t bytes = (uint32_t)((size_t)nrows * d * sizeof(T));
+      mbar_expect_tx(bar, bytes);
+      bulk_load(slab, xb + (int64_t)r0 * d, bytes, bar);
+    }
+  }
   for (int j = tid; j < 3 * d; j += kAspThreads) colA[j] = 0.f;
   __syncthreads();
+  if (RESIDENT && nrows > 0) mbar_wait(bar, 0);
 
   const AspMap<T> map(d);
   // ---- phase 0: stage the slab, column sums
@@ -85,8 +104,7 @@ asp_fwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, float* __r
         if (i < map.ncpt) {
           const int c = map.chunk(i);
           float xv[VN];
-          Vec<T>::load(xb + (int64_t)(r0 + t) * d + c * VN, xv);
-          if (RESIDENT) Vec<T>::store(slab + (int64_t)t * d + c * VN, xv);
+          Vec<T>::load((RESIDENT ? slab + (int64_t)t * d : xb + (int64_t)(r0 + t) * d) + c * VN, xv);
 #pragma unroll
           for (int j = 0; j < VN; ++j) acc[i][j] += xv[j];
         }
@@ -196,8 +214,10 @@ asp_bwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, const floa
   T* gxb = gx + (int64_t)b * Tlen * d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* pvec = reinterpret_cast<float*>(smem_raw);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const size_t slab_bytes = RESIDENT ? (((size_t)rows_per * d * sizeof(T) + 127) & ~(size_t)127) : 0;
+  T* slab = reinterpret_cast<T*>(smem_raw);
+  float* pvec = reinterpret_cast<float*>(smem_raw + slab_bytes);
   float* gmu = pvec + d;
   float* gm2 = gmu + d;
   float* gpP = gm2 + d;
@@ -206,7 +226,17 @@ asp_bwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, const floa
   float* g_s = a_s + ((rows_per + 3) & ~3);       // rows_per
   float* red = g_s + ((rows_per + 3) & ~3);
   float* xchg = red + 40;
-  T* slab = reinterpret_cast<T*>(xchg + 8);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(xchg + 8);
+
+  if (RESIDENT) {
+    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    __syncthreads();
+    if (tid == 0 && nrows > 0) {
+      const uint32_t bytes = (uint32_t)((size_t)nrows * d * sizeof(T));
+      mbar_expect_tx(bar, bytes);
+      bulk_load(slab, xb + (int64_t)r0 * d, bytes, bar);
+    }
+  }
 
   const float nrm = saved[b * 4 + 0], M = saved[b * 4 + 1], invZ = 1.f / saved[b * 4 + 2];
   for (int j = tid; j < d; j += kAspThreads) {
@@ -218,17 +248,8 @@ asp_bwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, const floa
     gpP[j] = 0.f;
   }
   const AspMap<T> map(d);
-  if (RESIDENT && map.active) {
-    for (int t = map.rg; t < nrows; t += map.RG)
-#pragma unroll
-      for (int i = 0; i < kMaxCPT; ++i)
-        if (i < map.ncpt) {
-          float xv[VN];
-          Vec<T>::load(xb + (int64_t)(r0 + t) * d + map.chunk(i) * VN, xv);
-          Vec<T>::store(slab + (int64_t)t * d + map.chunk(i) * VN, xv);
-        }
-  }
   __syncthreads();
+  if (RESIDENT && nrows > 0) mbar_wait(bar, 0);
 
   // ---- phase 1: a_t and g_a_t
   float dl = 0.f;
@@ -432,23 +453,34 @@ aam_gw_kernel(const float* __restrict__ fhat, const float* __restrict__ w, const
   }
 }
 
-// g_fhat[b] = sum_j gcos[b][j] * what_j ; kRows rows per CTA share each class row read
+// g_fhat[b] = sum_j gcos[b][j] * what_j.  CTA = 32 columns x 8 class lanes for kGfRows feature rows: a warp reads 128
+// contiguous bytes of one class row per step, the 8 class lanes are folded through shared memory.
 constexpr int kGfRows = 4;
 __global__ void __launch_bounds__(256)
 aam_gfhat_kernel(const float* __restrict__ w, const float* __restrict__ winv, const float* __restrict__ gcos, int B, int C, int d,
                  float* __restrict__ gfhat) {
+  __shared__ float sm[8][kGfRows][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.y * 32 + tx;
   const int b0 = blockIdx.x * kGfRows;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc[kGfRows];
+  float acc[kGfRows];
 #pragma unroll
-    for (int r = 0; r < kGfRows; ++r) acc[r] = 0.f;
-    for (int j = 0; j < C; ++j) {
-      const float wh = w[(int64_t)j * d + c] * winv[j];
+  for (int r = 0; r < kGfRows; ++r) acc[r] = 0.f;
+  if (col < d) {
+    for (int j = ty; j < C; j += 8) {
+      const float wh = w[(int64_t)j * d + col] * winv[j];
 #pragma unroll
       for (int r = 0; r < kGfRows; ++r) if (b0 + r < B) acc[r] = fmaf(gcos[(int64_t)(b0 + r) * C + j], wh, acc[r]);
     }
+  }
 #pragma unroll
-    for (int r = 0; r < kGfRows; ++r) if (b0 + r < B) gfhat[(int64_t)(b0 + r) * d + c] = acc[r];
+  for (int r = 0; r < kGfRows; ++r) sm[ty][r][tx] = acc[r];
+  __syncthreads();
+  if (ty < kGfRows && col < d && b0 + ty < B) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][ty][tx];
+    gfhat[(int64_t)(b0 + ty) * d + col] = t;
   }
 }
 
@@ -543,9 +575,10 @@ template <typename T, typename GT>
 __global__ void __launch_bounds__(512)
 lsce_kernel(const T* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ targets, int64_t ignore_id,
             float smoothing, float grad_scale, float* __restrict__ loss_sum, int32_t* __restrict__ counts, GT* __restrict__ dl,
-            int64_t ld_dl) {
+            int64_t ld_dl, int vec_ok) {
   __shared__ float red[40];
   __shared__ int redi;
+  constexpr int VN = Vec<T>::N;
   const int64_t row = blockIdx.x;
   const int tid = threadIdx.x;
   const T* l = logits + row * ld;
@@ -556,13 +589,24 @@ lsce_kernel(const T* __restrict__ logits, int64_t V, int64_t ld, const int64_t* 
     return;
   }
   const float ly = to_f32(l[y]);  // read before the in-place gradient write (dl may alias logits)
+  const int64_t nvec = vec_ok ? V / VN : 0;   // rows are 16-byte aligned (ld % VN == 0): whole vectors, then a scalar tail
   // online max / sum-exp and the plain sum of logits in one pass
   float m = -INFINITY, z = 0.f, sl = 0.f;
-  for (int64_t j = tid; j < V; j += blockDim.x) {
-    const float v = to_f32(l[j]);
+  auto fold = [&](float v) {
     sl += v;
     if (v > m) { z = z * expf(m - v) + 1.f; m = v; } else { z += expf(v - m); }
+  };
+  for (int64_t i = tid; i < nvec; i += blockDim.x) {
+    float v[VN];
+    Vec<T>::load(l + i * VN, v);
+    float vm = v[0];
+#pragma unroll
+    for (int j = 1; j < VN; ++j) vm = fmaxf(vm, v[j]);
+    if (vm > m) { z *= expf(m - vm); m = vm; }   // one rescale per vector
+#pragma unroll
+    for (int j = 0; j < VN; ++j) { sl += v[j]; z += expf(v[j] - m); }
   }
+  for (int64_t j = nvec * VN + tid; j < V; j += blockDim.x) fold(to_f32(l[j]));
   const float M = block_max(m, red);
   z = block_sum(m == -INFINITY ? 0.f : z * expf(m - M), red);
   sl = block_sum(sl, red);
@@ -570,7 +614,22 @@ lsce_kernel(const T* __restrict__ logits, int64_t V, int64_t ld, const int64_t* 
   if (tid == 0) redi = 0x7fffffff;
   __syncthreads();
   const float conf = 1.f - smoothing, low = smoothing / (float)(V - 1);
-  for (int64_t j = tid; j < V; j += blockDim.x) {
+  const bool gvec = g != nullptr && vec_ok && sizeof(GT) == sizeof(T);
+  for (int64_t i = tid; i < nvec; i += blockDim.x) {
+    float v[VN], o[VN];
+    Vec<T>::load(l + i * VN, v);
+#pragma unroll
+    for (int j = 0; j < VN; ++j) {
+      if (v[j] == M) atomicMin(&redi, (int)(i * VN + j));
+      o[j] = grad_scale * (expf(v[j] - lse) - ((i * VN + j) == y ? conf : low));
+    }
+    if (gvec) Vec<GT>::store(g + i * VN, o);
+    else if (g) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) g[i * VN + j] = from_f32<GT>(o[j]);
+    }
+  }
+  for (int64_t j = nvec * VN + tid; j < V; j += blockDim.x) {
     const float v = to_f32(l[j]);
     if (v == M) atomicMin(&redi, (int)j);
     if (g) g[j] = from_f32<GT>(grad_scale * (expf(v - lse) - (j == y ? conf : low)));
@@ -608,7 +667,7 @@ log_softmax_kernel(const T* __restrict__ logits, int64_t V, int64_t ld, float* _
 using namespace tsw;
 
 static size_t asp_fixed_smem(int64_t d, int rows_per, int nvecs, int nrowbufs) {
-  return sizeof(float) * ((size_t)nvecs * d + (size_t)nrowbufs * ((rows_per + 3) & ~3) + 48);
+  return sizeof(float) * ((size_t)nvecs * d + (size_t)nrowbufs * ((rows_per + 3) & ~3) + 48) + 16 + 128;
 }
 
 extern "C" int tsw_asp_pool_fwd(const void* x, int dtype, int64_t B, int64_t T, int64_t d, float gamma, float* ms, float* ptil,
@@ -620,7 +679,7 @@ extern "C" int tsw_asp_pool_fwd(const void* x, int dtype, int64_t B, int64_t T, 
   const int CL = asp_cluster_size(T);
   const int rows_per = (int)((T + CL - 1) / CL);
   const size_t fixed = asp_fixed_smem(d, rows_per, 4, 1);
-  const size_t slab = (size_t)rows_per * d * (dtype == TSW_F32 ? 4 : 2);
+  const size_t slab = (((size_t)rows_per * d * (dtype == TSW_F32 ? 4 : 2)) + 127) & ~(size_t)127;
   const bool resident = fixed + slab <= 200 * 1024;
   const size_t smem = fixed + (resident ? slab : 0);
   TSW_CHECK_ARG(smem <= 220 * 1024, "asp_pool_fwd: T=%lld d=%lld needs %zu B of shared memory", (long long)T, (long long)d, smem);
@@ -641,7 +700,7 @@ extern "C" int tsw_asp_pool_bwd(const void* x, int dtype, int64_t B, int64_t T, 
   const int CL = asp_cluster_size(T);
   const int rows_per = (int)((T + CL - 1) / CL);
   const size_t fixed = asp_fixed_smem(d, rows_per, 5, 2);
-  const size_t slab = (size_t)rows_per * d * (dtype == TSW_F32 ? 4 : 2);
+  const size_t slab = (((size_t)rows_per * d * (dtype == TSW_F32 ? 4 : 2)) + 127) & ~(size_t)127;
   const bool resident = fixed + slab <= 200 * 1024;
   const size_t smem = fixed + (resident ? slab : 0);
   TSW_CHECK_ARG(smem <= 220 * 1024, "asp_pool_bwd: T=%lld d=%lld needs %zu B of shared memory", (long long)T, (long long)d, smem);
@@ -685,7 +744,7 @@ extern "C" int tsw_aam_softmax_fwd_bwd(const float* f, const float* w, const int
   TSW_LAUNCH_CHECK();
   aam_gw_kernel<<<cgrid, 256, 0, st>>>(fhat, w, winv, gcos, (int)B, (int)C, (int)d, gw);
   TSW_LAUNCH_CHECK();
-  aam_gfhat_kernel<<<(unsigned)((B + kGfRows - 1) / kGfRows), 256, 0, st>>>(w, winv, gcos, (int)B, (int)C, (int)d, gfhat);
+  aam_gfhat_kernel<<<dim3((unsigned)((B + kGfRows - 1) / kGfRows), (unsigned)((d + 31) / 32)), 256, 0, st>>>(w, winv, gcos, (int)B, (int)C, (int)d, gfhat);
   TSW_LAUNCH_CHECK();
   return tsw_l2norm_bwd(fhat, fnorm, gfhat, gf, B, d, 1e-12f, stream);
 }
@@ -722,7 +781,9 @@ extern "C" int tsw_lsce_fwd_bwd(const void* logits, int dtype, int64_t rows, int
   cudaStream_t st = as_stream(stream);
   TSW_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(float), st));
   TSW_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int32_t), st));
-#define LSCE(TT, GT) lsce_kernel<TT, GT><<<(unsigned)rows, 512, 0, st>>>((const TT*)logits, V, ld, targets, ignore_id, smoothing, grad_scale, loss_sum, counts, (GT*)dlogits, ld_dl)
+  const int vn_l = dtype == TSW_F32 ? 4 : 8;
+  const int vec_ok = aligned16(logits) && ld % vn_l == 0 && (!dlogits || (aligned16(dlogits) && ld_dl % vn_l == 0));
+#define LSCE(TT, GT) lsce_kernel<TT, GT><<<(unsigned)rows, 512, 0, st>>>((const TT*)logits, V, ld, targets, ignore_id, smoothing, grad_scale, loss_sum, counts, (GT*)dlogits, ld_dl, vec_ok)
   if (dtype == TSW_F32 && dl_dtype == TSW_F32) LSCE(float, float);
   else if (dtype == TSW_F32 && dl_dtype == TSW_BF16) LSCE(float, __nv_bfloat16);
   else if (dtype == TSW_BF16 && dl_dtype == TSW_BF16) LSCE(__nv_bfloat16, __nv_bfloat16);
