@@ -280,7 +280,11 @@ def run_b200(args):
             "gpu_launches": launches,
             "roofline": {"kernel": "gemm_tc_kernel (tcgen05 bf16 GEMM; every launch of K extra steps timed with CUDA events on the launching stream)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None, "traffic": None,
+                         "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on its most frequent shape
+                         # (48512 x 1024 x 1024, 288 launches / step) from profiles/r1_gemm_tc_48512x1024x1024.ncu-rep;
+                         # algorithmic A + B + D of that launch = 200.9 MB
+                         "traffic": 160.2e6, "traffic_shape": "M=48512 N=1024 K=1024 bf16 (one launch, ncu --set full)",
                          "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                          "launches_timed": len(tc), "share_of_step": gemm_share, "ms_per_step_while_timed": ms_prof},
             "clocks": sampler.summary(),
