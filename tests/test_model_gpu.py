@@ -151,3 +151,52 @@ def test_base_bf16_training_step_runs_and_matches_port_losses():
     assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
     n_with_grad = sum(p.grad is not None for p in m.parameters())
     assert n_with_grad == sum(p.requires_grad for p in m.parameters()) - 0
+
+
+def test_edge_cases_batch1_and_over_30s_truncation():
+    """B = 1 (no same-speaker structure, no raggedness) and a 31 s mixture: positions beyond the 1500-row sinusoid table
+    are truncated exactly like the reference (whisper_encoder.py:451-455)."""
+    batch = synth.make_batch(1, 31.0, 1.5, ragged=False)
+    m, cfg, sd = build_model("tiny", 0, torch.float32)
+    with torch.no_grad():
+        ref = port.encoder_forward(sd, cfg, batch["speech"], batch["speech_lengths"], batch["enroll"], batch["enroll_lengths"])
+        b = to_cuda(batch)
+        got = m.encode(b["speech"], b["speech_lengths"], b["enroll"], b["enroll_lengths"])
+    assert got[0].shape == ref[0].shape == (1, 16 + 1500, 384)
+    assert torch.equal(got[1].cpu(), ref[1])
+    for g, r in zip((got[0], got[2], got[3]), (ref[0], ref[2], ref[3])):
+        assert rel(g, r) < 5e-4
+
+
+def test_short_enrollment_and_heavy_padding_masks():
+    """Enrollment much shorter than its padded length and a mixture with half of the frames padded: key-length masks of the
+    SQ-Former self- and cross-attention (Qformer.py:786, qformer_adapter.py:69-75)."""
+    batch = synth.make_batch(3, 6.0, 4.0, ragged=False)
+    batch["enroll_lengths"] = torch.tensor([64000, 9000, 1600])
+    batch["speech_lengths"] = torch.tensor([96000, 48000, 20000])
+    for i in range(3):
+        batch["enroll"][i, batch["enroll_lengths"][i]:] = 0
+        batch["speech"][i, batch["speech_lengths"][i]:] = 0
+    for dtype, tol in ((torch.float32, 5e-4), (torch.bfloat16, 3e-2)):
+        m, cfg, sd = build_model("tiny", 0, dtype)
+        with torch.no_grad():
+            ref = port.encoder_forward(sd, cfg, batch["speech"], batch["speech_lengths"], batch["enroll"], batch["enroll_lengths"])
+            b = to_cuda(batch)
+            got = m.encode(b["speech"], b["speech_lengths"], b["enroll"], b["enroll_lengths"])
+        assert torch.equal(got[1].cpu(), ref[1])
+        for g, r in zip((got[0], got[2], got[3]), (ref[0], ref[2], ref[3])):
+            assert rel(g.float(), r) < tol
+
+
+def test_epoch_warmups_change_the_losses_like_the_port():
+    """epoch < warm_up_epochs: AAM margin 0 and ASP gamma on its ramp (ts_qformer_espnet_model.py:377-380,742-750)."""
+    batch = synth.make_batch(4, 3.0, 2.0, text_len=9)
+    m, cfg, sd = build_model("tiny", 0, torch.float32)
+    neg_idx = torch.multinomial(port.negative_weight(port.similarity_weight(batch["utt_id"])), 10, replacement=True)
+    for epoch in (0, 3):
+        m.set_epoch(epoch)
+        with torch.no_grad():
+            _, rs, _ = port.model_forward(sd, cfg, {k: (v.clone() if torch.is_tensor(v) else v) for k, v in batch.items()}, epoch=epoch, neg_idx=neg_idx)
+            _, stats, _ = m(**to_cuda(batch), neg_idx=neg_idx)
+        for k in ("loss_con", "loss_aam", "loss_att"):
+            assert stats[k].item() == pytest.approx(float(rs[k]), rel=2e-4), (epoch, k)
