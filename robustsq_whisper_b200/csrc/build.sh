@@ -8,7 +8,7 @@ mkdir -p "$OBJ"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --use_fast_math"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 pids=()
-for f in errors logmel ops heads gemm gemm_simt gemm_tc fmha ${TSW_EXTRA_SRCS:-}; do
+for f in errors logmel ops heads gemm gemm_simt gemm_tc fmha decode ${TSW_EXTRA_SRCS:-}; do
   if [ ! -f "$OBJ/$f.o" ] || [ "$f.cu" -nt "$OBJ/$f.o" ] || [ common.cuh -nt "$OBJ/$f.o" ] || [ gemm_common.cuh -nt "$OBJ/$f.o" ] || [ tc_ptx.cuh -nt "$OBJ/$f.o" ] || [ ../../include/tsw.h -nt "$OBJ/$f.o" ]; then
     nvcc $FLAGS -c "$f.cu" -o "$OBJ/$f.o" &
     pids+=($!)

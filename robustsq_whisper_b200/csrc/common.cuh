@@ -132,10 +132,10 @@ template <> struct Vec<__nv_bfloat16> {
     for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(t.v[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
   }
   __device__ static void store(__nv_bfloat16* p, const float* in) {
-    bf16x8 t;
+    uint32_t w[4];   // packed through a uint4: a struct-of-bfloat162 copy is split into four 4-byte stores by nvcc
 #pragma unroll
-    for (int i = 0; i < 4; ++i) t.v[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
-    *reinterpret_cast<bf16x8*>(p) = t;
+    for (int i = 0; i < 4; ++i) { const __nv_bfloat162 t = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&t); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
 

@@ -313,6 +313,19 @@ def fmha_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, do: Tensor, lse: Tensor
     return dq, dk, dv
 
 
+def decode_attention(q: Tensor, k_cache: Tensor, v_cache: Tensor, L: int, n_head: int, scale: float) -> Tensor:
+    """q (B, d) one new token; caches (B, Lmax, d) with the first L rows valid -> (B, d)."""
+    require_cuda(q, k_cache, v_cache)
+    lib = _C.load()
+    B, d = q.shape
+    assert k_cache.stride(2) == 1 and v_cache.stride() == k_cache.stride() and d == n_head * 64
+    o = torch.empty((B, d), dtype=q.dtype, device=q.device)
+    check(lib.tsw_decode_attention(ptr(q), q.stride(0), ptr(k_cache), ptr(v_cache), k_cache.stride(1), k_cache.stride(0), B, n_head, L,
+                                   scale, ptr(o), o.stride(0), dtype_code(q.dtype), stream()), "tsw_decode_attention")
+    _count(1)
+    return o
+
+
 def decoder_embed(E: Tensor, pos: Tensor, prompt: Tensor, ids: Tensor, sop: int, dtype: torch.dtype) -> Tensor:
     lib = _C.load()
     B, n_tok = ids.shape
