@@ -273,11 +273,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ================================================================================================ backward
 // One CTA per (batch, head, 128-key tile); loop over the 128-query tiles that can see it.  Per iteration five MMAs:
 //   S = Q K^T, dP = dO V^T            -> TMEM (lanes = queries)
-//   P = exp2(S*c - lse), dS = P (dP - delta) * scale   (8 warps; thread = query row x 64-key half) -> bf16 in smem, [q][key]
+//   P = exp2(S*c - lse), dS = P (dP - delta) * scale   (16 warps; thread = query row x 32-key slice) -> bf16 in smem, [q][key]
 //   dV += P^T dO, dK += dS^T Q        -> TMEM accumulators over the whole loop (lanes = keys); P / dS are MN-major A operands
-//   dQ_i = dS K                       -> TMEM, staged to smem as fp32 and added into the fp32 dQ buffer with one
-//                                        cp.reduce.async.bulk.tensor (.add) per 32-column panel — no per-thread atomics.
+//   dQ_i = dS K                       -> TMEM (two buffers), staged per warp to smem as fp32 and added into the fp32 dQ buffer
+//                                        with one cp.reduce.async.bulk.tensor (.add) per warp — no per-thread atomics, no CTA barrier.
+// Software pipeline: the gradient warps pull S / dP of tile i into registers and release the TMEM columns at once
+// (s_drained), so the MMA warp issues S / dP of tile i+1 *before* it waits for P / dS of tile i: the tensor pipe computes
+// the next scores and the previous dQ / dV / dK while the gradient warps are in their exp phase.  Q / dO ride a 3-stage ring
+// (tile i+2 is in flight while i is consumed).
 constexpr int FB_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2-17 softmax/gradient (four per TMEM lane quarter: 32 keys each)
+constexpr int FB_QSTAGES = 3;
 
 struct FmhaBwdParams {
   int B, H, Sq, Sk;
@@ -291,14 +296,14 @@ struct FmhaBwdParams {
 
 
 template <bool MASKED>
-__device__ __forceinline__ void bwd_chunk(const float* sv, const float* dpv, float scale_log2, float lse2, float scale, float dlt_s,
+__device__ __forceinline__ void bwd_chunk(const uint32_t* sv, const uint32_t* dpv, float scale_log2, float lse2, float scale, float dlt_s,
                                           int first_key, int row_limit, uint32_t* pk, uint32_t* dk_) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
-    float p0 = ex2_approx(fmaf(sv[i], scale_log2, -lse2));
-    float p1 = ex2_approx(fmaf(sv[i + 1], scale_log2, -lse2));
+    float p0 = ex2_approx(fmaf(__uint_as_float(sv[i]), scale_log2, -lse2));
+    float p1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), scale_log2, -lse2));
     if (MASKED) { if (first_key + i >= row_limit) p0 = 0.f; if (first_key + i + 1 >= row_limit) p1 = 0.f; }
-    const float d0 = p0 * fmaf(dpv[i], scale, -dlt_s), d1 = p1 * fmaf(dpv[i + 1], scale, -dlt_s);   // P (dP - delta) scale
+    const float d0 = p0 * fmaf(__uint_as_float(dpv[i]), scale, -dlt_s), d1 = p1 * fmaf(__uint_as_float(dpv[i + 1]), scale, -dlt_s);   // P (dP - delta) scale
     const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1), db = __floats2bfloat162_rn(d0, d1);
     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
     dk_[i >> 1] = *reinterpret_cast<const uint32_t*>(&db);
@@ -308,12 +313,12 @@ __device__ __forceinline__ void bwd_chunk(const float* sv, const float* dpv, flo
 struct FmhaBwdSmem {
   unsigned char k[kTileBytes];
   unsigned char v[kTileBytes];
-  unsigned char q[2][kTileBytes];
-  unsigned char dO[2][kTileBytes];
+  unsigned char q[FB_QSTAGES][kTileBytes];
+  unsigned char dO[FB_QSTAGES][kTileBytes];
   unsigned char p[2 * kTileBytes];    // [q][key] bf16, two 64-key panels
   unsigned char ds[2 * kTileBytes];
-  unsigned char dq[2 * kTileBytes];   // fp32 staging: two 32-column panels of [128][128 B], SW128
-  uint64_t kv_full, q_full[2], q_empty[2], s_full, pds_full, dq_full, acc_full;
+  unsigned char dq[2 * kTileBytes];   // fp32 staging: 16 warps x [32 rows][64 B], SW64
+  uint64_t kv_full, q_full[FB_QSTAGES], q_empty[FB_QSTAGES], s_full, s_drained, pds_full, pds_empty, dq_full[2], acc_full;
   uint32_t tmem_slot;
 };
 
@@ -324,6 +329,28 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const v
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 32 TMEM columns -> 32 raw registers, no wait (pair with tmem_ld_wait + tmem_ld_fence32 before the first use)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// empty volatile asm that "rewrites" the 32 registers: pins every consumer of the loaded values behind the wait above
+__device__ __forceinline__ void tmem_ld_fence32(uint32_t* r) {
+  asm volatile(""
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+        "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+        "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+        "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+}
 
 // first / one-past-last query tile that can see key tile kv0 (causal) 
 __device__ __forceinline__ void fmha_q_range(const FmhaBwdParams& p, int kv0, int* qt0, int* qt1) {
@@ -355,27 +382,29 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
     mbar_init(&s.kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
-    mbar_init(&s.s_full, 1); mbar_init(&s.pds_full, 16); mbar_init(&s.dq_full, 1); mbar_init(&s.acc_full, 1);
+    for (int i = 0; i < FB_QSTAGES; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
+    mbar_init(&s.s_full, 1); mbar_init(&s.s_drained, 16); mbar_init(&s.pds_full, 16); mbar_init(&s.pds_empty, 1);
+    mbar_init(&s.dq_full[0], 1); mbar_init(&s.dq_full[1], 1); mbar_init(&s.acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t t_s = s.tmem_slot, t_dp = t_s + 128, t_dv = t_s + 256, t_dk = t_s + 320, t_dq = t_s + 384;
+  const uint32_t t_s = s.tmem_slot, t_dp = t_s + 128, t_dv = t_s + 256, t_dk = t_s + 320, t_dq = t_s + 384;   // dQ: 2 x 64 columns
 
   if (warp == 0) {
     if (lane == 0 && active) {
       mbar_expect_tx(&s.kv_full, 2 * kTileBytes);
       tma_load_4d(&tmK, &s.kv_full, s.k, h * FD, kv0, b, 0);
       tma_load_4d(&tmV, &s.kv_full, s.v, h * FD, kv0, b, 0);
+      int st = 0; uint32_t ph = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
         mbar_wait(&s.q_empty[st], ph ^ 1);
         mbar_expect_tx(&s.q_full[st], 2 * kTileBytes);
         tma_load_4d(&tmQ, &s.q_full[st], s.q[st], h * FD, (qt0 + it) * FQ, b, 0);
         tma_load_4d(&tmdO, &s.q_full[st], s.dO[st], h * FD, (qt0 + it) * FQ, b, 0);
+        if (++st == FB_QSTAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -390,15 +419,12 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t dK_mn = make_smem_desc(ka, kTileBytes, 1024);                                        // MN-major view (dQ)
       const uint64_t dP_mn = make_smem_desc(pa, kTileBytes, 1024), dS_mn = make_smem_desc(dsa, kTileBytes, 1024);
       const uint64_t dS_k0 = make_smem_desc(dsa, 16, 1024), dS_k1 = make_smem_desc(dsa + kTileBytes, 16, 1024);
-      const uint64_t dQ_k[2] = {make_smem_desc(smem_u32(s.q[0]), 16, 1024), make_smem_desc(smem_u32(s.q[1]), 16, 1024)};
-      const uint64_t dQ_mn[2] = {make_smem_desc(smem_u32(s.q[0]), kTileBytes, 1024), make_smem_desc(smem_u32(s.q[1]), kTileBytes, 1024)};
-      const uint64_t dO_k[2] = {make_smem_desc(smem_u32(s.dO[0]), 16, 1024), make_smem_desc(smem_u32(s.dO[1]), 16, 1024)};
-      const uint64_t dO_mn[2] = {make_smem_desc(smem_u32(s.dO[0]), kTileBytes, 1024), make_smem_desc(smem_u32(s.dO[1]), kTileBytes, 1024)};
-      auto issue_scores = [&](int it) {
-        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&s.q_full[st], ph);
+      const uint32_t qa = smem_u32(s.q[0]), oa = smem_u32(s.dO[0]);
+      int sst = 0; uint32_t sph = 0;      // ring position of the next scores issue
+      auto issue_scores = [&]() {
+        mbar_wait(&s.q_full[sst], sph);
         tc_fence_after();
-        const uint64_t qd = dQ_k[st], od = dO_k[st];
+        const uint64_t qd = make_smem_desc(qa + sst * kTileBytes, 16, 1024), od = make_smem_desc(oa + sst * kTileBytes, 16, 1024);
         if (leader_lane) {
         umma_bf16_c<false>(t_s, qd, dK_k, id_s);
 #pragma unroll
@@ -409,21 +435,28 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&s.s_full);
         }
         __syncwarp();
+        if (++sst == FB_QSTAGES) { sst = 0; sph ^= 1; }
       };
       mbar_wait(&s.kv_full, 0);
-      issue_scores(0);
+      issue_scores();
+      int st = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        mbar_wait(&s.pds_full, it & 1);   // P, dS in smem; S, dP and dQ TMEM drained
+        if (it + 1 < n_it) {
+          mbar_wait(&s.s_drained, it & 1);   // S / dP of tile it are in the gradient warps' registers
+          tc_fence_after();
+          issue_scores();                    // tile it + 1: runs while the gradient warps exponentiate tile it
+        }
+        mbar_wait(&s.pds_full, it & 1);      // P, dS of tile it in smem; dQ buffer (it & 1) drained
         tc_fence_after();
-        const uint64_t qd = dQ_mn[st], od = dO_mn[st];
+        const uint64_t qd = make_smem_desc(qa + st * kTileBytes, kTileBytes, 1024), od = make_smem_desc(oa + st * kTileBytes, kTileBytes, 1024);
+        const uint32_t tq = t_dq + (it & 1) * 64;
         if (leader_lane) {
         // dQ_i = dS K first (reduction over the 128 keys): its drain by the gradient warps then overlaps dV / dK below
-        umma_bf16_c<false>(t_dq, dS_k0, dK_mn, id_q);
+        umma_bf16_c<false>(tq, dS_k0, dK_mn, id_q);
 #pragma unroll
         for (int k = 1; k < FK / 16; ++k)
-          umma_bf16_c<true>(t_dq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
-        umma_commit(&s.dq_full);
+          umma_bf16_c<true>(tq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
+        umma_commit(&s.dq_full[it & 1]);
         // dV += P^T dO, dK += dS^T Q: reduction over the 128 queries, 16 per instruction (2048 B per step in both operands)
         if (it == 0) umma_bf16_c<false>(t_dv, dP_mn, od, id_g); else umma_bf16_c<true>(t_dv, dP_mn, od, id_g);
 #pragma unroll
@@ -432,10 +465,11 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dk, desc_advance(dS_mn, k * 2048), desc_advance(qd, k * 2048), id_g);
         umma_commit(&s.q_empty[st]);
+        umma_commit(&s.pds_empty);                      // P / dS smem may be overwritten
         if (it + 1 == n_it) umma_commit(&s.acc_full);   // dK / dV accumulators final
         }
         __syncwarp();
-        if (it + 1 < n_it) issue_scores(it + 1);
+        if (++st == FB_QSTAGES) st = 0;
       }
     }
   } else {
@@ -444,10 +478,10 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int part = (warp - 2) >> 2;      // which 32-key slice (and 16-column slice of dQ / dK / dV) this warp handles
     const int r = quarter * 32 + lane;     // row inside the tile (query row in the loop, key row at the end)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const bool leader = (warp == 2 && lane == 0);
     const int c0 = part * 32;              // first key column of the slice
     const int poff = (part >> 1) * kTileBytes + r * 128;   // 64-key panel + row
     const int ubase = (part & 1) * 4;      // first 16-byte unit of the slice inside the 128-byte panel row
+    unsigned char* stage = s.dq + (warp - 2) * 2048;        // this warp's [32][16] fp32 dQ staging block (SWIZZLE_64B)
     auto load_stats = [&](int it, float& lse_nat, float& dl) {
       const int qn = (qt0 + it) * FQ + r;
       lse_nat = -INFINITY; dl = 0.f;
@@ -456,11 +490,29 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         lse_nat = __ldg(p.lse + idx); dl = __ldg(p.delta + idx);
       }
     };
+    // dQ of tile `it` (TMEM buffer it & 1) -> this warp's staging block -> one TMA reduce-add of 32 rows x 16 columns
+    auto drain_dq = [&](int it) {
+      mbar_wait(&s.dq_full[it & 1], (it >> 1) & 1);
+      tc_fence_after();
+      float v[16];
+      tmem_ld16(t_dq + (it & 1) * 64 + lane_off + part * 16, v);
+      tc_fence_before();
+      if (lane == 0) bulk_wait_read0();       // this warp's previous reduce has finished reading the staging block
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        *reinterpret_cast<float4*>(stage + lane * 64 + ((t ^ ((lane >> 1) & 3)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_4d(&tmdQ, stage, h * FD + part * 16, (qt0 + it) * FQ + quarter * 32, b, 0);
+        bulk_commit();
+      }
+    };
     float lse_next, dlt_next;
     load_stats(0, lse_next, dlt_next);
     for (int it = 0; it < n_it; ++it) {
-      const int q0 = (qt0 + it) * FQ;
-      const int qi = q0 + r;
+      const int qi = (qt0 + it) * FQ + r;
       const float lse2 = lse_next * 1.44269504088896340736f, dlt = dlt_next;
       load_stats(it + 1, lse_next, dlt_next);   // in flight during this iteration
       int row_limit = 0;
@@ -471,46 +523,30 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool full = kv0 + c0 + 32 <= row_limit;
       mbar_wait(&s.s_full, it & 1);
       tc_fence_after();
-      {
-        float sv[32], dpv[32];
-        tmem_ld32(t_s + lane_off + c0, sv);
-        tmem_ld32(t_dp + lane_off + c0, dpv);
-        uint32_t pk[16], dk_[16];
-        if (full) bwd_chunk<false>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
-        else bwd_chunk<true>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int u = (ubase + t) ^ (r & 7);
-          *reinterpret_cast<uint4*>(s.p + poff + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-          *reinterpret_cast<uint4*>(s.ds + poff + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
-        }
-      }
-      fence_async_smem();
+      uint32_t sv[32], dpv[32];
+      tmem_ld32_async(t_s + lane_off + c0, sv);
+      tmem_ld32_async(t_dp + lane_off + c0, dpv);
+      tmem_ld_wait();
+      tmem_ld_fence32(sv); tmem_ld_fence32(dpv);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s.pds_full);
-      // dQ tile of this iteration -> fp32 smem panels -> TMA reduce-add into the global fp32 dQ
-      mbar_wait(&s.dq_full, it & 1);
-      tc_fence_after();
-      if (leader) bulk_wait_read0();            // the previous reduce has finished reading the staging buffer
-      named_bar_sync(1, 512);
-      {
-        float v[16];
-        tmem_ld16(t_dq + lane_off + part * 16, v);
-        unsigned char* row = s.dq + poff;      // 32-column fp32 panel (part >> 1), this row
+      if (lane == 0) mbar_arrive(&s.s_drained);          // the MMA warp may overwrite S / dP with the next tile
+      uint32_t pk[16], dk_[16];
+      if (full) bwd_chunk<false>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
+      else bwd_chunk<true>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
+      if (it > 0) mbar_wait(&s.pds_empty, (it - 1) & 1);  // dV / dK of the previous tile have consumed P / dS
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          *reinterpret_cast<float4*>(row + (((ubase + t) ^ (r & 7)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+      for (int t = 0; t < 4; ++t) {
+        const int u = (ubase + t) ^ (r & 7);
+        *reinterpret_cast<uint4*>(s.p + poff + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+        *reinterpret_cast<uint4*>(s.ds + poff + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
       }
       fence_async_smem();
-      tc_fence_before();
-      named_bar_sync(1, 512);
-      if (leader) {
-        tma_reduce_add_4d(&tmdQ, s.dq, h * FD, q0, b, 0);
-        tma_reduce_add_4d(&tmdQ, s.dq + kTileBytes, h * FD + 32, q0, b, 0);
-        bulk_commit();
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.pds_full);
+      if (it > 0) drain_dq(it - 1);   // finished long ago; its TMEM buffer is rewritten only after pds_full of tile it + 1
     }
+    if (n_it > 0) drain_dq(n_it - 1);
     // ---- dK, dV of this key tile (lanes = keys); inactive tiles write zeros
     const int key = kv0 + r;
     if (active) { mbar_wait(&s.acc_full, 0); tc_fence_after(); }  // all MMAs of the last iteration have completed
@@ -528,7 +564,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
     }
-    if (leader) bulk_wait0();   // the last reduce must be complete before the CTA (and its smem) goes away
+    if (lane == 0) bulk_wait0();   // this warp's last reduce must be complete before the CTA (and its smem) goes away
     tc_fence_before();
   }
   __syncthreads();
@@ -558,10 +594,10 @@ static int make_bsd_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S,
   cuuint64_t dims[4] = {(cuuint64_t)d_cols, (cuuint64_t)S, (cuuint64_t)B, 1};
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)S * ld * es, (cuuint64_t)B * S * ld * es};
-  cuuint32_t box[4] = {f32 ? 32u : 64u, 128u, 1u, 1u};  // 128-byte inner box either way
+  cuuint32_t box[4] = {f32 ? 16u : 64u, f32 ? 32u : 128u, 1u, 1u};  // bf16 operand tiles: 128 rows x 128 B; fp32 dQ reduce: one warp's 32 rows x 64 B
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("fmha: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSW_E_CUDA; }
   return TSW_OK;
 }
