@@ -12,6 +12,7 @@
 //   warp 1      TMEM allocator + MMA issuer (one elected lane)
 //   warps 2-5   softmax / output (each owns the 32 TMEM lanes its index allows)
 // Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
+#include <algorithm>
 #include <mutex>
 
 #include "tc_ptx.cuh"
@@ -271,21 +272,29 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 
 // ================================================================================================ backward
-// One CTA per (batch, head, 128-key tile); loop over the 128-query tiles that can see it.  Per iteration five MMAs:
+// Persistent kernel: one CTA per SM walks the (batch, head, 128-key tile) work items; per item it loops over the 128-query
+// tiles that can see the key tile.  Per query tile five MMAs:
 //   S = Q K^T, dP = dO V^T            -> TMEM (lanes = queries)
 //   P = exp2(S*c - lse), dS = P (dP - delta) * scale   (16 warps; thread = query row x 32-key slice) -> bf16 in smem, [q][key]
-//   dV += P^T dO, dK += dS^T Q        -> TMEM accumulators over the whole loop (lanes = keys); P / dS are MN-major A operands
-//   dQ_i = dS K                       -> TMEM (two buffers), staged per warp to smem as fp32 and added into the fp32 dQ buffer
-//                                        with one cp.reduce.async.bulk.tensor (.add) per warp — no per-thread atomics, no CTA barrier.
+//   dV += P^T dO, dK += dS^T Q        -> TMEM accumulators over the item (lanes = keys); P / dS are MN-major A operands
+//   dQ_i = dS K                       -> TMEM (two buffers), staged by four dedicated warps to smem as fp32 and added into the
+//                                        fp32 dQ buffer with cp.reduce.async.bulk.tensor (.add) — no per-thread atomics.
+// Warp roles (24 warps, register budget re-split with setmaxnreg):
+//   warp 0        TMA producer: K/V double buffer (next item's keys land during the current item), Q/dO ring
+//   warp 1        TMEM allocator + MMA issuer (one elected lane)
+//   warps 4-19    gradient warps (P / dS, final dK / dV)
+//   warps 20-23   dQ drain (TMEM -> smem -> bulk tensor reduce-add), off the gradient warps' critical path
 // Software pipeline: the gradient warps pull S / dP of tile i into registers and release the TMEM columns at once
 // (s_drained), so the MMA warp issues S / dP of tile i+1 *before* it waits for P / dS of tile i: the tensor pipe computes
-// the next scores and the previous dQ / dV / dK while the gradient warps are in their exp phase.  Q / dO ride a 3-stage ring
-// (tile i+2 is in flight while i is consumed).
-constexpr int FB_THREADS = 576;  // warp 0 TMA, warp 1 MMA, warps 2-17 softmax/gradient (four per TMEM lane quarter: 32 keys each)
+// the next scores and the previous dQ / dV / dK while the gradient warps are in their exp phase.  The pipeline runs
+// straight across work items (the first scores of the next item are issued during the last tile of the current one),
+// so per-item prologue / epilogue latencies are hidden.
+constexpr int FB_THREADS = 768;
 constexpr int FB_QSTAGES = 3;
+constexpr int FB_GRAD_WARP0 = 4, FB_DQ_WARP0 = 20;
 
 struct FmhaBwdParams {
-  int B, H, Sq, Sk;
+  int B, H, Sq, Sk, n_kt, total;   // n_kt key tiles per (b, h); total = B * H * n_kt work items
   float scale, scale_log2;
   const int32_t* key_len;
   int causal;
@@ -294,6 +303,8 @@ struct FmhaBwdParams {
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
 };
 
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 template <bool MASKED>
 __device__ __forceinline__ void bwd_chunk(const uint32_t* sv, const uint32_t* dpv, float scale_log2, float lse2, float scale, float dlt_s,
@@ -311,14 +322,15 @@ __device__ __forceinline__ void bwd_chunk(const uint32_t* sv, const uint32_t* dp
 }
 
 struct FmhaBwdSmem {
-  unsigned char k[kTileBytes];
-  unsigned char v[kTileBytes];
+  unsigned char k[2][kTileBytes];     // double-buffered: the next item's K lands during the current item
+  unsigned char v[kTileBytes];        // single: V is dead after the item's last dP, one whole query tile before the item ends
   unsigned char q[FB_QSTAGES][kTileBytes];
   unsigned char dO[FB_QSTAGES][kTileBytes];
   unsigned char p[2 * kTileBytes];    // [q][key] bf16, two 64-key panels
   unsigned char ds[2 * kTileBytes];
-  unsigned char dq[2 * kTileBytes];   // fp32 staging: 16 warps x [32 rows][64 B], SW64
-  uint64_t kv_full, q_full[FB_QSTAGES], q_empty[FB_QSTAGES], s_full, s_drained, pds_full, pds_empty, dq_full[2], acc_full;
+  unsigned char dq[kTileBytes];       // fp32 staging: 4 dQ warps x one panel of [32 rows][128 B], SW128
+  uint64_t k_full[2], k_empty[2], v_full, v_empty, q_full[FB_QSTAGES], q_empty[FB_QSTAGES], s_full, s_drained, pds_full, pds_empty, dq_full[2], dq_empty[2],
+      acc_full;
   uint32_t tmem_slot;
 };
 
@@ -352,15 +364,29 @@ __device__ __forceinline__ void tmem_ld_fence32(uint32_t* r) {
         "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
 }
 
-// first / one-past-last query tile that can see key tile kv0 (causal) 
-__device__ __forceinline__ void fmha_q_range(const FmhaBwdParams& p, int kv0, int* qt0, int* qt1) {
+// work item w -> (batch, head, key tile) and the query tiles [qt0, qt0 + n_it) that can see it; n_it == 0: no gradient reaches the tile
+struct BwdItem { int b, h, kv0, qt0, n_it, klimit, rot; };
+__device__ __forceinline__ BwdItem bwd_item(const FmhaBwdParams& p, int w) {
+  BwdItem I;
+  const int kt = w % p.n_kt, bh = w / p.n_kt;
+  I.h = bh % p.H; I.b = bh / p.H; I.kv0 = kt * FK;
+  I.klimit = p.Sk;
+  if (p.key_len) I.klimit = min(I.klimit, p.key_len[I.b]);
   const int n_q = (p.Sq + FQ - 1) / FQ;
   int lo = 0;
-  if (p.causal) {  // query i sees key k iff k <= i + off  ->  i >= kv0 - off
-    const int off = p.Sk - p.Sq;
-    lo = max(0, kv0 - off) / FQ;
-  }
-  *qt0 = min(lo, n_q); *qt1 = n_q;
+  if (p.causal) lo = max(0, I.kv0 - (p.Sk - p.Sq)) / FQ;   // query i sees key k iff k <= i + (Sk - Sq)
+  I.qt0 = min(lo, n_q);
+  I.n_it = (I.kv0 < I.klimit) ? n_q - I.qt0 : 0;
+  I.rot = I.n_it > 0 ? kt % I.n_it : 0;
+  return I;
+}
+
+// Query tiles are visited in rotated order (start = key-tile index): the CTAs that work on the key tiles of one (batch, head)
+// at the same time then add into different dQ rows and pull different Q / dO tiles, instead of all hitting tile 0 together.
+__device__ __forceinline__ int bwd_qtile(const BwdItem& I, int it) {
+  int t = it + I.rot;
+  if (t >= I.n_it) t -= I.n_it;
+  return I.qt0 + t;
 }
 
 __global__ void __launch_bounds__(FB_THREADS, 1)
@@ -369,22 +395,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   FmhaBwdSmem& s = *reinterpret_cast<FmhaBwdSmem*>(smem_raw);
   const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * FK, h = blockIdx.y, b = blockIdx.z;
   if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_bwd: dynamic smem not 1024-aligned\n"); __trap(); }
-
-  int klimit = p.Sk;
-  if (p.key_len) klimit = min(klimit, p.key_len[b]);
-  int qt0, qt1;
-  fmha_q_range(p, kv0, &qt0, &qt1);
-  const bool active = kv0 < klimit && qt0 < qt1;   // otherwise this key tile receives no gradient
-  const int n_it = active ? qt1 - qt0 : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmdQ);
-    mbar_init(&s.kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.k_full[i], 1); mbar_init(&s.k_empty[i], 1); mbar_init(&s.dq_full[i], 1); mbar_init(&s.dq_empty[i], 4); }
+    mbar_init(&s.v_full, 1); mbar_init(&s.v_empty, 1);
     for (int i = 0; i < FB_QSTAGES; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
     mbar_init(&s.s_full, 1); mbar_init(&s.s_drained, 16); mbar_init(&s.pds_full, 16); mbar_init(&s.pds_empty, 1);
-    mbar_init(&s.dq_full[0], 1); mbar_init(&s.dq_full[1], 1); mbar_init(&s.acc_full, 1);
+    mbar_init(&s.acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
@@ -392,39 +411,63 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t t_s = s.tmem_slot, t_dp = t_s + 128, t_dv = t_s + 256, t_dk = t_s + 320, t_dq = t_s + 384;   // dQ: 2 x 64 columns
+  const int step = gridDim.x;
 
-  if (warp == 0) {
-    if (lane == 0 && active) {
-      mbar_expect_tx(&s.kv_full, 2 * kTileBytes);
-      tma_load_4d(&tmK, &s.kv_full, s.k, h * FD, kv0, b, 0);
-      tma_load_4d(&tmV, &s.kv_full, s.v, h * FD, kv0, b, 0);
-      int st = 0; uint32_t ph = 0;
-      for (int it = 0; it < n_it; ++it) {
-        mbar_wait(&s.q_empty[st], ph ^ 1);
-        mbar_expect_tx(&s.q_full[st], 2 * kTileBytes);
-        tma_load_4d(&tmQ, &s.q_full[st], s.q[st], h * FD, (qt0 + it) * FQ, b, 0);
-        tma_load_4d(&tmdO, &s.q_full[st], s.dO[st], h * FD, (qt0 + it) * FQ, b, 0);
-        if (++st == FB_QSTAGES) { st = 0; ph ^= 1; }
+  if (warp < FB_GRAD_WARP0) {
+    reg_dec<40>();
+    if (warp == 0) {
+      // ===================================================== TMA producer
+      if (lane == 0) {
+        int j = 0, st = 0; uint32_t ph = 0;
+        for (int w = blockIdx.x; w < p.total; w += step) {
+          const BwdItem I = bwd_item(p, w);
+          if (I.n_it == 0) continue;
+          const int kb = j & 1;
+          mbar_wait(&s.k_empty[kb], ((j >> 1) & 1) ^ 1);
+          mbar_expect_tx(&s.k_full[kb], kTileBytes);
+          tma_load_4d(&tmK, &s.k_full[kb], s.k[kb], I.h * FD, I.kv0, I.b, 0);
+          mbar_wait(&s.v_empty, (j & 1) ^ 1);      // the previous item's last dP has read V
+          mbar_expect_tx(&s.v_full, kTileBytes);
+          tma_load_4d(&tmV, &s.v_full, s.v, I.h * FD, I.kv0, I.b, 0);
+          for (int it = 0; it < I.n_it; ++it) {
+            const int q0 = bwd_qtile(I, it) * FQ;
+            mbar_wait(&s.q_empty[st], ph ^ 1);
+            mbar_expect_tx(&s.q_full[st], 2 * kTileBytes);
+            tma_load_4d(&tmQ, &s.q_full[st], s.q[st], I.h * FD, q0, I.b, 0);
+            tma_load_4d(&tmdO, &s.q_full[st], s.dO[st], I.h * FD, q0, I.b, 0);
+            if (++st == FB_QSTAGES) { st = 0; ph ^= 1; }
+          }
+          ++j;
+        }
       }
-    }
-  } else if (warp == 1) {
-    if (active) {   // the whole warp walks the loop (uniform control flow); one elected lane issues the MMAs / commits
+    } else if (warp == 1) {
+      // ===================================================== MMA issuer (whole warp walks the loop; one elected lane issues)
       const bool leader_lane = elect_one();
       const uint32_t id_s = idesc_bf16(128, 128, 0, 0);   // S, dP: K-major x K-major, N = 128 keys
       const uint32_t id_g = idesc_bf16(128, 64, 1, 1);    // dV, dK: A = P^T / dS^T (MN-major), B = dO / Q (MN-major), N = 64
       const uint32_t id_q = idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major over keys), B = K tile (MN-major), N = 64
-      const uint32_t ka = smem_u32(s.k), va = smem_u32(s.v), pa = smem_u32(s.p), dsa = smem_u32(s.ds);
-      // descriptors built once; the issue loop only bumps the address field
-      const uint64_t dK_k = make_smem_desc(ka, 16, 1024), dV_k = make_smem_desc(va, 16, 1024);          // K-major views (S, dP)
-      const uint64_t dK_mn = make_smem_desc(ka, kTileBytes, 1024);                                        // MN-major view (dQ)
+      const uint32_t ka = smem_u32(s.k[0]), va = smem_u32(s.v), pa = smem_u32(s.p), dsa = smem_u32(s.ds);
+      const uint32_t qa = smem_u32(s.q[0]), oa = smem_u32(s.dO[0]);
       const uint64_t dP_mn = make_smem_desc(pa, kTileBytes, 1024), dS_mn = make_smem_desc(dsa, kTileBytes, 1024);
       const uint64_t dS_k0 = make_smem_desc(dsa, 16, 1024), dS_k1 = make_smem_desc(dsa + kTileBytes, 16, 1024);
-      const uint32_t qa = smem_u32(s.q[0]), oa = smem_u32(s.dO[0]);
-      int sst = 0; uint32_t sph = 0;      // ring position of the next scores issue
+      // ---- scores cursor: runs exactly one query tile ahead of the gradient MMAs, across work items
+      int sw = blockIdx.x, sj = -1, s_it = 0, s_nit = 0, sst = 0; uint32_t sph = 0;
+      auto next_item = [&]() -> bool {
+        while (sw < p.total) {
+          const BwdItem I = bwd_item(p, sw);
+          sw += step;
+          if (I.n_it > 0) { s_nit = I.n_it; s_it = 0; ++sj; return true; }
+        }
+        return false;
+      };
+      bool s_valid = next_item();
       auto issue_scores = [&]() {
+        const int kb = sj & 1;
+        if (s_it == 0) { mbar_wait(&s.k_full[kb], (sj >> 1) & 1); mbar_wait(&s.v_full, sj & 1); }
         mbar_wait(&s.q_full[sst], sph);
         tc_fence_after();
         const uint64_t qd = make_smem_desc(qa + sst * kTileBytes, 16, 1024), od = make_smem_desc(oa + sst * kTileBytes, 16, 1024);
+        const uint64_t dK_k = make_smem_desc(ka + kb * kTileBytes, 16, 1024), dV_k = make_smem_desc(va, 16, 1024);
         if (leader_lane) {
         umma_bf16_c<false>(t_s, qd, dK_k, id_s);
 #pragma unroll
@@ -433,140 +476,175 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_dp, desc_advance(od, k * 32), desc_advance(dV_k, k * 32), id_s);
         umma_commit(&s.s_full);
+        if (s_it + 1 == s_nit) umma_commit(&s.v_empty);   // last dP of the item: V may be replaced
         }
         __syncwarp();
         if (++sst == FB_QSTAGES) { sst = 0; sph ^= 1; }
+        if (++s_it == s_nit) s_valid = next_item();
       };
-      mbar_wait(&s.kv_full, 0);
-      issue_scores();
-      int st = 0;
-      for (int it = 0; it < n_it; ++it) {
-        if (it + 1 < n_it) {
-          mbar_wait(&s.s_drained, it & 1);   // S / dP of tile it are in the gradient warps' registers
+      if (s_valid) issue_scores();
+      int g = 0, j = 0, st = 0;
+      for (int w = blockIdx.x; w < p.total; w += step) {
+        const BwdItem I = bwd_item(p, w);
+        if (I.n_it == 0) continue;
+        const int kb = j & 1;
+        const uint64_t dK_mn = make_smem_desc(ka + kb * kTileBytes, kTileBytes, 1024);   // MN-major view of K (dQ)
+        for (int it = 0; it < I.n_it; ++it, ++g) {
+          if (s_valid) {
+            mbar_wait(&s.s_drained, g & 1);    // S / dP of tile g are in the gradient warps' registers
+            tc_fence_after();
+            issue_scores();                    // tile g + 1: runs while the gradient warps exponentiate tile g
+          }
+          mbar_wait(&s.pds_full, g & 1);       // P, dS of tile g in smem
+          mbar_wait(&s.dq_empty[g & 1], ((g >> 1) & 1) ^ 1);   // dQ buffer (tile g - 2) drained
           tc_fence_after();
-          issue_scores();                    // tile it + 1: runs while the gradient warps exponentiate tile it
+          const uint64_t qd = make_smem_desc(qa + st * kTileBytes, kTileBytes, 1024), od = make_smem_desc(oa + st * kTileBytes, kTileBytes, 1024);
+          const uint32_t tq = t_dq + (g & 1) * 64;
+          if (leader_lane) {
+          // dQ = dS K first (reduction over the 128 keys): its drain then overlaps dV / dK below
+          umma_bf16_c<false>(tq, dS_k0, dK_mn, id_q);
+#pragma unroll
+          for (int k = 1; k < FK / 16; ++k)
+            umma_bf16_c<true>(tq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
+          umma_commit(&s.dq_full[g & 1]);
+          // dV += P^T dO, dK += dS^T Q: reduction over the 128 queries, 16 per instruction (2048 B per step in both operands)
+          if (it == 0) umma_bf16_c<false>(t_dv, dP_mn, od, id_g); else umma_bf16_c<true>(t_dv, dP_mn, od, id_g);
+#pragma unroll
+          for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dv, desc_advance(dP_mn, k * 2048), desc_advance(od, k * 2048), id_g);
+          if (it == 0) umma_bf16_c<false>(t_dk, dS_mn, qd, id_g); else umma_bf16_c<true>(t_dk, dS_mn, qd, id_g);
+#pragma unroll
+          for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dk, desc_advance(dS_mn, k * 2048), desc_advance(qd, k * 2048), id_g);
+          umma_commit(&s.q_empty[st]);
+          umma_commit(&s.pds_empty);                        // P / dS smem may be overwritten
+          if (it + 1 == I.n_it) { umma_commit(&s.acc_full); umma_commit(&s.k_empty[kb]); }   // dK / dV final; K / V buffer free
+          }
+          __syncwarp();
+          if (++st == FB_QSTAGES) st = 0;
         }
-        mbar_wait(&s.pds_full, it & 1);      // P, dS of tile it in smem; dQ buffer (it & 1) drained
-        tc_fence_after();
-        const uint64_t qd = make_smem_desc(qa + st * kTileBytes, kTileBytes, 1024), od = make_smem_desc(oa + st * kTileBytes, kTileBytes, 1024);
-        const uint32_t tq = t_dq + (it & 1) * 64;
-        if (leader_lane) {
-        // dQ_i = dS K first (reduction over the 128 keys): its drain by the gradient warps then overlaps dV / dK below
-        umma_bf16_c<false>(tq, dS_k0, dK_mn, id_q);
-#pragma unroll
-        for (int k = 1; k < FK / 16; ++k)
-          umma_bf16_c<true>(tq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
-        umma_commit(&s.dq_full[it & 1]);
-        // dV += P^T dO, dK += dS^T Q: reduction over the 128 queries, 16 per instruction (2048 B per step in both operands)
-        if (it == 0) umma_bf16_c<false>(t_dv, dP_mn, od, id_g); else umma_bf16_c<true>(t_dv, dP_mn, od, id_g);
-#pragma unroll
-        for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dv, desc_advance(dP_mn, k * 2048), desc_advance(od, k * 2048), id_g);
-        if (it == 0) umma_bf16_c<false>(t_dk, dS_mn, qd, id_g); else umma_bf16_c<true>(t_dk, dS_mn, qd, id_g);
-#pragma unroll
-        for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dk, desc_advance(dS_mn, k * 2048), desc_advance(qd, k * 2048), id_g);
-        umma_commit(&s.q_empty[st]);
-        umma_commit(&s.pds_empty);                      // P / dS smem may be overwritten
-        if (it + 1 == n_it) umma_commit(&s.acc_full);   // dK / dV accumulators final
-        }
-        __syncwarp();
-        if (++st == FB_QSTAGES) st = 0;
+        ++j;
       }
     }
-  } else {
-    // ===================================================== P / dS, dQ staging, final dK / dV   (warps 2..17)
-    const int quarter = warp & 3;          // TMEM lane quarter
-    const int part = (warp - 2) >> 2;      // which 32-key slice (and 16-column slice of dQ / dK / dV) this warp handles
-    const int r = quarter * 32 + lane;     // row inside the tile (query row in the loop, key row at the end)
+  } else if (warp < FB_DQ_WARP0) {
+    // ===================================================== gradient warps: P / dS per query tile, dK / dV per item
+    reg_inc<96>();   // 4 x 32 x 40 + 16 x 32 x 96 + 4 x 32 x 56 = 61440 = the 768 x 80 registers the CTA was launched with
+    const int quarter = warp & 3;                     // TMEM lane quarter
+    const int part = (warp - FB_GRAD_WARP0) >> 2;     // which 32-key slice (and 16-column slice of dK / dV) this warp handles
+    const int r = quarter * 32 + lane;                // row inside the tile (query row in the loop, key row at the end)
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const int c0 = part * 32;              // first key column of the slice
+    const int c0 = part * 32;                         // first key column of the slice
     const int poff = (part >> 1) * kTileBytes + r * 128;   // 64-key panel + row
-    const int ubase = (part & 1) * 4;      // first 16-byte unit of the slice inside the 128-byte panel row
-    unsigned char* stage = s.dq + (warp - 2) * 2048;        // this warp's [32][16] fp32 dQ staging block (SWIZZLE_64B)
-    auto load_stats = [&](int it, float& lse_nat, float& dl) {
-      const int qn = (qt0 + it) * FQ + r;
-      lse_nat = -INFINITY; dl = 0.f;
-      if (it < n_it && qn < p.Sq) {
-        const int64_t idx = ((int64_t)b * p.H + h) * p.Sq + qn;
-        lse_nat = __ldg(p.lse + idx); dl = __ldg(p.delta + idx);
+    const int ubase = (part & 1) * 4;                 // first 16-byte unit of the slice inside the 128-byte panel row
+    int g = 0, j = 0;
+    for (int w = blockIdx.x; w < p.total; w += step) {
+      const BwdItem I = bwd_item(p, w);
+      const int key = I.kv0 + r;
+      __nv_bfloat16* dvrow = p.dv + ((int64_t)I.b * p.Sk + key) * p.lddv + I.h * FD + part * 16;
+      __nv_bfloat16* dkrow = p.dk + ((int64_t)I.b * p.Sk + key) * p.lddk + I.h * FD + part * 16;
+      if (I.n_it == 0) {                              // no query sees this key tile: zero gradients
+        if (key < p.Sk) {
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          reinterpret_cast<uint4*>(dvrow)[0] = z; reinterpret_cast<uint4*>(dvrow)[1] = z;
+          reinterpret_cast<uint4*>(dkrow)[0] = z; reinterpret_cast<uint4*>(dkrow)[1] = z;
+        }
+        continue;
       }
-    };
-    // dQ of tile `it` (TMEM buffer it & 1) -> this warp's staging block -> one TMA reduce-add of 32 rows x 16 columns
-    auto drain_dq = [&](int it) {
-      mbar_wait(&s.dq_full[it & 1], (it >> 1) & 1);
-      tc_fence_after();
-      float v[16];
-      tmem_ld16(t_dq + (it & 1) * 64 + lane_off + part * 16, v);
-      tc_fence_before();
-      if (lane == 0) bulk_wait_read0();       // this warp's previous reduce has finished reading the staging block
-      __syncwarp();
+      const int64_t stat_base = ((int64_t)I.b * p.H + I.h) * p.Sq;
+      auto load_stats = [&](int it, float& lse_nat, float& dl) {
+        lse_nat = -INFINITY; dl = 0.f;
+        if (it >= I.n_it) return;
+        const int qn = bwd_qtile(I, it) * FQ + r;
+        if (qn < p.Sq) { lse_nat = __ldg(p.lse + stat_base + qn); dl = __ldg(p.delta + stat_base + qn); }
+      };
+      float lse_next, dlt_next;
+      load_stats(0, lse_next, dlt_next);
+      for (int it = 0; it < I.n_it; ++it, ++g) {
+        const int qi = bwd_qtile(I, it) * FQ + r;
+        const float lse2 = lse_next * 1.44269504088896340736f, dlt = dlt_next;
+        load_stats(it + 1, lse_next, dlt_next);   // in flight during this iteration
+        int row_limit = 0;
+        if (qi < p.Sq && lse2 > -INFINITY) {
+          row_limit = I.klimit;
+          if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
+        }
+        const bool full = I.kv0 + c0 + 32 <= row_limit;
+        mbar_wait(&s.s_full, g & 1);
+        tc_fence_after();
+        uint32_t sv[32], dpv[32];
+        tmem_ld32_async(t_s + lane_off + c0, sv);
+        tmem_ld32_async(t_dp + lane_off + c0, dpv);
+        tmem_ld_wait();
+        tmem_ld_fence32(sv); tmem_ld_fence32(dpv);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.s_drained);          // the MMA warp may overwrite S / dP with the next tile
+        uint32_t pk[16], dk_[16];
+        if (full) bwd_chunk<false>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, I.kv0 + c0, row_limit, pk, dk_);
+        else bwd_chunk<true>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, I.kv0 + c0, row_limit, pk, dk_);
+        if (g > 0) mbar_wait(&s.pds_empty, (g - 1) & 1);   // dV / dK of the previous tile have consumed P / dS
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
-        *reinterpret_cast<float4*>(stage + lane * 64 + ((t ^ ((lane >> 1) & 3)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_reduce_add_4d(&tmdQ, stage, h * FD + part * 16, (qt0 + it) * FQ + quarter * 32, b, 0);
-        bulk_commit();
+        for (int t = 0; t < 4; ++t) {
+          const int u = (ubase + t) ^ (r & 7);
+          *reinterpret_cast<uint4*>(s.p + poff + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          *reinterpret_cast<uint4*>(s.ds + poff + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.pds_full);
       }
-    };
-    float lse_next, dlt_next;
-    load_stats(0, lse_next, dlt_next);
-    for (int it = 0; it < n_it; ++it) {
-      const int qi = (qt0 + it) * FQ + r;
-      const float lse2 = lse_next * 1.44269504088896340736f, dlt = dlt_next;
-      load_stats(it + 1, lse_next, dlt_next);   // in flight during this iteration
-      int row_limit = 0;
-      if (qi < p.Sq && lse2 > -INFINITY) {
-        row_limit = klimit;
-        if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
-      }
-      const bool full = kv0 + c0 + 32 <= row_limit;
-      mbar_wait(&s.s_full, it & 1);
+      // ---- dK, dV of this key tile (lanes = keys)
+      mbar_wait(&s.acc_full, j & 1);   // all MMAs of the item's last tile have completed
       tc_fence_after();
-      uint32_t sv[32], dpv[32];
-      tmem_ld32_async(t_s + lane_off + c0, sv);
-      tmem_ld32_async(t_dp + lane_off + c0, dpv);
-      tmem_ld_wait();
-      tmem_ld_fence32(sv); tmem_ld_fence32(dpv);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.s_drained);          // the MMA warp may overwrite S / dP with the next tile
-      uint32_t pk[16], dk_[16];
-      if (full) bwd_chunk<false>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
-      else bwd_chunk<true>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, kv0 + c0, row_limit, pk, dk_);
-      if (it > 0) mbar_wait(&s.pds_empty, (it - 1) & 1);  // dV / dK of the previous tile have consumed P / dS
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int u = (ubase + t) ^ (r & 7);
-        *reinterpret_cast<uint4*>(s.p + poff + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-        *reinterpret_cast<uint4*>(s.ds + poff + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.pds_full);
-      if (it > 0) drain_dq(it - 1);   // finished long ago; its TMEM buffer is rewritten only after pds_full of tile it + 1
-    }
-    if (n_it > 0) drain_dq(n_it - 1);
-    // ---- dK, dV of this key tile (lanes = keys); inactive tiles write zeros
-    const int key = kv0 + r;
-    if (active) { mbar_wait(&s.acc_full, 0); tc_fence_after(); }  // all MMAs of the last iteration have completed
-    float gv[16], gk[16];
-    if (active) {
+      float gv[16], gk[16];
       tmem_ld16(t_dv + lane_off + part * 16, gv);
       tmem_ld16(t_dk + lane_off + part * 16, gk);
-    } else {
+      tc_fence_before();               // ordered before this warp's next pds_full arrival (-> the next item's first dV / dK MMA)
+      if (key < p.Sk) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) gv[i] = gk[i] = 0.f;
+        for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
+      }
+      ++j;
     }
-    if (key < p.Sk) {
-      __nv_bfloat16* dvrow = p.dv + ((int64_t)b * p.Sk + key) * p.lddv + h * FD + part * 16;
-      __nv_bfloat16* dkrow = p.dk + ((int64_t)b * p.Sk + key) * p.lddk + h * FD + part * 16;
+  } else {
+    // ===================================================== dQ drain warps: TMEM -> swizzled fp32 staging -> bulk tensor reduce-add
+    reg_dec<56>();
+    const int quarter = warp & 3;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    unsigned char* stage = s.dq + quarter * 4096;   // one panel of [32 rows][32 fp32]
+    int g = 0;
+    for (int w = blockIdx.x; w < p.total; w += step) {
+      const BwdItem I = bwd_item(p, w);
+      for (int it = 0; it < I.n_it; ++it, ++g) {
+        const int q0 = bwd_qtile(I, it) * FQ + quarter * 32;
+        mbar_wait(&s.dq_full[g & 1], (g >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
+        for (int half = 0; half < 2; ++half) {      // 32 dQ columns per round through the one staging panel
+          float v[32];
+          tmem_ld16(t_dq + (g & 1) * 64 + lane_off + half * 32, v);
+          tmem_ld16(t_dq + (g & 1) * 64 + lane_off + half * 32 + 16, v + 16);
+          if (half == 1) {                           // every dQ column of this lane quarter is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.dq_empty[g & 1]);
+          }
+          if (lane == 0) bulk_wait_read0();          // the previous reduce has finished reading the staging panel
+          __syncwarp();
+          unsigned char* row = stage + lane * 128;
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            *reinterpret_cast<float4*>(row + ((t ^ (lane & 7)) << 4)) = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (q0 < p.Sq) tma_reduce_add_4d(&tmdQ, stage, I.h * FD + half * 32, q0, I.b, 0);
+            bulk_commit();
+          }
+        }
+      }
     }
-    if (lane == 0) bulk_wait0();   // this warp's last reduce must be complete before the CTA (and its smem) goes away
-    tc_fence_before();
+    if (lane == 0) bulk_wait0();   // the last reduces must be complete before the CTA (and its smem) goes away
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(s.tmem_slot); }
 }
@@ -594,10 +672,10 @@ static int make_bsd_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S,
   cuuint64_t dims[4] = {(cuuint64_t)d_cols, (cuuint64_t)S, (cuuint64_t)B, 1};
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)S * ld * es, (cuuint64_t)B * S * ld * es};
-  cuuint32_t box[4] = {f32 ? 16u : 64u, f32 ? 32u : 128u, 1u, 1u};  // bf16 operand tiles: 128 rows x 128 B; fp32 dQ reduce: one warp's 32 rows x 64 B
+  cuuint32_t box[4] = {f32 ? 32u : 64u, f32 ? 32u : 128u, 1u, 1u};  // bf16 operand tiles: 128 rows x 128 B; fp32 dQ reduce: 32 rows x 128 B
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
   CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   f32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("fmha: cuTensorMapEncodeTiled failed (%d)", (int)r); return TSW_E_CUDA; }
   return TSW_OK;
 }
@@ -671,6 +749,9 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   if ((rc = make_bsd_map(&tdq, dq32, B, Sq, dcols, dcols, true))) return rc;
   FmhaBwdParams p;
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
+  p.n_kt = (int)((Sk + FK - 1) / FK);
+  TSW_CHECK_ARG(B * H * p.n_kt < (1ll << 31), "fmha_bwd: too many work items");
+  p.total = (int)(B * H * p.n_kt);
   p.scale = scale; p.scale_log2 = scale * 1.44269504088896340736f;
   p.key_len = key_len; p.causal = causal ? 1 : 0;
   p.lse = lse; p.delta = delta;
@@ -681,7 +762,7 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
     TSW_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  dim3 grid((unsigned)((Sk + FK - 1) / FK), (unsigned)H, (unsigned)B);
+  const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
   fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   TSW_LAUNCH_CHECK();
   // dq (B, Sq, ldq) bf16 <- fp32 accumulator (contiguous when ldq == H*64, the only layout the host side uses)
