@@ -7,11 +7,16 @@
 //                               tcgen05.commit releases ring slots and publishes the accumulator)
 //   warp 2      TMEM allocator (2 accumulator stages x BN fp32 columns, so the epilogue of tile i overlaps the
 //                               main loop of tile i+1)
-//   warps 4-7   epilogue       (each warp owns the 32 TMEM lanes = tile rows its index allows; 32 columns per tcgen05.ld)
+//   warps 4-11  epilogue       (each warp owns the 32 TMEM lanes = tile rows its index allows; 32 columns per tcgen05.ld)
+// CL = 2: two CTAs of a thread-block cluster work on vertically adjacent output tiles (same columns) and share the B tile:
+// each CTA fetches half of it and TMA-multicasts that half into both shared memories, so a CTA pulls 32 KB instead of
+// 48 KB per stage out of L2 (the ring, not the tensor pipe, is what the K = 1024 shapes wait on).  Ring slots are released
+// by a multicast tcgen05.commit that arrives on both CTAs' `empty` barriers.
 // Operands may be K-major ([rows][K]) or MN-major ([K][rows]) in global memory — the layouts forward, dgrad and wgrad
 // GEMMs need — without any transposition pass: MN-major tiles are fetched as 64-wide column panels and described to
 // the tensor core with the MN-major canonical layout (LBO = panel stride, SBO = 8-row group stride).
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_common.cuh"
@@ -137,7 +142,7 @@ struct TcSmem {
   static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256 + TC_EPI_WARPS * kStgFloats * 4;
 };
 
-template <int BN, int STAGES, typename DT, bool GENERIC>
+template <int BN, int STAGES, typename DT, bool GENERIC, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p, const EpiParams ep) {
   using S = TcSmem<BN, STAGES>;
@@ -157,30 +162,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int64_t w_first = blockIdx.x / CL, w_step = gridDim.x / CL;   // work items are walked per cluster
 
   const int num_kb = (int)((p.K + TBK - 1) / TBK);
-  const int64_t tiles_per_batch = (int64_t)p.tiles_m * p.tiles_n;
+  const int64_t tiles_per_batch = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n;   // work items (tiles, or vertical tile pairs) per batch
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int64_t w = w_first; w < p.total_work; w += w_step) {
         const int64_t t = w / p.splits;
         const int sp = (int)(w - t * p.splits);
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         const int bt = (int)(t / tiles_per_batch);
         const int64_t r = t - (int64_t)bt * tiles_per_batch;
-        const int mt = (int)(r / p.tiles_n), nt = (int)(r - (int64_t)mt * p.tiles_n);
+        const int mt = (int)(r / p.tiles_n) * CL + crank, nt = (int)(r % p.tiles_n);
         const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
         const int m0 = mt * TBM, n0 = nt * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -195,11 +202,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < TBM / 64; ++j) tma_load_4d(&tmA, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);  // box {64 m, 64 k}
           }
-          if (!p.b_mn) {
-            tma_load_4d(&tmB, &full[stage], sb, k0, n0, bi, bo);                       // box {64 k, BN n}
-          } else {
+          if (CL == 1) {
+            if (!p.b_mn) {
+              tma_load_4d(&tmB, &full[stage], sb, k0, n0, bi, bo);                       // box {64 k, BN n}
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_4d(&tmB, &full[stage], sb + j * kPanelBytes, n0 + 64 * j, k0, bi, bo);
+              for (int j = 0; j < BN / 64; ++j) tma_load_4d(&tmB, &full[stage], sb + j * kPanelBytes, n0 + 64 * j, k0, bi, bo);
+            }
+          } else {   // this CTA's half of the B tile, delivered to both CTAs of the pair
+            if (!p.b_mn) {
+              tma_load_4d_mc(&tmB, &full[stage], sb + crank * (S::kBBytes / 2), k0, n0 + crank * (BN / 2), bi, bo, (uint16_t)3);   // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) {
+                const int jj = crank * (BN / 128) + j;
+                tma_load_4d_mc(&tmB, &full[stage], sb + jj * kPanelBytes, n0 + 64 * jj, k0, bi, bo, (uint16_t)3);
+              }
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -213,7 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;  // bytes per UMMA_K = 16
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+      for (int64_t w = w_first; w < p.total_work; w += w_step) {
         const int sp = (int)(w % p.splits);
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -230,7 +249,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+          if (CL > 1) umma_commit_mc(&empty[stage], (uint16_t)3);   // the slot is refilled by both CTAs: release it in both
+          else umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[as]);       // accumulator complete
@@ -251,12 +271,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     DT* const AOp = reinterpret_cast<DT*>(ep.aux_out);
     const int64_t row4 = 4 * ep.ldd;
     int as = 0; uint32_t aphase = 0;
-    for (int64_t w = blockIdx.x; w < p.total_work; w += gridDim.x) {
+    for (int64_t w = w_first; w < p.total_work; w += w_step) {
       const int64_t t = w / p.splits;
       const bool first_split = (w - t * p.splits) == 0;
       const int bt = (int)(t / tiles_per_batch);
       const int64_t r = t - (int64_t)bt * tiles_per_batch;
-      const int mt = (int)(r / p.tiles_n), nt = (int)(r - (int64_t)mt * p.tiles_n);
+      const int mt = (int)(r / p.tiles_n) * CL + crank, nt = (int)(r % p.tiles_n);
       const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
       const int64_t d_off = bo * p.d_so + bi * p.d_si, r_off = bo * p.r_so + bi * p.r_si;
       const int64_t m_first = (int64_t)mt * TBM + q * 32 + rsub;  // this lane's rows: m_first + 4 i, i < 8
@@ -267,13 +287,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (GENERIC) {
         // pull the NEXT tile's extra epilogue operand (residual | aux_in | old D) into L2 now: its loads then hit L2
         // (~250 cycles) instead of DRAM (~800) when that tile's epilogue runs one main loop later
-        const int64_t wn = w + gridDim.x;
+        const int64_t wn = w + w_step;
         const DT* src = Rp ? Rp : ((ep.epilogue == TSW_EPI_MUL_DGELU || ep.epilogue == TSW_EPI_MUL_AUX) ? AIp : (ep.beta != 0.f ? Dp : nullptr));
         if (src != nullptr && wn < p.total_work && ep.res_row_mod == 0) {
           const int64_t tn = wn / p.splits;
           const int btn = (int)(tn / tiles_per_batch);
           const int64_t rn = tn - (int64_t)btn * tiles_per_batch;
-          const int mtn = (int)(rn / p.tiles_n), ntn = (int)(rn - (int64_t)mtn * p.tiles_n);
+          const int mtn = (int)(rn / p.tiles_n) * CL + crank, ntn = (int)(rn % p.tiles_n);
           const int bon = btn / p.batch_inner, bin = btn - bon * p.batch_inner;
           const int64_t ld = Rp ? ep.ldres : ep.ldd;
           const int64_t boff = Rp ? (bon * p.r_so + bin * p.r_si) : (bon * p.d_so + bin * p.d_si);
@@ -345,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer may still multicast into this CTA's smem / barriers until it is done
   if (warp == 2) { tc_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
 }
 
@@ -395,13 +415,13 @@ bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
   return true;
 }
 
-template <int BN, int STAGES, typename DT, bool GENERIC>
+template <int BN, int STAGES, typename DT, bool GENERIC, int CL>
 static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   using S = TcSmem<BN, STAGES>;
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, g.A, g.a_mn_major, g.M, g.K, g.lda, g.batch_inner, g.a_stride_inner, g.batch_outer, g.a_stride_outer, TBM);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, g.B, g.b_mn_major, g.N, g.K, g.ldb, g.batch_inner, g.b_stride_inner, g.batch_outer, g.b_stride_outer, BN);
+  rc = make_operand_map(&tmB, g.B, g.b_mn_major, g.N, g.K, g.ldb, g.batch_inner, g.b_stride_inner, g.batch_outer, g.b_stride_outer, BN / CL);
   if (rc) return rc;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
@@ -409,27 +429,40 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   p.a_mn = g.a_mn_major; p.b_mn = g.b_mn_major;
   p.d_so = g.d_stride_outer; p.d_si = g.d_stride_inner; p.r_so = g.res_stride_outer; p.r_si = g.res_stride_inner;
   p.tiles_m = (int)((g.M + TBM - 1) / TBM); p.tiles_n = (int)((g.N + BN - 1) / BN);
-  p.total_tiles = (int64_t)p.tiles_m * p.tiles_n * p.batches;
+  // CL = 2: a work item is a vertical pair of tiles (one per CTA of the cluster); an odd last row pairs with a phantom
+  // tile whose loads are zero-filled and whose rows the epilogue masks
+  p.total_tiles = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.batches;
+  const int units = sm_count() / CL;   // CTAs (CL = 1) or clusters (CL = 2) that run concurrently
   const int num_kb = (int)((g.K + TBK - 1) / TBK);
   p.splits = 1;
   // split-K when the output has too few tiles to occupy the machine (weight gradients: M, N ~ 1e3, K ~ 5e4): fp32 output,
   // plain epilogue, whole rows 16-byte aligned (vector atomics), one batch
-  if (!GENERIC && sizeof(DT) == 4 && p.batches == 1 && ep.vec4_ok && g.N % 4 == 0 && p.total_tiles * 2 <= sm_count() && num_kb >= 16) {
-    p.splits = (int)std::min<int64_t>(sm_count() / p.total_tiles, num_kb / 8);
+  if (!GENERIC && sizeof(DT) == 4 && p.batches == 1 && ep.vec4_ok && g.N % 4 == 0 && p.total_tiles * 2 <= units && num_kb >= 16) {
+    p.splits = (int)std::min<int64_t>(units / p.total_tiles, num_kb / 8);
     if (p.splits < 1) p.splits = 1;
   }
   p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.total_work = p.total_tiles * p.splits;
   if (p.splits > 1) TSW_CUDA(cudaMemset2DAsync(g.D, (size_t)g.ldd * 4, 0, (size_t)g.N * 4, (size_t)g.M, st));
-  auto kern = gemm_tc_kernel<BN, STAGES, DT, GENERIC>;
+  auto kern = gemm_tc_kernel<BN, STAGES, DT, GENERIC, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     TSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done = true;
   }
-  const int grid = (int)std::min<int64_t>(p.total_work, sm_count());
-  kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, p, ep);
+  const int grid = (int)std::min<int64_t>(p.total_work, units) * CL;
+  if (CL == 1) {
+    kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, p, ep);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::kBytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    TSW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, ep));
+  }
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }
@@ -440,10 +473,15 @@ int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st)
   // wide tiles when N is large enough to fill them; narrow tiles keep more CTAs busy on small N
   const bool wide = g.N > 128;
   const bool generic = ep.epilogue != TSW_EPI_NONE || ep.residual || ep.aux_out || ep.beta != 0.f;
+  // clustered pairs when there are enough tile rows to pair up without stranding half the machine on phantom tiles
+  const int64_t tiles_m = (g.M + TBM - 1) / TBM;
+  static const bool no_cluster = getenv("TSW_GEMM_NO_CLUSTER") != nullptr;
+  const bool pair = wide && !no_cluster && (tiles_m >= 8 || (tiles_m >= 2 && tiles_m % 2 == 0));
 #define TC_DISPATCH(DT)                                                                                   \
   do {                                                                                                    \
-    if (wide) return generic ? tc_go<256, 4, DT, true>(g, ep, st) : tc_go<256, 4, DT, false>(g, ep, st);  \
-    return generic ? tc_go<128, 6, DT, true>(g, ep, st) : tc_go<128, 6, DT, false>(g, ep, st);            \
+    if (pair) return generic ? tc_go<256, 4, DT, true, 2>(g, ep, st) : tc_go<256, 4, DT, false, 2>(g, ep, st);  \
+    if (wide) return generic ? tc_go<256, 4, DT, true, 1>(g, ep, st) : tc_go<256, 4, DT, false, 1>(g, ep, st);  \
+    return generic ? tc_go<128, 6, DT, true, 1>(g, ep, st) : tc_go<128, 6, DT, false, 1>(g, ep, st);            \
   } while (0)
   if (g.d_dtype == TSW_BF16) TC_DISPATCH(__nv_bfloat16);
   if (g.d_dtype == TSW_F32) TC_DISPATCH(float);

@@ -37,3 +37,8 @@ bench(S, 4096, 1024, bias=True, epi=3, aux=True)
 bench(S, 4096, 1024, bias=True, epi=1)
 bench(S, 1024, 1024, bias=True, res=True)
 bench(S, 1024, 4096, bias=True, res=True)
+bench(S, 1024, 1024, bias=True)
+bench(S, 1024, 1024, b_mn=True)
+bench(1024, 4096, S, a_mn=True, b_mn=True, out=torch.float32)
+bench(1024, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
+bench(4096, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
