@@ -151,7 +151,8 @@ int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o, float* ls
                  int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, const int32_t* key_len, int causal,
                  tsw_stream_t stream);
 
-/* Backward of tsw_fmha_fwd: recomputes the probabilities from lse; dq (B, Sq, H*64 contiguous), dk/dv laid out like k/v.
+/* Backward of tsw_fmha_fwd: recomputes the probabilities from lse; dq / dk / dv are laid out like q / k / v (row strides
+ * ldq / ldk / ldv: they may be column slices of one packed q|k|v gradient buffer).
  * workspace holds the fp32 dQ accumulator (filled by bulk tensor reduce-adds) and delta = rowsum(dO * O). */
 size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq);
 int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,

@@ -665,6 +665,19 @@ fmha_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   if (lane == 0) { const int64_t b = bi / Sq, i = bi - b * Sq; delta[(b * H + h) * Sq + i] = sum; }
 }
 
+// fp32 dQ accumulator (rows, 8 * cols8) contiguous -> bf16 rows with stride ld (dq may be a column slice of a packed q|k|v gradient)
+__global__ void __launch_bounds__(256)
+fmha_dq_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n8, int cols8, int64_t ld) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int64_t row = i / cols8;
+  const int c8 = (int)(i - row * cols8);
+  float v[8];
+  Vec<float>::load(src + i * 8, v);
+  Vec<float>::load(src + i * 8 + 4, v + 4);
+  Vec<__nv_bfloat16>::store(dst + row * ld + c8 * 8, v);
+}
+
 // (B, S, d) bf16 tensor -> 4-D map {d, S, B, 1}, box {64, 128, 1, 1}, SWIZZLE_128B
 static int make_bsd_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t d_cols, int64_t ld, bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
@@ -713,8 +726,6 @@ extern "C" int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }
-
-extern "C" int tsw_cast(const void*, int, void*, int, int64_t, tsw_stream_t);
 
 extern "C" size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq) {
   return (size_t)(B * Sq * H * FD) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256);
@@ -765,7 +776,11 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
   fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   TSW_LAUNCH_CHECK();
-  // dq (B, Sq, ldq) bf16 <- fp32 accumulator (contiguous when ldq == H*64, the only layout the host side uses)
-  TSW_CHECK_ARG(ldq == dcols, "fmha_bwd: dq must be contiguous (ldq == H * 64)");
-  return tsw_cast(dq32, TSW_F32, dq, TSW_BF16, B * Sq * dcols, stream);
+  // dq (B * Sq rows, row stride ldq) bf16 <- contiguous fp32 accumulator
+  {
+    const int64_t n8 = B * Sq * (dcols / 8);
+    fmha_dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dq, n8, (int)(dcols / 8), ldq);
+    TSW_LAUNCH_CHECK();
+  }
+  return TSW_OK;
 }

@@ -35,6 +35,22 @@ def shadow(p: Tensor, dtype: torch.dtype) -> Tensor:
     return s
 
 
+def shadow_cat(ps: Tuple[Optional[Tensor], ...], dtype: torch.dtype, rows_each: int = 0) -> Tensor:
+    """Shadow of several master parameters stacked along dim 0 (the packed q|k|v or k|v projection weight / bias); a
+    ``None`` entry contributes ``rows_each`` zeros (Whisper's key projection has no bias).  Rebuilt when any part changes."""
+    key = ("cat", tuple(id(p) for p in ps), dtype)
+    ver = tuple((p._version, p.data_ptr()) if p is not None else None for p in ps)
+    ent = _shadow_cache.get(key)
+    if ent is not None and ent[0] == ver:
+        return ent[1]
+    ref = next(p for p in ps if p is not None)
+    parts = [p.detach() if p is not None else ref.new_zeros((rows_each,) + tuple(ref.shape[1:])) for p in ps]
+    full = torch.cat(parts, dim=0)
+    s = full if full.dtype == dtype else K.cast(full, dtype)
+    _shadow_cache[key] = (ver, s)
+    return s
+
+
 def clear_shadow_cache() -> None:
     _shadow_cache.clear()
 
@@ -326,6 +342,95 @@ class _FusedAttention(Function):
         n_head, scale, causal, has_len = ctx.meta
         dq, dk, dv = K.fmha_bwd(q, k, v, o, do, lse, n_head, scale, key_len=key_len if has_len else None, causal=causal)
         return dq, dk, dv, None, None, None, None
+
+
+class _PackedSelfAttention(Function):
+    """Self-attention with the q | k | v projections packed into one (3d, d) GEMM (Whisper blocks: openai-whisper
+    MultiHeadAttention behind whisper_encoder.py:497-500 / whisper_decoder.py:281-284).  Forward: one N = 3d GEMM, the
+    fused attention reads q / k / v as column slices of its output.  Backward: the attention kernel writes dq | dk | dv
+    into one packed buffer, so dX is one K = 3d GEMM, the three weight gradients one M = 3d GEMM and the two bias
+    gradients one column sum.  The parameters stay separate tensors (state-dict names of the reference)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, wq: Tensor, bq: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float, causal: bool):
+        B, S, d = x.shape
+        x2 = x.reshape(B * S, d)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        w = shadow_cat((wq, wk, wv), x.dtype)
+        b = shadow_cat((bq, None, bv), torch.float32, rows_each=d)
+        qkv = K.gemm(x2, w, M=B * S, N=3 * d, K=d, bias=b, out_dtype=x.dtype).view(B, S, 3 * d)
+        q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        o, lse = K.fmha_fwd(q, k, v, n_head, scale, causal=causal)
+        ctx.save_for_backward(x2, qkv, o, lse, wq, wk, wv)
+        ctx.meta = (n_head, scale, causal)
+        return o
+
+    @staticmethod
+    def backward(ctx, do: Tensor):
+        x2, qkv, o, lse, wq, wk, wv = ctx.saved_tensors
+        n_head, scale, causal = ctx.meta
+        B, S, d3 = qkv.shape
+        d = d3 // 3
+        rows = B * S
+        q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+        dqkv = torch.empty_like(qkv)
+        K.fmha_bwd(q, k, v, o, do, lse, n_head, scale, causal=causal, out=(dqkv[..., :d], dqkv[..., d:2 * d], dqkv[..., 2 * d:]))
+        dy2 = dqkv.view(rows, d3)
+        w = shadow_cat((wq, wk, wv), x2.dtype)
+        dx = K.gemm(dy2, w, M=rows, N=d, K=d3, b_mn=True, ldb=d, out_dtype=x2.dtype).view(B, S, d) if ctx.needs_input_grad[0] else None
+        dw = K.gemm(dy2, x2, M=d3, N=d, K=rows, a_mn=True, b_mn=True, lda=d3, ldb=d, out_dtype=torch.float32)
+        db = K.colsum(dy2, rows, d3)
+        return dx, dw[:d], db[:d], dw[d:2 * d], dw[2 * d:], db[2 * d:], None, None, None
+
+
+class _PackedCrossAttention(Function):
+    """Cross-attention with the k | v projections of the memory packed into one (2d, d) GEMM; q comes in projected."""
+
+    @staticmethod
+    def forward(ctx, q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float):
+        B, Sk, d = xa.shape
+        xa2 = xa.reshape(B * Sk, d)
+        if not xa2.is_contiguous():
+            xa2 = xa2.contiguous()
+        w = shadow_cat((wk, wv), xa.dtype)
+        b = shadow_cat((None, bv), torch.float32, rows_each=d)
+        kv = K.gemm(xa2, w, M=B * Sk, N=2 * d, K=d, bias=b, out_dtype=xa.dtype).view(B, Sk, 2 * d)
+        q = q.contiguous()
+        o, lse = K.fmha_fwd(q, kv[..., :d], kv[..., d:], n_head, scale)
+        ctx.save_for_backward(q, xa2, kv, o, lse, wk, wv)
+        ctx.meta = (n_head, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do: Tensor):
+        q, xa2, kv, o, lse, wk, wv = ctx.saved_tensors
+        n_head, scale = ctx.meta
+        B, Sk, d2 = kv.shape
+        d = d2 // 2
+        rows = B * Sk
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        K.fmha_bwd(q, kv[..., :d], kv[..., d:], o, do, lse, n_head, scale, out=(dq, dkv[..., :d], dkv[..., d:]))
+        dy2 = dkv.view(rows, d2)
+        w = shadow_cat((wk, wv), xa2.dtype)
+        dxa = K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, out_dtype=xa2.dtype).view(B, Sk, d) if ctx.needs_input_grad[1] else None
+        dw = K.gemm(dy2, xa2, M=d2, N=d, K=rows, a_mn=True, b_mn=True, lda=d2, ldb=d, out_dtype=torch.float32)
+        db = K.colsum(dy2, rows, d2)
+        return dq, dxa, dw[:d], dw[d:], db[d:], None, None
+
+
+def packed_attention_ok(x: Tensor, n_head: int) -> bool:
+    """The packed paths need the fused attention kernel (bf16, head dim 64)."""
+    return x.dtype == torch.bfloat16 and x.shape[-1] == n_head * 64
+
+
+def self_attention_packed(x: Tensor, wq: Tensor, bq: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float, causal: bool = False) -> Tensor:
+    return _PackedSelfAttention.apply(x, wq, bq, wk, wv, bv, n_head, scale, causal)
+
+
+def cross_attention_packed(q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float) -> Tensor:
+    return _PackedCrossAttention.apply(q, xa, wk, wv, bv, n_head, scale)
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False) -> Tensor:

@@ -298,13 +298,19 @@ def fmha_fwd(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len
 
 
 def fmha_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, do: Tensor, lse: Tensor, n_head: int, scale: float,
-             key_len: Optional[Tensor] = None, causal: bool = False):
-    """-> dq, dk, dv (bf16, shapes of q, k, v)."""
+             key_len: Optional[Tensor] = None, causal: bool = False, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None):
+    """-> dq, dk, dv (bf16, shapes and row strides of q, k, v; ``out`` supplies them, e.g. as slices of a packed buffer)."""
     lib = _C.load()
     B, Sq, d = q.shape
     Sk = k.shape[1]
     do = do.contiguous()
-    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    if out is None:
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    else:
+        dq, dk, dv = out
+        if (dq.stride(1), dk.stride(1), dv.stride(1)) != (q.stride(1), k.stride(1), v.stride(1)):
+            raise _C.TswError("fmha_bwd: dq / dk / dv must have the row strides of q / k / v")
     ws = _ws(lib.tsw_fmha_bwd_workspace_bytes(B, n_head, Sq), q.device)
     check(lib.tsw_fmha_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dq), ptr(dk), ptr(dv), B, n_head, Sq, Sk, q.stride(1),
                            k.stride(1), v.stride(1), o.stride(1), do.stride(1), scale, ptr(key_len), int(causal), ptr(ws), ws.numel(),

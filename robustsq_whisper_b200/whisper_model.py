@@ -113,6 +113,14 @@ def build_text_decoder(name: str, download_root=None) -> TextDecoderParams:
 def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False, residual: Optional[Tensor] = None) -> Tensor:
     """openai-whisper MultiHeadAttention: q,k scaled by dh**-0.25 each (folded into the softmax scale), fp32 softmax,
     no key-padding mask (the reference passes none, whisper_encoder.py:497-500)."""
+    if F.packed_attention_ok(x, p.n_head):   # training regime: packed projections around the fused attention kernel
+        scale = (x.shape[-1] // p.n_head) ** -0.5
+        if xa is None:
+            a = F.self_attention_packed(x, p.query.weight, p.query.bias, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale, causal)
+        else:
+            q = F.linear(x, p.query.weight, p.query.bias)
+            a = F.cross_attention_packed(q, xa, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale)
+        return F.linear(a, p.out.weight, p.out.bias, residual=residual)
     src = x if xa is None else xa
     q = F.linear(x, p.query.weight, p.query.bias)
     k = F.linear(src, p.key.weight, None)
