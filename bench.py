@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--negatives", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--graph", action="store_true", help="replay the whole step as one CUDA graph (robustsq_whisper_b200.graph) instead of the eager plugin call; "
+                    "measured equal on this host (the step is GPU-bound, inter-kernel gaps ~1 us), so the default stays the reference-facing eager call")
     return ap.parse_args()
 
 
@@ -160,7 +162,7 @@ def run_b200(args):
     model.decoder.compute_dtype = torch.bfloat16
     model.materialize_heads()
     model.set_epoch(6)
-    reducer = GradientAllReducer(model.parameters())
+    reducer = GradientAllReducer(model.parameters(), overlap=os.environ.get("TSW_DDP_OVERLAP", "1") != "0")
 
     B = args.batch
     batch = synth.make_batch(B, args.mix_s, args.enr_s, seed=1234 + rank, utt_offset=rank * B)
@@ -180,12 +182,27 @@ def run_b200(args):
         w = torch.softmax(torch.ones_like(sim).masked_fill_(sim == 1, -10000), dim=1)
         return torch.multinomial(w, K_neg, replacement=True)
 
-    def step(inputs):
+    def eager_step(inputs):
         for p in model.parameters():
             p.grad = None
         loss, stats, weight = model(**inputs, utt_id=batch["utt_id"], neg_idx=make_negatives())
         loss.backward()
         reducer.reduce()
+        return loss
+
+    graphed = None
+    if args.graph:
+        # the step geometry is fixed: capture forward + backward (+ the overlapped gradient all-reduce) once, replay per step
+        from robustsq_whisper_b200.graph import GraphedTrainStep
+        ex = {k: v.to(dev) for k, v in pinned.items()}
+        ex["utt_id"] = batch["utt_id"]
+        ex["neg_idx"] = make_negatives()
+        graphed = GraphedTrainStep(model, ex, reducer=reducer if world > 1 else None, warmup=max(args.warmup, 3))
+
+    def step(inputs):
+        if graphed is None:
+            return eager_step(inputs)
+        loss, stats, weight = graphed(**inputs, utt_id=batch["utt_id"], neg_idx=make_negatives())
         return loss
 
     def resident_inputs():
@@ -226,7 +243,8 @@ def run_b200(args):
     e2.record()
     last = None
     for i in range(args.steps):
-        loss = step(resident_inputs())
+        # host buffers in: the graphed step copies the pinned tensors straight into its static inputs (H2D inside the region)
+        loss = step(resident_inputs() if graphed is None else pinned)
         last = loss.detach().float().cpu()  # device -> host read of the step's result
     e3.record()
     sync_all()
@@ -245,7 +263,7 @@ def run_b200(args):
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()
     for i in range(args.steps):
-        step(staged[i])
+        eager_step(staged[i])   # eager: CUDA events cannot be recorded between the nodes of a replayed graph
     e5.record()
     sync_all()
     ms_prof = e4.elapsed_time(e5) / args.steps
@@ -273,6 +291,7 @@ def run_b200(args):
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"whisper-{args.model} TS-ASR training step (fwd+bwd), {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment, "
                                    f"q=16, SQ-Former L=2, K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE",
+                       "launch": "eager (one launch per kernel)" if graphed is None else "one CUDA graph per step (forward + backward + gradient all-reduce), host-side utt-id parsing / negative sampling outside it",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step inputs and activations (>10 GB) exceed the 126 MB L2; fresh input copies each step",
                        "loss_last": None if last is None else float(last)},

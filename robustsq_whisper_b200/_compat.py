@@ -47,8 +47,8 @@ def force_gatherable(data, device):
         if data.dim() == 0:
             data = data[None]
         return data.to(device)
-    if isinstance(data, float):
-        return torch.tensor([data], dtype=torch.float, device=device)
+    if isinstance(data, float):   # torch.full: a fill kernel, no pageable host-to-device copy (legal under CUDA-graph capture)
+        return torch.full((1,), data, dtype=torch.float, device=device)
     if isinstance(data, int):
-        return torch.tensor([data], dtype=torch.long, device=device)
+        return torch.full((1,), data, dtype=torch.long, device=device)
     return data

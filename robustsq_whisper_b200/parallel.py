@@ -40,47 +40,104 @@ def all_gather_with_grad(x: Tensor) -> Tensor:
     return _AllGatherWithGrad.apply(x)
 
 
-class GradientAllReducer:
-    """Bucketed mean all-reduce of ``.grad`` for a replicated model.  ``reduce()`` flattens gradients into fixed
-    buckets (default 64 MiB fp32), launches one async all-reduce per bucket on the communication stream NCCL owns and
-    copies the averaged values back; parameters that received no gradient (the frozen dead SQ-Former ``cls`` head,
-    SURVEY.md §2.2) are skipped, so no ``find_unused_parameters`` machinery is needed."""
+class _Bucket:
+    __slots__ = ("params", "offsets", "numel", "flat", "ready", "work")
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20):
+    def __init__(self):
+        self.params: List[torch.nn.Parameter] = []
+        self.offsets: List[int] = []
+        self.numel = 0
+        self.flat: Optional[Tensor] = None
+        self.ready = 0
+        self.work = None
+
+
+class GradientAllReducer:
+    """Bucketed mean all-reduce of ``.grad`` for a replicated model, overlapped with backward.
+
+    Parameters are assigned to fixed buckets (default 64 MiB of fp32) in reverse registration order, which is roughly
+    the order backward produces their gradients.  A post-accumulate-grad hook copies each finished gradient into its
+    bucket's flat buffer and, when the bucket is complete, starts one asynchronous all-reduce on NCCL's own stream, so
+    the exchange of the late layers runs under the backward kernels of the early ones.  ``reduce()`` (call it after
+    ``backward()``) flushes whatever has not been started, waits, and re-points every ``.grad`` at its averaged slice of
+    the flat buffer (no copy back).  Parameters that receive no gradient (the frozen dead SQ-Former ``cls`` head,
+    SURVEY.md §2.2) are skipped, so no ``find_unused_parameters`` machinery is needed: which parameters take part is
+    learnt from the first step, which runs un-overlapped.  At world size 1 everything is a no-op."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, overlap: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
+        self.overlap = overlap
+        self._buckets: Optional[List[_Bucket]] = None   # built from the parameters that had a gradient in the first step
+        self._where = {}                                 # id(param) -> (bucket, index)
+        self._hooks = []
+        if overlap and hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
-    def reduce(self) -> None:
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        world = dist.get_world_size()
-        bucket: List[Tensor] = []
-        size = 0
-        pending = []
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _active() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
-        def flush():
-            nonlocal bucket, size
-            if not bucket:
-                return
-            flat = torch.cat([g.reshape(-1) for g in bucket])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True)
-            pending.append((work, flat, bucket))
-            bucket, size = [], 0
-
-        for p in reversed(self.params):  # roughly the order backward produced them
+    def _build(self) -> None:
+        self._buckets, self._where = [], {}
+        cur = _Bucket()
+        for p in reversed(self.params):
             if p.grad is None:
                 continue
-            g = p.grad
-            bucket.append(g)
-            size += g.numel() * g.element_size()
-            if size >= self.bucket_bytes:
-                flush()
-        flush()
-        for work, flat, grads in pending:
-            work.wait()
-            flat.div_(world)
-            off = 0
-            for g in grads:
-                n = g.numel()
-                g.copy_(flat[off:off + n].view_as(g))
-                off += n
+            self._where[id(p)] = (cur, len(cur.params))
+            cur.params.append(p)
+            cur.offsets.append(cur.numel)
+            cur.numel += p.numel()
+            if cur.numel * 4 >= self.bucket_bytes:
+                self._buckets.append(cur)
+                cur = _Bucket()
+        if cur.params:
+            self._buckets.append(cur)
+
+    def _launch(self, b: _Bucket) -> None:
+        avg = dist.get_backend() == "nccl"
+        b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, async_op=True)
+
+    def _stage(self, b: _Bucket, i: int) -> None:
+        p = b.params[i]
+        if b.flat is None:
+            b.flat = torch.empty(b.numel, dtype=torch.float32, device=p.grad.device)
+        dst = b.flat[b.offsets[i]:b.offsets[i] + p.numel()]
+        if p.grad.data_ptr() != dst.data_ptr():   # after a zero_grad(set_to_none=False) the gradient already lives in its slice
+            dst.copy_(p.grad.reshape(-1))
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if self._buckets is None or not self._active():
+            return
+        ent = self._where.get(id(p))
+        if ent is None:
+            return
+        b, i = ent
+        self._stage(b, i)
+        b.ready += 1
+        if b.ready == len(b.params):
+            self._launch(b)
+
+    # ------------------------------------------------------------------ API
+    def reduce(self) -> None:
+        if not self._active():
+            return
+        if self._buckets is None:
+            self._build()
+        world = dist.get_world_size()
+        for b in self._buckets:
+            if b.work is None:   # first step, gradients assigned by hand, or a bucket the hooks did not complete
+                for i, p in enumerate(b.params):
+                    if p.grad is None:
+                        raise RuntimeError("GradientAllReducer: a parameter that had a gradient in the first step has none now")
+                    self._stage(b, i)
+                self._launch(b)
+        for b in self._buckets:
+            b.work.wait()
+            if dist.get_backend() != "nccl":
+                b.flat.div_(world)
+            for i, p in enumerate(b.params):
+                p.grad = b.flat[b.offsets[i]:b.offsets[i] + p.numel()].view_as(p)
+            b.work, b.ready = None, 0

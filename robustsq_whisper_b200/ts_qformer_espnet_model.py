@@ -28,6 +28,10 @@ from . import kernels as K
 from ._compat import compute_dtype, force_gatherable
 
 
+def _capturing(t: Tensor) -> bool:
+    return t.is_cuda and torch.cuda.is_current_stream_capturing()
+
+
 # ----------------------------------------------------------------------------------------------- utt-id parsing (a13)
 def _speaker_of(utt: str, is_wsj2mix: bool = False, is_ami: bool = False) -> str:
     if is_wsj2mix:
@@ -225,8 +229,9 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
     def encode(self, speech: Tensor, speech_lengths: Tensor, enroll: Tensor, enroll_lengths: Tensor):
         """Frontend (identity: frontend=None) + encoder (:254-302)."""
         assert speech_lengths.dim() == 1, speech_lengths.shape
-        speech = speech[:, : int(speech_lengths.max())]
-        enroll = enroll[:, : int(enroll_lengths.max())]
+        if not _capturing(speech):   # under CUDA-graph capture the batch geometry is static (and .max() would be a host sync)
+            speech = speech[:, : int(speech_lengths.max())]
+            enroll = enroll[:, : int(enroll_lengths.max())]
         return self.encoder(speech, speech_lengths, enroll, enroll_lengths)
 
     # ------------------------------------------------------------------ losses
@@ -289,8 +294,9 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
                 == enroll_lengths.shape[0]), (speech.shape, speech_lengths.shape, text.shape, text_lengths.shape, enroll.shape, enroll_lengths.shape)
         batch_size = speech.shape[0]
         text[text == -1] = self.ignore_id          # in place, like the reference (:557)
-        text = text[:, : int(text_lengths.max())]  # for data-parallel (:560)
-        utt_id = kwargs["utt_id"]
+        if not _capturing(text):
+            text = text[:, : int(text_lengths.max())]  # for data-parallel (:560)
+        utt_id = kwargs.get("utt_id")
 
         neg_idx = kwargs.get("neg_idx")
         neg_weight = None
@@ -298,7 +304,9 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
             if neg_idx is None:
                 neg_weight, neg_idx = self._negatives(utt_id)
         encoder_out, encoder_out_lens, spk_prompt, enroll_embedding = self.encode(speech, speech_lengths, enroll, enroll_lengths)
-        speaker_labels = get_speaker_labels(utt_id, self.is_wsj2mix, self.is_ami).to(enroll_embedding.device)
+        speaker_labels = kwargs.get("speaker_labels")   # precomputed on the host by graph.GraphedTrainStep
+        if speaker_labels is None:
+            speaker_labels = get_speaker_labels(utt_id, self.is_wsj2mix, self.is_ami).to(enroll_embedding.device)
 
         stats: Dict[str, Optional[Tensor]] = dict()
         loss_con = loss_aam = None

@@ -115,7 +115,26 @@ def _gloo_worker(rank, world, port_no, q):
     frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
     GradientAllReducer([p, frozen], bucket_bytes=8).reduce()
     ok_reduce = torch.allclose(p.grad, torch.full((5,), sum(range(1, world + 1)) / world))
-    q.put((rank, bool(ok_gather), bool(ok_reduce)))
+    # overlapped path: hooks stage gradients during backward and start the bucket all-reduces; three steps, the first
+    # one learns which parameters take part (the unused one never gets a gradient)
+    torch.manual_seed(0)
+    lin1, lin2, unused = torch.nn.Linear(4, 4), torch.nn.Linear(4, 2), torch.nn.Linear(3, 3)
+    params = list(lin1.parameters()) + list(lin2.parameters()) + list(unused.parameters())
+    red = GradientAllReducer(params, bucket_bytes=64)
+    ok_overlap = True
+    for step in range(3):
+        for prm in params:
+            prm.grad = None
+        xs = [torch.full((2, 4), float(r + 1 + step)) for r in range(world)]
+        lin2(torch.tanh(lin1(xs[rank]))).sum().backward()
+        red.reduce()
+        want = [torch.zeros_like(prm) for prm in params[:4]]
+        for r in range(world):   # the same computation for every rank's input, averaged
+            g = torch.autograd.grad(lin2(torch.tanh(lin1(xs[r]))).sum(), params[:4])
+            want = [w_ + g_ / world for w_, g_ in zip(want, g)]
+        ok_overlap &= all(torch.allclose(prm.grad, w_, atol=1e-6) for prm, w_ in zip(params[:4], want))
+        ok_overlap &= all(prm.grad is None for prm in unused.parameters())
+    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_overlap)))
     dist.destroy_process_group()
 
 

@@ -200,3 +200,35 @@ def test_epoch_warmups_change_the_losses_like_the_port():
             _, stats, _ = m(**to_cuda(batch), neg_idx=neg_idx)
         for k in ("loss_con", "loss_aam", "loss_att"):
             assert stats[k].item() == pytest.approx(float(rs[k]), rel=2e-4), (epoch, k)
+
+
+def test_graphed_train_step_equals_the_eager_step():
+    """robustsq_whisper_b200.graph.GraphedTrainStep: one CUDA graph per step geometry; losses and gradients must equal
+    the eager forward/backward on the same batch, for the captured batch and for a different batch replayed through it."""
+    from robustsq_whisper_b200.graph import GraphedTrainStep
+    m, cfg, sd = build_model("tiny", 0, torch.bfloat16, num_negatives=4)
+    m.set_epoch(6)
+    b1 = synth.make_batch(4, 6.0, 3.0, text_len=12, seed=11, ragged=False)
+    b2 = synth.make_batch(4, 6.0, 3.0, text_len=12, seed=12, ragged=False, utt_offset=3)
+    neg = [torch.randint(0, 4, (4, 4), generator=torch.Generator().manual_seed(s)) for s in (1, 2)]
+
+    def eager(batch, neg_idx):
+        for p in m.parameters():
+            p.grad = None
+        loss, stats, _ = m(**to_cuda(batch), neg_idx=neg_idx)
+        loss.backward()
+        return loss.detach().clone(), {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+
+    want1, want2 = eager(b1, neg[0]), eager(b2, neg[1])
+    step = GraphedTrainStep(m, dict(b1, neg_idx=neg[0]))
+    assert step.launches_per_replay > 100
+    for batch, neg_idx, (wl, wg) in ((b1, neg[0], want1), (b2, neg[1], want2), (b1, neg[0], want1)):
+        loss, stats, weight = step(**to_cuda(batch), neg_idx=neg_idx)
+        torch.cuda.synchronize()
+        assert loss.item() == pytest.approx(wl.item(), rel=1e-5)
+        got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+        assert set(got) == set(wg)
+        for n in wg:   # same kernels, same order; fp32 split-K / dQ reduce-adds may reorder and bf16 rounding amplifies that
+            assert rel(got[n], wg[n]) < 1e-2, n
+    with pytest.raises(ValueError):
+        step(**to_cuda(synth.make_batch(4, 5.0, 3.0, text_len=12, seed=11, ragged=False)))
