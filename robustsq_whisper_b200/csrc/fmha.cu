@@ -53,12 +53,12 @@ __device__ __forceinline__ int fmha_kv_limit(const FmhaParams& p, int b, int q0)
 
 // 32 scores of one row -> probabilities against the fixed reference: bf16 pairs for the P operand, running sum, raw max.
 template <bool MASKED>
-__device__ __forceinline__ void fwd_chunk(const float* v, float scale_log2, float m_ref, int first_key, int row_limit, uint32_t* pk,
+__device__ __forceinline__ void fwd_chunk(const uint32_t* v, float scale_log2, float m_ref, int first_key, int row_limit, uint32_t* pk,
                                           float& lsum, float& tmax) {
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
-    float a = v[i], b = v[i + 1];
+    float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
     float p0 = ex2_approx(fmaf(a, scale_log2, -m_ref));
     float p1 = ex2_approx(fmaf(b, scale_log2, -m_ref));
     if (MASKED) {
@@ -78,11 +78,15 @@ struct FmhaFwdSmem {
   unsigned char k[2][kTileBytes];
   unsigned char v[2][kTileBytes];
   unsigned char p[2 * kTileBytes];  // 128 x 128 bf16 probabilities: two 64-key panels
-  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, p_full, o_full;
+  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_drained, p_full, pv_done;
   uint32_t tmem_slot;
   __nv_bfloat16 xmax[2][FQ];   // per-row partial maxima exchanged between the two threads of a row (rounded UP: any bound works)
 };
 
+// Software pipeline of the forward kernel: the softmax warps pull S of tile j into registers and release the TMEM columns
+// at once (s_drained), so S of tile j+1 is computed while they exponentiate tile j; the output accumulates in TMEM over
+// all key tiles (P V of tile j runs while the softmax warps are already on tile j+1), so they never wait for an MMA in
+// steady state.  The lazy running maximum makes rescaling the TMEM accumulator a rare event (first tiles only).
 __global__ void __launch_bounds__(F_THREADS, 2)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                 const FmhaParams p) {
@@ -96,7 +100,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(&s.q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&s.k_full[i], 1); mbar_init(&s.k_empty[i], 1); mbar_init(&s.v_full[i], 1); mbar_init(&s.v_empty[i], 1); }
-    mbar_init(&s.s_full, 1); mbar_init(&s.p_full, 8); mbar_init(&s.o_full, 1);
+    mbar_init(&s.s_full, 1); mbar_init(&s.s_drained, 8); mbar_init(&s.p_full, 8); mbar_init(&s.pv_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<256>(&s.tmem_slot);
@@ -104,7 +108,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_s = s.tmem_slot;          // 128 columns: S
-  const uint32_t tmem_pv = s.tmem_slot + 128;   // 64 columns: P V of the current tile
+  const uint32_t tmem_o = s.tmem_slot + 128;    // 64 columns: the output accumulator (all key tiles)
 
   const int limit = fmha_kv_limit(p, b, q0);
   const int n_kv = (limit + FK - 1) / FK;
@@ -151,20 +155,24 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_s(0);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&s.p_full, j & 1);   // probabilities of tile j are in smem; S and PV TMEM have been drained
+        if (j + 1 < n_kv) {
+          mbar_wait(&s.s_drained, j & 1);   // S of tile j sits in the softmax warps' registers
+          tc_fence_after();
+          issue_s(j + 1);                   // runs under the exponentials of tile j
+        }
+        mbar_wait(&s.p_full, j & 1);        // probabilities of tile j are in smem (and any accumulator rescale is done)
         mbar_wait(&s.v_full[st], ph);
         tc_fence_after();
         const uint64_t vd = dV_[st];
         if (leader_lane) {
-        umma_bf16_c<false>(tmem_pv, dP0, vd, id_pv);
+        if (j == 0) umma_bf16_c<false>(tmem_o, dP0, vd, id_pv); else umma_bf16_c<true>(tmem_o, dP0, vd, id_pv);
 #pragma unroll
         for (int k = 1; k < FK / 16; ++k)
-          umma_bf16_c<true>(tmem_pv, desc_advance(k < 4 ? dP0 : dP1, (k & 3) * 32), desc_advance(vd, k * 2048), id_pv);
-        umma_commit(&s.o_full);
+          umma_bf16_c<true>(tmem_o, desc_advance(k < 4 ? dP0 : dP1, (k & 3) * 32), desc_advance(vd, k * 2048), id_pv);
+        umma_commit(&s.pv_done);
         umma_commit(&s.v_empty[st]);
         }
         __syncwarp();
-        if (j + 1 < n_kv) issue_s(j + 1);  // next S overlaps the softmax warps' output update
       }
     }
   } else {
@@ -174,81 +182,89 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int r = quarter * 32 + lane;
     const int qi = q0 + r;
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    float o[32];   // output columns [hf*32, hf*32 + 32) of this row
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = 0.f;
     // Lazy running maximum: tile j is exponentiated against the reference m_ref fixed BEFORE the tile (exact for tile 0,
-    // where S is read twice), so S leaves TMEM once per tile and no row-wide exchange sits between the MMA and the
-    // exponentials.  The reference moves (and o, l are rescaled) only after a tile whose maximum exceeded it by > 2^8 —
+    // where S is read twice), so no row-wide exchange sits between the MMA and the exponentials.  The reference moves
+    // (and the TMEM accumulator and l are rescaled) only after a tile whose maximum exceeded it by > 2^8 —
     // probabilities up to 256 are harmless in bf16 / fp32; the final division by l removes the common factor.
     float m_ref = -INFINITY, l_part = 0.f;
     int row_limit = limit;
     if (p.causal) row_limit = min(row_limit, qi + 1 + (p.Sk - p.Sq));
+    unsigned char* prow = s.p + hf * kTileBytes + r * 128;
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(&s.s_full, j & 1);
       tc_fence_after();
       const int kb = j * FK + hf * 64;                 // first key of this thread's half
       const bool full = kb + 64 <= row_limit;          // no masking needed
+      uint32_t sv[64];
+      tmem_ld32_async(tmem_s + lane_off + hf * 64, sv);
+      tmem_ld32_async(tmem_s + lane_off + hf * 64 + 32, sv + 32);
+      tmem_ld_wait();
+      tmem_ld_fence32(sv); tmem_ld_fence32(sv + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.s_drained);        // the MMA warp may start S of the next tile
       if (j == 0) {                                    // exact maximum of the first tile -> initial reference
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-          float v[32];
-          tmem_ld32(tmem_s + lane_off + hf * 64 + c, v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (full || kb + c + i < row_limit) mx = fmaxf(mx, v[i]);
-        }
+        for (int i = 0; i < 64; ++i) if (full || kb + i < row_limit) mx = fmaxf(mx, __uint_as_float(sv[i]));
         const __nv_bfloat16 mxb = __float2bfloat16_ru(mx);   // both threads of the row must agree bit-for-bit
         s.xmax[hf][r] = mxb;
         named_bar_sync(1, 256);
         m_ref = fmaxf(__bfloat162float(mxb), __bfloat162float(s.xmax[hf ^ 1][r])) * p.scale_log2;
         if (m_ref == -INFINITY) m_ref = 0.f;
+        named_bar_sync(1, 256);                        // xmax is rewritten below
       }
       float lsum = 0.f, tmax = -INFINITY;
-      unsigned char* prow = s.p + hf * kTileBytes + r * 128;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        tmem_ld32(tmem_s + lane_off + hf * 64 + c, v);
-        uint32_t pk[16];
-        if (full) fwd_chunk<false>(v, p.scale_log2, m_ref, kb + c, row_limit, pk, lsum, tmax);
-        else fwd_chunk<true>(v, p.scale_log2, m_ref, kb + c, row_limit, pk, lsum, tmax);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int u = (c >> 3) + t;  // 16-byte unit inside this row of the panel
-          *reinterpret_cast<uint4*>(prow + ((u ^ (r & 7)) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
-        }
+      for (int c = 0; c < 2; ++c) {                    // 32 keys at a time: exponentials -> bf16 -> swizzled P panel
+        uint32_t pk[16];
+        if (full) fwd_chunk<false>(sv + 32 * c, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
+        else fwd_chunk<true>(sv + 32 * c, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
+        if (c == 0 && j > 0) mbar_wait(&s.pv_done, (j - 1) & 1);   // P V of the previous tile has read the P buffer
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          *reinterpret_cast<uint4*>(prow + (((4 * c + t) ^ (r & 7)) << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
       }
       l_part += lsum;
-      s.xmax[hf][r] = __float2bfloat16_ru(tmax);   // read by the partner after p_full / o_full below (ordered by the barriers)
+      s.xmax[hf][r] = __float2bfloat16_ru(tmax);
       fence_async_smem();     // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
       tc_fence_before();
-      __syncwarp();
+      named_bar_sync(1, 256); // every row's two partial maxima are published
       if (lane == 0) mbar_arrive(&s.p_full);
-      // accumulate P V of this tile (this thread's 32 output columns)
-      mbar_wait(&s.o_full, j & 1);
-      tc_fence_after();
-      {
-        float v[32];
-        tmem_ld32(tmem_pv + lane_off + hf * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] += v[i];
-      }
-      // move the reference if this tile overshot it by more than 2^8 (both threads of the row take the same decision:
-      // o_full implies every softmax warp has passed p_full, i.e. has published its xmax)
+      // move the reference if this tile overshot it by more than 2^8 (both threads of a row take the same decision)
       const float m_tile = fmaxf(__bfloat162float(s.xmax[0][r]), __bfloat162float(s.xmax[1][r])) * p.scale_log2;
-      named_bar_sync(1, 256);                        // xmax is rewritten in the next tile
-      if (m_tile > m_ref + 8.f) {
-        const float alpha = ex2_approx(m_ref - m_tile);
-        l_part *= alpha;
+      const bool move = m_tile > m_ref + 8.f;
+      named_bar_sync(1, 256); // xmax is rewritten in the next tile
+      if (__any_sync(0xffffffffu, move)) {
+        // rare (first tiles): the accumulator in TMEM — including this tile's P V, which used the old reference — is
+        // rescaled once that MMA has completed; P V of the next tile is not issued before this warp's next p_full arrival
+        const float alpha = move ? ex2_approx(m_ref - m_tile) : 1.f;
+        mbar_wait(&s.pv_done, j & 1);
+        tc_fence_after();
+        uint32_t ov[32];
+        tmem_ld32_async(tmem_o + lane_off + hf * 32, ov);
+        tmem_ld_wait();
+        tmem_ld_fence32(ov);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= alpha;
-        m_ref = m_tile;
+        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+        tmem_st32(tmem_o + lane_off + hf * 32, ov);
+        tc_fence_before();
+        l_part *= alpha;
+        if (move) m_ref = m_tile;
       }
     }
     const float m_run = m_ref;
+    float o[32];
+    if (n_kv > 0) {
+      mbar_wait(&s.pv_done, (n_kv - 1) & 1);
+      tc_fence_after();
+      tmem_ld32(tmem_o + lane_off + hf * 32, o);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    }
     // total row sum = sum of the two halves (same running maximum on both sides)
-    float* lx = reinterpret_cast<float*>(s.p);   // the P buffer is free once the last P V has completed (o_full)
+    float* lx = reinterpret_cast<float*>(s.p);   // the P buffer is free once the last P V has completed
     lx[hf * FQ + r] = l_part;
     named_bar_sync(1, 256);
     const float l_run = l_part + lx[(hf ^ 1) * FQ + r];
@@ -341,28 +357,6 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* tm, const v
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
-// 32 TMEM columns -> 32 raw registers, no wait (pair with tmem_ld_wait + tmem_ld_fence32 before the first use)
-__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// empty volatile asm that "rewrites" the 32 registers: pins every consumer of the loaded values behind the wait above
-__device__ __forceinline__ void tmem_ld_fence32(uint32_t* r) {
-  asm volatile(""
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
-        "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
-        "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
-        "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
-}
 
 // work item w -> (batch, head, key tile) and the query tiles [qt0, qt0 + n_it) that can see it; n_it == 0: no gradient reaches the tile
 struct BwdItem { int b, h, kv0, qt0, n_it, klimit, rot; };

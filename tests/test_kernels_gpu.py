@@ -480,6 +480,34 @@ def test_fmha_fwd(K, B, H, Sq, Sk, use_len, causal):
     assert rel_err(o.float(), o_ref) < 1e-2
 
 
+def test_fmha_fwd_moving_maximum_rescales_the_tmem_accumulator(K):
+    """Scores that grow by >> 2^8 from key tile to key tile: the lazy running-max reference has to move after (almost)
+    every tile, which rescales the output accumulator that lives in TMEM (fmha.cu, forward softmax warps)."""
+    torch.manual_seed(20)
+    B, H, Sq, Sk = 2, 2, 200, 900
+    d = H * 64
+    q = torch.randn(B, Sq, d).bfloat16()
+    ramp = torch.linspace(0.2, 6.0, Sk)[None, :, None]          # key norm grows along the sequence
+    k = (torch.randn(B, Sk, d) * ramp).bfloat16()
+    k = k + (q.float().mean(1, keepdim=True) * ramp * 0.5).bfloat16()   # and aligns with the queries: maxima keep rising
+    v = torch.randn(B, Sk, d).bfloat16()
+    scale = 0.5
+    o_ref, lse_ref = _attn_ref(q, k, v, H, scale)
+    o, lse = K.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), H, scale)
+    torch.cuda.synchronize()
+    s_max = ((q.float().view(B, Sq, H, 64).permute(0, 2, 1, 3) @ k.float().view(B, Sk, H, 64).permute(0, 2, 3, 1)) * scale)
+    tile_max = torch.stack([s_max[..., i:i + 128].amax(-1) for i in range(0, Sk, 128)], -1) * 1.4427
+    assert ((tile_max[..., 1:] - tile_max[..., :-1].cummax(-1).values) > 8).any(), "test data does not move the reference"
+    assert (lse.cpu() - lse_ref).abs().max().item() < 5e-2 * max(1.0, lse_ref.abs().max().item() / 50)
+    assert rel_err(o.float(), o_ref) < 1e-2
+    do = torch.randn(B, Sq, d).bfloat16()
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    _attn_ref(qr, kr, vr, H, scale)[0].backward(do.float())
+    dq, dk, dv = K.fmha_bwd(q.cuda(), k.cuda(), v.cuda(), o, do.cuda(), lse, H, scale)
+    for got, ref, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
+        assert rel_err(got.float(), ref) < 3e-2, (name, rel_err(got.float(), ref))
+
+
 @pytest.mark.parametrize("B,H,Sq,Sk,use_len,causal", FMHA_CASES)
 def test_fmha_bwd(K, B, H, Sq, Sk, use_len, causal):
     torch.manual_seed(19)
