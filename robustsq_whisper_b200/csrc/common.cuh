@@ -97,6 +97,63 @@ __device__ __forceinline__ float dgelu_fast(float x) {
   return fmaf(x * 0.39894228040143267794f, __expf(-0.5f * x * x), cdf);
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2): two IEEE fp32 operations per issued instruction.  The fused GEMM
+// epilogues are issue-bound (20+ instructions per element next to a 128 x 256 x 1024 main loop), so their arithmetic
+// runs on pairs.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx_f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float with_sign_of(float mag_nonneg, float s) {   // copysign for a non-negative magnitude: one LOP3
+  return __uint_as_float(__float_as_uint(mag_nonneg) | (__float_as_uint(s) & 0x80000000u));
+}
+
+// gelu_and_grad_fast on a pair: the same Abramowitz-Stegun 7.1.26 erf, constants folded so that exp(-x^2/2) is one
+// ex2 of (x*x) * (-log2(e)/2); 14 packed FP instructions + 4 MUFU + 4 LOP3 for two elements.
+__device__ __forceinline__ void gelu_and_grad_fast2(float2 x, float2& g, float2& dg) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = ffma2(splat2(0.3275911f * 0.70710678118654752440f), ax, splat2(1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 p = ffma2(splat2(1.061405429f), t, splat2(-1.453152027f));
+  p = ffma2(p, t, splat2(1.421413741f));
+  p = ffma2(p, t, splat2(-0.284496736f));
+  p = ffma2(p, t, splat2(0.254829592f));
+  const float2 arg = fmul2(fmul2(x, x), splat2(-0.5f * 1.44269504088896340736f));
+  const float2 ex = make_float2(ex2_approx_f(arg.x), ex2_approx_f(arg.y));      // exp(-x^2 / 2)
+  const float2 erfm = ffma2(fmul2(fmul2(p, t), ex), splat2(-1.f), splat2(1.f));   // |erf(x / sqrt 2)|
+  const float2 erfs = make_float2(with_sign_of(erfm.x, x.x), with_sign_of(erfm.y, x.y));
+  const float2 cdf = ffma2(splat2(0.5f), erfs, splat2(0.5f));
+  g = fmul2(x, cdf);
+  dg = ffma2(fmul2(x, splat2(0.39894228040143267794f)), ex, cdf);
+}
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 den = ffma2(splat2(0.3275911f * 0.70710678118654752440f), ax, splat2(1.f));
+  const float2 t = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+  float2 p = ffma2(splat2(1.061405429f), t, splat2(-1.453152027f));
+  p = ffma2(p, t, splat2(1.421413741f));
+  p = ffma2(p, t, splat2(-0.284496736f));
+  p = ffma2(p, t, splat2(0.254829592f));
+  const float2 arg = fmul2(fmul2(x, x), splat2(-0.5f * 1.44269504088896340736f));
+  const float2 ex = make_float2(ex2_approx_f(arg.x), ex2_approx_f(arg.y));
+  const float2 erfm = ffma2(fmul2(fmul2(p, t), ex), splat2(-1.f), splat2(1.f));
+  const float2 erfs = make_float2(with_sign_of(erfm.x, x.x), with_sign_of(erfm.y, x.y));
+  return fmul2(x, ffma2(splat2(0.5f), erfs, splat2(0.5f)));
+}
+
 // gelu(x) and gelu'(x) from one erf evaluation: the exp(-x^2/2) inside erf_fast is the Gaussian density gelu' needs
 __device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& dg) {
   const float ax = fabsf(x) * 0.70710678118654752440f;

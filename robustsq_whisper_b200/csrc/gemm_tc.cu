@@ -106,7 +106,15 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
     if (i < rows_ok) {
       const int rl = i * 4 + rsub;
       const float4 a = *reinterpret_cast<const float4*>(srow + i * 128 + ((u ^ (rl & 7)) * 4));
-      float o[4] = {fmaf(alpha, a.x, b4.x), fmaf(alpha, a.y, b4.y), fmaf(alpha, a.z, b4.z), fmaf(alpha, a.w, b4.w)};
+      float o[4];
+      float2 o01, o23;
+      if (KIND == EK_GELU || KIND == EK_GELU_GRAD) {   // packed all the way through the activation
+        o01 = ffma2(splat2(alpha), make_float2(a.x, a.y), make_float2(b4.x, b4.y));
+        o23 = ffma2(splat2(alpha), make_float2(a.z, a.w), make_float2(b4.z, b4.w));
+        o[0] = o01.x; o[1] = o01.y; o[2] = o23.x; o[3] = o23.y;
+      } else {
+        o[0] = fmaf(alpha, a.x, b4.x); o[1] = fmaf(alpha, a.y, b4.y); o[2] = fmaf(alpha, a.z, b4.z); o[3] = fmaf(alpha, a.w, b4.w);
+      }
       if (KIND == EK_RES || KIND == EK_MUL_AUX || KIND == EK_MUL_DGELU) {
         float ex[4];
         RawVec<DT>::unpack(pre[i], ex);
@@ -114,12 +122,14 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
         for (int j = 0; j < 4; ++j) o[j] = KIND == EK_RES ? o[j] + ex[j] : KIND == EK_MUL_AUX ? o[j] * ex[j] : o[j] * dgelu_fast(ex[j]);
       } else if (KIND == EK_GELU) {
         if (AOp) store4(AOp + off + (int64_t)i * row4, o);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = gelu_fast(o[j]);
+        const float2 g01 = gelu_fast2(o01), g23 = gelu_fast2(o23);
+        o[0] = g01.x; o[1] = g01.y; o[2] = g23.x; o[3] = g23.y;
       } else if (KIND == EK_GELU_GRAD) {
-        float dg[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) gelu_and_grad_fast(o[j], o[j], dg[j]);
+        float2 g01, g23, d01, d23;
+        gelu_and_grad_fast2(o01, g01, d01);
+        gelu_and_grad_fast2(o23, g23, d23);
+        o[0] = g01.x; o[1] = g01.y; o[2] = g23.x; o[3] = g23.y;
+        const float dg[4] = {d01.x, d01.y, d23.x, d23.y};
         store4(AOp + off + (int64_t)i * row4, dg);
       }
       DT* dst = Dp + off + (int64_t)i * row4;

@@ -229,6 +229,8 @@ def test_graphed_train_step_equals_the_eager_step():
         got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
         assert set(got) == set(wg)
         for n in wg:   # same kernels, same order; fp32 split-K / dQ reduce-adds may reorder and bf16 rounding amplifies that
+            if n.endswith(".key.bias"):   # softmax is shift invariant: the true gradient is 0, what is left is rounding noise
+                continue
             assert rel(got[n], wg[n]) < 1e-2, n
     with pytest.raises(ValueError):
         step(**to_cuda(synth.make_batch(4, 5.0, 3.0, text_len=12, seed=11, ragged=False)))
