@@ -161,12 +161,15 @@ int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, con
                  tsw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ cached decode
- * One new query token per (batch item, head) against L cached keys/values: o[b, h*64:(h+1)*64] = softmax_j(scale <q, K_j>) V_j.
+ * One new query token per (hypothesis, head) against L cached keys/values: o[b, h*64:(h+1)*64] = softmax_j(scale <q, K_j>) V_j.
  * Replaces the full-prefix recompute of forward_one_step (whisper_decoder.py:318-320) once the host keeps K/V caches.
- * q (B, ldq), caches (B, >= L, ldkv) with batch stride kv_batch_stride (elements), o (B, ldo); head dim 64; no mask (all L valid). */
-int tsw_decode_attention(const void* q, int64_t ldq, const void* k_cache, const void* v_cache, int64_t ldkv,
-                         int64_t kv_batch_stride, int64_t B, int64_t H, int64_t L, float scale, void* o, int64_t ldo,
-                         int dtype, tsw_stream_t stream);
+ * q (B, ldq), caches (B, >= L, ldkv) with batch stride kv_batch_stride (elements; 0 = one cache shared by all hypotheses, the
+ * cross-attention memory of a beam), o (B, ldo); head dim 64; no mask (all L rows valid).  k_new / v_new (B, ld_new) or NULL:
+ * this step's key / value row, written into the caches at row L-1 before attending.  L_dev (int32, device) overrides L when
+ * not NULL (replayable CUDA graphs). */
+int tsw_decode_attention(const void* q, int64_t ldq, void* k_cache, void* v_cache, int64_t ldkv, int64_t kv_batch_stride, int64_t B,
+                         int64_t H, int64_t L, const int32_t* L_dev, float scale, void* o, int64_t ldo, int dtype, const void* k_new,
+                         const void* v_new, int64_t ld_new, tsw_stream_t stream);
 
 /* Token embedding gather + learned positions (whisper_decoder.py:267-279):
  * out[b, u, :] = (u == 0 ? E[sop] : u <= q ? prompt[b, u-1] : E[ids[b, u-1-q]]) + pos[u], out dtype `dtype`. */

@@ -68,7 +68,7 @@ SIGNATURES = {
     "tsw_fmha_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _F, _P, _I, _P]),
     "tsw_fmha_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "tsw_fmha_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _F, _P, _I, _P, _SZ, _P]),
-    "tsw_decode_attention": (c_int, [_P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _F, _P, _I64, _I, _P]),
+    "tsw_decode_attention": (c_int, [_P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _F, _P, _I64, _I, _P, _P, _I64, _P]),
     "tsw_decoder_embed": (c_int, [_P, _P, _P, _I, _P, _I64, _I64, _I64, _I64, _I64, _P, _I, _P]),
     "tsw_decoder_embed_bwd": (c_int, [_P, _I, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P]),
     "tsw_asp_pool_fwd": (c_int, [_P, _I, _I64, _I64, _I64, _F, _P, _P, _P, _P, _P]),

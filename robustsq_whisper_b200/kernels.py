@@ -319,15 +319,20 @@ def fmha_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, do: Tensor, lse: Tensor
     return dq, dk, dv
 
 
-def decode_attention(q: Tensor, k_cache: Tensor, v_cache: Tensor, L: int, n_head: int, scale: float) -> Tensor:
-    """q (B, d) one new token; caches (B, Lmax, d) with the first L rows valid -> (B, d)."""
-    require_cuda(q, k_cache, v_cache)
+def decode_attention(q: Tensor, k_cache: Tensor, v_cache: Tensor, L: int, n_head: int, scale: float, k_new: Optional[Tensor] = None,
+                     v_new: Optional[Tensor] = None, L_dev: Optional[Tensor] = None) -> Tensor:
+    """q (B, d) one new token per hypothesis; caches (B or 1, Lmax, d) views with the first L rows valid -> (B, d).
+    ``k_new`` / ``v_new`` (B, d): this step's rows, appended at row L-1 by the kernel.  A cache of batch size 1 is shared
+    by every hypothesis (cross-attention memory of a beam)."""
+    require_cuda(q, k_cache, v_cache, k_new, v_new, L_dev)
     lib = _C.load()
     B, d = q.shape
-    assert k_cache.stride(2) == 1 and v_cache.stride() == k_cache.stride() and d == n_head * 64
+    assert k_cache.stride(2) == 1 and v_cache.stride() == k_cache.stride() and d == n_head * 64 and q.stride(1) == 1
+    shared = k_cache.shape[0] == 1 and B > 1
     o = torch.empty((B, d), dtype=q.dtype, device=q.device)
-    check(lib.tsw_decode_attention(ptr(q), q.stride(0), ptr(k_cache), ptr(v_cache), k_cache.stride(1), k_cache.stride(0), B, n_head, L,
-                                   scale, ptr(o), o.stride(0), dtype_code(q.dtype), stream()), "tsw_decode_attention")
+    check(lib.tsw_decode_attention(ptr(q), q.stride(0), ptr(k_cache), ptr(v_cache), k_cache.stride(1), 0 if shared else k_cache.stride(0), B,
+                                   n_head, L, ptr(L_dev), scale, ptr(o), o.stride(0), dtype_code(q.dtype), ptr(k_new), ptr(v_new),
+                                   0 if k_new is None else k_new.stride(0), stream()), "tsw_decode_attention")
     _count(1)
     return o
 

@@ -92,6 +92,9 @@ def test_tiny_fp32_matches_reference_fixture(golden_dir, tiny_case):
             ys = torch.cat([ys, logp.argmax(-1, keepdim=True)], dim=1)
         assert np.array_equal(ys[:, 1:].cpu().numpy(), gold["greedy_ids"])
         assert np.abs(logp.max(-1)[0].cpu().numpy() - gold["greedy_last_logp_max"]).max() < 1e-3
+        # the KV-cached decoder must emit the reference's ids too
+        cached = m.decoder.greedy_decode(xs, prompt, m.sos, -1, 6)
+        assert np.array_equal(cached.cpu().numpy(), gold["greedy_ids"])
 
 
 def test_tiny_bf16_within_budget(golden_dir, tiny_case):
@@ -234,3 +237,56 @@ def test_graphed_train_step_equals_the_eager_step():
             assert rel(got[n], wg[n]) < 1e-2, n
     with pytest.raises(ValueError):
         step(**to_cuda(synth.make_batch(4, 5.0, 3.0, text_len=12, seed=11, ragged=False)))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_kv_cached_decoding_equals_the_full_prefix_recompute(dtype):
+    """decode_prefill / decode_step / greedy_decode and batch_score(use_kv_cache) against the
+    reference-style full-prefix recompute (whisper_decoder.py:297-380): identical greedy token ids in fp32 (north-star
+    bar), log-probs within the bf16 budget in bf16; beam-style re-ordering of the hypotheses through the states."""
+    m, cfg, sd = build_model("tiny", 0, dtype, num_negatives=4)
+    dec = m.decoder
+    torch.manual_seed(5)
+    n, S, d, steps = 3, 150, 384, 7
+    memory = torch.randn(n, S, d, device="cuda").to(dtype)
+    prompt = (0.5 * torch.randn(n, 16, d, device="cuda")).to(dtype)
+    # reference-style loop (no cache)
+    ys = torch.full((n, 1), m.sos, dtype=torch.long, device="cuda")
+    ref_logps = []
+    for _ in range(steps):
+        logp, st = dec.batch_score(ys, None, memory, prompt)
+        assert st is None
+        ref_logps.append(logp)
+        ys = torch.cat([ys, logp.argmax(-1, keepdim=True)], dim=1)
+    ref_ids = ys[:, 1:]
+    tol = 2e-4 if dtype == torch.float32 else 6e-2
+    # explicit cache API
+    got = dec.greedy_decode(memory, prompt, m.sos, -1, steps)
+    if dtype == torch.float32:
+        assert torch.equal(got, ref_ids)
+    # batch_score with the cache, same loop as above: states carry (generation, row)
+    dec.use_kv_cache = True
+    try:
+        ys = torch.full((n, 1), m.sos, dtype=torch.long, device="cuda")
+        states = None
+        for t in range(steps):
+            logp, states = dec.batch_score(ys, states, memory, prompt)
+            assert (logp - ref_logps[t]).abs().max().item() < tol * max(1.0, ref_logps[t].abs().max().item() / 10), t
+            ys = torch.cat([ys, ref_ids[:, t:t + 1]], dim=1)   # teacher-forced with the reference ids: same prefixes in both loops
+        # beam-style step: hypotheses re-ordered / duplicated, one shared utterance (ESPnet expands the memory to the beam)
+        mem1, pr1 = memory[:1].expand(4, -1, -1), prompt[:1]
+        ys = torch.full((4, 1), m.sos, dtype=torch.long, device="cuda")
+        logp, states = dec.batch_score(ys, None, mem1, pr1)
+        top = logp[0].topk(4).indices
+        ys = torch.cat([ys, top[:, None]], dim=1)               # four different continuations of the same prefix
+        logp, states = dec.batch_score(ys, states, mem1, pr1)
+        order = [2, 2, 0, 3]                                    # survivors of the beam
+        ys2 = torch.cat([ys[order], logp[order].argmax(-1, keepdim=True)], dim=1)
+        logp2, _ = dec.batch_score(ys2, [states[i] for i in order], mem1, pr1)
+        dec.use_kv_cache = False
+        want2, _ = dec.batch_score(ys2, None, mem1, pr1)
+        assert (logp2 - want2).abs().max().item() < tol * max(1.0, want2.abs().max().item() / 10)
+        if dtype == torch.float32:
+            assert torch.equal(logp2.argmax(-1), want2.argmax(-1))
+    finally:
+        dec.use_kv_cache = False
