@@ -447,9 +447,17 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   p.splits = 1;
   // split-K when the output has too few tiles to occupy the machine (weight gradients: M, N ~ 1e3, K ~ 5e4): fp32 output,
   // plain epilogue, whole rows 16-byte aligned (vector atomics), one batch
-  if (!GENERIC && sizeof(DT) == 4 && p.batches == 1 && ep.vec4_ok && g.N % 4 == 0 && p.total_tiles * 2 <= units && num_kb >= 16) {
-    p.splits = (int)std::min<int64_t>(units / p.total_tiles, num_kb / 8);
-    if (p.splits < 1) p.splits = 1;
+  if (!GENERIC && sizeof(DT) == 4 && p.batches == 1 && ep.vec4_ok && g.N % 4 == 0 && p.total_tiles < 2 * units && num_kb >= 16) {
+    // pick the split count with the cheapest wave schedule (48 tile pairs on 74 clusters: 1 split keeps 65 % of the
+    // machine busy for 758 k-blocks, 3 splits run two waves at 97 % for 253 k-blocks each)
+    // cost of a launch in k-block times: waves x (k-blocks per split + one atomic epilogue ~ 40 k-blocks)
+    const int max_splits = (int)std::min<int64_t>(std::max<int64_t>(2 * units / p.total_tiles, 1), num_kb / 8);
+    double best = 1e30;
+    for (int sct = 1; sct <= max_splits; ++sct) {
+      const int64_t items = p.total_tiles * sct, waves = (items + units - 1) / units;
+      const double cost = (double)waves * ((double)((num_kb + sct - 1) / sct) + 40.0);
+      if (cost < best * 0.98) { best = cost; p.splits = sct; }
+    }
   }
   p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits

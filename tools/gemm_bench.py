@@ -42,3 +42,6 @@ bench(S, 1024, 1024, b_mn=True)
 bench(1024, 4096, S, a_mn=True, b_mn=True, out=torch.float32)
 bench(1024, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
 bench(4096, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
+bench(3072, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
+bench(2048, 1024, S, a_mn=True, b_mn=True, out=torch.float32)
+bench(768, 768, 16512, a_mn=True, b_mn=True, out=torch.float32)
