@@ -153,6 +153,13 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # optional: cap NCCL's CTAs and keep that many SMs out of the persistent kernels' grids (tsw_set_sm_reserve).
+        # Measured on 2 and 8 B200: no gain over letting the all-reduce share the SMs (207 vs 211 ms, 225 vs 232 ms), so off
+        reserve = int(os.environ.get("TSW_SM_RESERVE", "0"))
+        if reserve > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
+            from robustsq_whisper_b200 import _C
+            _C.check(_C.load().tsw_set_sm_reserve(reserve), "tsw_set_sm_reserve")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 

@@ -44,6 +44,11 @@ int tsw_abi_version(void);
 const char* tsw_last_error(void);
 /* sm count / compute capability of the current device; fails with TSW_E_UNSUPPORTED unless cc == 10.x */
 int tsw_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Data-parallel runs: the persistent kernels (tcgen05 GEMM, attention backward) size their grids to sm_count - n_sm so that
+ * the communication library's kernels (gradient all-reduce overlapped with backward) always find free SMs.  With a static
+ * tile schedule a persistent CTA that has to wait for an SM held by a long all-reduce kernel delays the whole launch.
+ * n_sm even, 0 restores the full machine.  Process-wide. */
+int tsw_set_sm_reserve(int n_sm);
 
 /* ------------------------------------------------------------------------------------------------ K1 log-mel
  * Replaces OpenAIWhisperEncoder.log_mel_spectrogram, whisper_encoder.py:99-129 (torch.stft -> |.|^2 ->

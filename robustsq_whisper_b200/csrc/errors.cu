@@ -11,6 +11,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static int g_sm_reserve = 0;   // SMs the persistent kernels leave free (for NCCL's kernels in data-parallel runs)
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -20,10 +21,15 @@ int sm_count() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
     cached[dev] = n;
   }
-  return cached[dev];
+  return cached[dev] - g_sm_reserve > 8 ? cached[dev] - g_sm_reserve : cached[dev];
 }
 }  // namespace tsw
 
+extern "C" int tsw_set_sm_reserve(int n_sm) {
+  TSW_CHECK_ARG(n_sm >= 0 && n_sm % 2 == 0 && n_sm <= 64, "set_sm_reserve: expected an even count in [0, 64]");
+  tsw::g_sm_reserve = n_sm;
+  return TSW_OK;
+}
 extern "C" int tsw_abi_version(void) { return TSW_ABI_VERSION; }
 extern "C" const char* tsw_last_error(void) { return tsw::g_err; }
 extern "C" int tsw_device_info(int* sm_count, int* cc_major, int* cc_minor) {
