@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--negatives", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--lora", type=int, default=0, metavar="R", help="BASELINE configs[4]: q/k/v/o LoRA adapters of rank R on the Whisper blocks, base weights frozen "
+                    "(robustsq_whisper_b200.lora); the default 0 is the full fine-tune the headline metric is quoted on")
     ap.add_argument("--graph", action="store_true", help="replay the whole step as one CUDA graph (robustsq_whisper_b200.graph) instead of the eager plugin call; "
                     "measured equal on this host (the step is GPU-bound, inter-kernel gaps ~1 us), so the default stays the reference-facing eager call")
     return ap.parse_args()
@@ -169,6 +171,13 @@ def run_b200(args):
     model.decoder.compute_dtype = torch.bfloat16
     model.materialize_heads()
     model.set_epoch(6)
+    if args.lora > 0:
+        from robustsq_whisper_b200 import lora
+        lora.apply_lora(model, rank=args.lora, alpha=float(args.lora))
+        with torch.no_grad():   # B = 0 at initialisation would make dA identically zero: use the state after a few updates
+            for mod in model.modules():
+                if getattr(mod, "lora_B", None) is not None:
+                    mod.lora_B.normal_(0.0, 0.01)
     reducer = GradientAllReducer(model.parameters(), overlap=os.environ.get("TSW_DDP_OVERLAP", "1") != "0")
 
     B = args.batch
@@ -297,7 +306,8 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"whisper-{args.model} TS-ASR training step (fwd+bwd), {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment, "
-                                   f"q=16, SQ-Former L=2, K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE",
+                                   f"q=16, SQ-Former L=2, K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE"
+                                   + (f", LoRA q/k/v/o r={args.lora} on the Whisper blocks with the base frozen" if args.lora > 0 else ""),
                        "launch": "eager (one launch per kernel)" if graphed is None else "one CUDA graph per step (forward + backward + gradient all-reduce), host-side utt-id parsing / negative sampling outside it",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2_policy": "per-step inputs and activations (>10 GB) exceed the 126 MB L2; fresh input copies each step",

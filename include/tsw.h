@@ -28,7 +28,7 @@ extern "C" {
 
 typedef struct CUstream_st* tsw_stream_t; /* == cudaStream_t */
 
-#define TSW_ABI_VERSION 1
+#define TSW_ABI_VERSION 2
 
 enum { TSW_F32 = 0, TSW_BF16 = 1 };
 
@@ -96,6 +96,12 @@ typedef struct {
   int32_t impl;        /* TSW_GEMM_* */
   float alpha, beta;   /* beta in {0,1} */
   const float* alpha_dev; /* optional device scalar multiplied into alpha (upstream loss gradient), or NULL */
+  /* Optional second operand pair appended along the contraction: D = epilogue(alpha * (A B + A2 B2)), A2 (M x K2) and
+   * B2 (K2 x N) with the dtypes and majors of A and B, unbatched.  This is how a LoRA update y = x W^T + (x A^T)(s B)^T
+   * (loralib Linear.forward, the `lora_qkvo_r16` recipe of the reference README:55) and its input gradient
+   * dx = dy W + (dy s B) A ride in the main loop of the base GEMM as one extra k-block instead of a second pass over y.
+   * NULL / 0 when unused.  Both kernels take it with every epilogue. */
+  const void* A2; const void* B2; int64_t K2, lda2, ldb2;
 } tsw_gemm_desc;
 
 size_t tsw_gemm_workspace_bytes(const tsw_gemm_desc* d);
@@ -109,7 +115,8 @@ int tsw_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
                       float* mean, float* rstd, int64_t rows, int64_t d, float eps, int dtype, tsw_stream_t stream);
 size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d);
 /* dx = LN'(dy) (+ dres, the gradient arriving on the residual branch that bypasses the LN, or NULL); dgamma/dbeta (d) fp32
- * are OVERWRITTEN. x is the LN input (x + res when fused). */
+ * are OVERWRITTEN (both NULL: frozen affine parameters, the parameter-gradient pass is skipped). x is the LN input
+ * (x + res when fused). */
 int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
                       void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
                       size_t workspace_bytes, tsw_stream_t stream);

@@ -103,6 +103,12 @@ def _lin(x: Tensor, p: P, name: str) -> Tensor:
     return F.linear(x, p[name + ".weight"].to(x.dtype), None if b is None else b.to(x.dtype))
 
 
+def lora_linear(x: Tensor, W: Tensor, b: Optional[Tensor], A: Tensor, Bm: Tensor, scaling: float) -> Tensor:
+    """loralib ``Linear.forward`` (r > 0, not merged, dropout 0) [upstream, un-vendored; the recipe README.md:55 names]:
+    F.linear(x, W, b) + (x @ A^T @ B^T) * (lora_alpha / r)."""
+    return F.linear(x, W, b) + (x @ A.t() @ Bm.t()) * scaling
+
+
 def _heads(x: Tensor, h: int) -> Tensor:
     return x.view(x.size(0), x.size(1), h, -1).permute(0, 2, 1, 3)
 

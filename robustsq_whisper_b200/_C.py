@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtsw_sm100.so")
 
 F32, BF16 = 0, 1
+ABI_VERSION = 2
 EPI_NONE, EPI_GELU, EPI_MUL_DGELU, EPI_GELU_SAVE_GRAD, EPI_MUL_AUX = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 
@@ -37,6 +38,7 @@ class GemmDesc(Structure):
         ("epilogue", c_int32), ("impl", c_int32),
         ("alpha", c_float), ("beta", c_float),
         ("alpha_dev", c_void_p),
+        ("A2", c_void_p), ("B2", c_void_p), ("K2", c_int64), ("lda2", c_int64), ("ldb2", c_int64),
     ]
 
 
@@ -102,7 +104,7 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.tsw_abi_version() != 1:
+    if lib.tsw_abi_version() != ABI_VERSION:
         raise TswError(f"ABI version mismatch: library reports {lib.tsw_abi_version()}")
     _lib = lib
     return lib

@@ -18,6 +18,9 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   TSW_CHECK_ARG((g.epilogue != TSW_EPI_MUL_DGELU && g.epilogue != TSW_EPI_MUL_AUX) || g.aux_in, "gemm: MUL_DGELU / MUL_AUX need aux_in");
   TSW_CHECK_ARG(!g.residual || (g.res_dtype == g.d_dtype && g.ldres >= g.N), "gemm: residual must have the output dtype");
   TSW_CHECK_ARG(g.beta == 0.f || g.beta == 1.f, "gemm: beta must be 0 or 1");
+  TSW_CHECK_ARG((g.A2 == nullptr) == (g.B2 == nullptr), "gemm: A2 and B2 go together");
+  TSW_CHECK_ARG(!g.A2 || (g.K2 > 0 && g.lda2 >= (g.a_mn_major ? g.M : g.K2) && g.ldb2 >= (g.b_mn_major ? g.N : g.K2)),
+                "gemm: second operand pair: bad K2 / leading dimensions");
 
   EpiParams ep;
   ep.D = g.D; ep.ldd = g.ldd;

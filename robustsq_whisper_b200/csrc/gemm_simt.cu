@@ -11,7 +11,7 @@ template <typename AT, typename BT, typename DT>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const AT* __restrict__ A, const BT* __restrict__ B, int64_t K, int a_mn, int b_mn, int64_t lda, int64_t ldb,
                  int64_t a_so, int64_t a_si, int64_t b_so, int64_t b_si, int64_t d_so, int64_t d_si, int64_t r_so, int64_t r_si,
-                 int batch_inner, EpiParams ep) {
+                 int batch_inner, const AT* __restrict__ A2, const BT* __restrict__ B2, int64_t K2, int64_t lda2, int64_t ldb2, EpiParams ep) {
   __shared__ __align__(16) float As[SBK][SBM + SPAD];
   __shared__ __align__(16) float Bs[SBK][SBN + SPAD];
   const int tid = threadIdx.x;
@@ -27,6 +27,8 @@ gemm_simt_kernel(const AT* __restrict__ A, const BT* __restrict__ B, int64_t K, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // the contraction over A x B, then over the optional second pair A2 x B2 (tsw.h: the LoRA low-rank term)
+  auto contract = [&](const AT* Ab, const BT* Bb, int64_t K, int64_t lda, int64_t ldb) {
   for (int64_t k0 = 0; k0 < K; k0 += SBK) {
     // 64 x 16 elements per operand, 4 per thread; the fast thread index follows the contiguous dimension
 #pragma unroll
@@ -58,6 +60,9 @@ gemm_simt_kernel(const AT* __restrict__ A, const BT* __restrict__ B, int64_t K, 
     }
     __syncthreads();
   }
+  };
+  contract(Ab, Bb, K, lda, ldb);
+  if (A2 != nullptr) contract(A2, B2, K2, lda2, ldb2);
   // 4 consecutive columns per row; fp32 D takes them as one vector, bf16 D needs 8 -> scalar path via vec_ok = 0
   EpiParams e2 = ep;
   if (sizeof(DT) == 2) e2.vec_ok = 0;
@@ -78,12 +83,13 @@ template <typename AT, typename BT, typename DT>
 static int simt_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   const int64_t batches = (int64_t)g.batch_outer * g.batch_inner;
   TSW_CHECK_ARG(batches <= 65535, "gemm(simt): batch %lld > 65535", (long long)batches);
+  TSW_CHECK_ARG(!g.A2 || batches == 1, "gemm(simt): the second operand pair needs an unbatched problem");
   dim3 grid((unsigned)((g.N + SBN - 1) / SBN), (unsigned)((g.M + SBM - 1) / SBM), (unsigned)batches);
   TSW_CHECK_ARG(grid.y <= 65535, "gemm(simt): M too large");
   gemm_simt_kernel<AT, BT, DT><<<grid, 256, 0, st>>>((const AT*)g.A, (const BT*)g.B, g.K, g.a_mn_major, g.b_mn_major, g.lda, g.ldb,
                                                      g.a_stride_outer, g.a_stride_inner, g.b_stride_outer, g.b_stride_inner,
                                                      g.d_stride_outer, g.d_stride_inner, g.res_stride_outer, g.res_stride_inner,
-                                                     g.batch_inner, ep);
+                                                     g.batch_inner, (const AT*)g.A2, (const BT*)g.B2, g.K2, g.lda2, g.ldb2, ep);
   TSW_LAUNCH_CHECK();
   return TSW_OK;
 }

@@ -38,6 +38,7 @@ struct TcParams {
   int tiles_m, tiles_n;
   int64_t total_tiles;   // output tiles
   int splits, kb_per_split;  // split-K: work item = (tile, split); partial sums are atomically added into fp32 D
+  int kb_main, kb_total;     // k-blocks of A x B, and including the appended low-rank pair A2 x B2 (LoRA term)
   int64_t total_work;    // total_tiles * splits
 };
 
@@ -154,7 +155,8 @@ struct TcSmem {
 
 template <int BN, int STAGES, typename DT, bool GENERIC, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p, const EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB2, const TcParams p, const EpiParams ep) {
   using S = TcSmem<BN, STAGES>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -170,7 +172,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    if (p.kb_total > p.kb_main) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+  }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
@@ -184,7 +189,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
   const int64_t w_first = blockIdx.x / CL, w_step = gridDim.x / CL;   // work items are walked per cluster
 
-  const int num_kb = (int)((p.K + TBK - 1) / TBK);
+  // the contraction runs over the k-blocks of A x B followed by those of the optional second pair A2 x B2 (same majors):
+  // D = epilogue(alpha (A B + A2 B2)) — the low-rank LoRA update rides in the main loop as one extra k-block
+  const int num_kb = p.kb_total;
   const int64_t tiles_per_batch = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n;   // work items (tiles, or vertical tile pairs) per batch
 
   if (warp == 0) {
@@ -205,28 +212,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           unsigned char* sa = tiles + (size_t)stage * S::kStageBytes;
           unsigned char* sb = sa + S::kABytes;
           mbar_expect_tx(&full[stage], S::kStageBytes);
-          const int k0 = kb * TBK;
+          const bool second = kb >= p.kb_main;
+          const CUtensorMap* ta = second ? &tmA2 : &tmA;
+          const CUtensorMap* tb = second ? &tmB2 : &tmB;
+          const int k0 = (second ? kb - p.kb_main : kb) * TBK;
           if (!p.a_mn) {
-            tma_load_4d(&tmA, &full[stage], sa, k0, m0, bi, bo);                       // box {64 k, 128 m}
+            tma_load_4d(ta, &full[stage], sa, k0, m0, bi, bo);                       // box {64 k, 128 m}
           } else {
 #pragma unroll
-            for (int j = 0; j < TBM / 64; ++j) tma_load_4d(&tmA, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);  // box {64 m, 64 k}
+            for (int j = 0; j < TBM / 64; ++j) tma_load_4d(ta, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);  // box {64 m, 64 k}
           }
           if (CL == 1) {
             if (!p.b_mn) {
-              tma_load_4d(&tmB, &full[stage], sb, k0, n0, bi, bo);                       // box {64 k, BN n}
+              tma_load_4d(tb, &full[stage], sb, k0, n0, bi, bo);                       // box {64 k, BN n}
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_4d(&tmB, &full[stage], sb + j * kPanelBytes, n0 + 64 * j, k0, bi, bo);
+              for (int j = 0; j < BN / 64; ++j) tma_load_4d(tb, &full[stage], sb + j * kPanelBytes, n0 + 64 * j, k0, bi, bo);
             }
           } else {   // this CTA's half of the B tile, delivered to both CTAs of the pair
             if (!p.b_mn) {
-              tma_load_4d_mc(&tmB, &full[stage], sb + crank * (S::kBBytes / 2), k0, n0 + crank * (BN / 2), bi, bo, (uint16_t)3);   // box {64 k, BN/2 n}
+              tma_load_4d_mc(tb, &full[stage], sb + crank * (S::kBBytes / 2), k0, n0 + crank * (BN / 2), bi, bo, (uint16_t)3);   // box {64 k, BN/2 n}
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 128; ++j) {
                 const int jj = crank * (BN / 128) + j;
-                tma_load_4d_mc(&tmB, &full[stage], sb + jj * kPanelBytes, n0 + 64 * jj, k0, bi, bo, (uint16_t)3);
+                tma_load_4d_mc(tb, &full[stage], sb + jj * kPanelBytes, n0 + 64 * jj, k0, bi, bo, (uint16_t)3);
               }
             }
           }
@@ -422,6 +432,11 @@ bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
     return bad("batch strides must be multiples of 8 elements");
   if (g.M < 1 || g.N < 1 || g.K < 1) return bad("empty problem");
   if (g.M >= (1ll << 31) || g.N >= (1ll << 31) || g.K >= (1ll << 31)) return bad("dimension exceeds 2^31");
+  if (g.A2) {
+    if (!aligned16(g.A2) || !aligned16(g.B2)) return bad("second operand pair: base pointers must be 16-byte aligned");
+    if (g.lda2 % 8 || g.ldb2 % 8) return bad("second operand pair: leading dimensions must be multiples of 8 elements");
+    if (g.batch_inner * g.batch_outer != 1) return bad("second operand pair: unbatched problems only");
+  }
   return true;
 }
 
@@ -433,6 +448,13 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   if (rc) return rc;
   rc = make_operand_map(&tmB, g.B, g.b_mn_major, g.N, g.K, g.ldb, g.batch_inner, g.b_stride_inner, g.batch_outer, g.b_stride_outer, BN / CL);
   if (rc) return rc;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;   // second (low-rank) operand pair, same majors; unbatched
+  if (g.A2) {
+    rc = make_operand_map(&tmA2, g.A2, g.a_mn_major, g.M, g.K2, g.lda2, 1, 0, 1, 0, TBM);
+    if (rc) return rc;
+    rc = make_operand_map(&tmB2, g.B2, g.b_mn_major, g.N, g.K2, g.ldb2, 1, 0, 1, 0, BN / CL);
+    if (rc) return rc;
+  }
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.batch_inner = g.batch_inner; p.batches = g.batch_inner * g.batch_outer;
@@ -443,7 +465,9 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   // tile whose loads are zero-filled and whose rows the epilogue masks
   p.total_tiles = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.batches;
   const int units = sm_count() / CL;   // CTAs (CL = 1) or clusters (CL = 2) that run concurrently
-  const int num_kb = (int)((g.K + TBK - 1) / TBK);
+  p.kb_main = (int)((g.K + TBK - 1) / TBK);
+  p.kb_total = p.kb_main + (g.A2 ? (int)((g.K2 + TBK - 1) / TBK) : 0);
+  const int num_kb = p.kb_total;
   p.splits = 1;
   // split-K when the output has too few tiles to occupy the machine (weight gradients: M, N ~ 1e3, K ~ 5e4): fp32 output,
   // plain epilogue, whole rows 16-byte aligned (vector atomics), one batch
@@ -471,7 +495,7 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   }
   const int grid = (int)std::min<int64_t>(p.total_work, units) * CL;
   if (CL == 1) {
-    kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, p, ep);
+    kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, tmA2, tmB2, p, ep);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::kBytes; cfg.stream = st;
@@ -479,7 +503,7 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    TSW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p, ep));
+    TSW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, p, ep));
   }
   TSW_LAUNCH_CHECK();
   return TSW_OK;

@@ -537,7 +537,8 @@ extern "C" size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d) {
 extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
                                  void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
                                  size_t workspace_bytes, tsw_stream_t stream) {
-  TSW_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "layernorm_bwd: null/empty argument");
+  TSW_CHECK_ARG(dy && x && gamma && mean && rstd && dx && rows > 0, "layernorm_bwd: null/empty argument");
+  TSW_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
   const int vn = dtype == TSW_F32 ? 4 : 8;
   TSW_CHECK_ARG(d % vn == 0 && d / vn <= 32 * kLnChunks, "layernorm_bwd: d=%lld unsupported", (long long)d);
   TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!dres || aligned16(dres)), "layernorm_bwd: pointers must be 16-byte aligned");
@@ -547,6 +548,7 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   const int nc = (int)((d / vn + 31) / 32);
   DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (ln_bwd_dx_kernel<T, NC><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d))));
   TSW_LAUNCH_CHECK();
+  if (!dgamma) return TSW_OK;   // frozen affine parameters: no parameter-gradient pass
   const int64_t chunks = colsum_chunks(rows, d, vn);
   const int64_t rpc = (rows + chunks - 1) / chunks;
   dim3 g2((unsigned)((d + 32 * vn - 1) / (32 * vn)), (unsigned)chunks);

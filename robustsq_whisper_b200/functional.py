@@ -171,11 +171,19 @@ class _MLP(Function):
         dy2 = dy.reshape(rows, N)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl)
-        db2 = K.colsum(dy2, rows, N)
+        need = ctx.needs_input_grad   # frozen parameters (LoRA fine-tuning) skip their weight-gradient GEMM / column sum
+        dw1 = db1 = dw2 = db2 = None
+        if need[3]:
+            dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl)
+        if need[4]:
+            db2 = K.colsum(dy2, rows, N)
+        if not (need[0] or need[1] or need[2]):
+            return None, None, None, dw2, db2, (dy if ctx.has_res else None)
         dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_AUX, out_dtype=dt, impl=impl)
-        dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl)
-        db1 = K.colsum(dh, rows, H)
+        if need[1]:
+            dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl)
+        if need[2]:
+            db1 = K.colsum(dh, rows, H)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.gemm(dh, shadow(w1, dt), M=rows, N=d, K=H, b_mn=True, ldb=d, out_dtype=dt, impl=impl).view(ctx.in_shape)
@@ -198,7 +206,7 @@ class _LayerNorm(Function):
     @staticmethod
     def backward(ctx, dy: Tensor):
         xin, gamma, mean, rstd = ctx.saved_tensors
-        dx, dg, db = K.layernorm_bwd(dy, xin, gamma.detach(), mean, rstd)
+        dx, dg, db = K.layernorm_bwd(dy, xin, gamma.detach(), mean, rstd, param_grads=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         return dx, dg, db, None, (dx if ctx.has_res else None)
 
 
@@ -219,7 +227,7 @@ class _LayerNormTap(Function):
         x, gamma, mean, rstd = ctx.saved_tensors
         if gy is None:
             return g_skip, None, None, None
-        dx, dg, db = K.layernorm_bwd(gy, x, gamma.detach(), mean, rstd, dres=g_skip)
+        dx, dg, db = K.layernorm_bwd(gy, x, gamma.detach(), mean, rstd, dres=g_skip, param_grads=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         return dx, dg, db, None
 
 

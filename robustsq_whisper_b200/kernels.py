@@ -93,11 +93,13 @@ def gemm(
     res_strides: Tuple[int, int] = (0, 0), res_row_mod: int = 0,
     aux_in: Optional[Tensor] = None, aux_out: Optional[Tensor] = None, epilogue: int = _C.EPI_NONE,
     alpha: float = 1.0, beta: float = 0.0, impl: int = _C.GEMM_AUTO, alpha_dev: Optional[Tensor] = None,
+    a2: Optional[Tensor] = None, b2: Optional[Tensor] = None, K2: int = 0, lda2: Optional[int] = None, ldb2: Optional[int] = None,
 ) -> Tensor:
     """D = epilogue(alpha * A @ B) with the operand layouts of include/tsw.h.  ``a``/``b`` are only used for their
     storage (data_ptr, dtype): the logical shapes come from M/N/K, the majors and the leading dimensions.
-    batch = (outer, inner); *_strides = (outer stride, inner stride) in elements."""
-    require_cuda(a, b, out, bias, residual, aux_in, aux_out)
+    batch = (outer, inner); *_strides = (outer stride, inner stride) in elements.
+    a2 / b2 / K2: optional second operand pair appended along the contraction (D = epilogue(alpha (A B + A2 B2)))."""
+    require_cuda(a, b, out, bias, residual, aux_in, aux_out, a2, b2)
     lib = _C.load()
     bo, bi = batch
     if out is None:
@@ -129,13 +131,19 @@ def gemm(
     if alpha_dev is not None and (alpha_dev.dtype != torch.float32 or not alpha_dev.is_cuda):
         raise _C.TswError("gemm: alpha_dev must be a float32 cuda scalar")
     g.alpha_dev = ptr(alpha_dev)
+    if a2 is not None:
+        if b2 is None or K2 <= 0 or a2.dtype != a.dtype or b2.dtype != b.dtype:
+            raise _C.TswError("gemm: a2/b2 need K2 > 0 and the dtypes of a/b")
+        g.A2, g.B2, g.K2 = ptr(a2), ptr(b2), K2
+        g.lda2 = lda2 if lda2 is not None else (M if a_mn else K2)
+        g.ldb2 = ldb2 if ldb2 is not None else (N if b_mn else K2)
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
         e1.record()
         tc = impl != _C.GEMM_SIMT and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
-        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * K * bo * bi, "tcgen05" if tc else "simt", M, N, K, bo * bi))
+        GEMM_PROFILE.append((e0, e1, 2.0 * M * N * (K + K2) * bo * bi, "tcgen05" if tc else "simt", M, N, K, bo * bi))
     else:
         check(lib.tsw_gemm(ctypes.byref(g), None, 0, stream()), "tsw_gemm")
     _count(1)
@@ -161,7 +169,7 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optio
     return y, sum_out, mean, rstd
 
 
-def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dres: Optional[Tensor] = None):
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dres: Optional[Tensor] = None, param_grads: bool = True):
     lib = _C.load()
     d = x.shape[-1]
     rows = x.numel() // d
@@ -169,12 +177,12 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
     if dres is not None:
         dres = dres.contiguous()
     dx = torch.empty_like(x)
-    dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
+    dgamma = torch.empty(d, dtype=torch.float32, device=x.device) if param_grads else None
+    dbeta = torch.empty(d, dtype=torch.float32, device=x.device) if param_grads else None
     ws = _ws(lib.tsw_layernorm_bwd_workspace_bytes(rows, d), x.device)
     check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
                                 dtype_code(x.dtype), ptr(ws), ws.numel(), stream()), "tsw_layernorm_bwd")
-    _count(2)
+    _count(2 if param_grads else 1)
     return dx, dgamma, dbeta
 
 

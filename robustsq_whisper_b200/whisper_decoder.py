@@ -16,6 +16,7 @@ from torch import Tensor
 
 from . import functional as F
 from . import kernels as K
+from . import lora
 from . import whisper_model as W
 from ._compat import AbsDecoder, BatchScorerInterface, compute_dtype
 
@@ -101,6 +102,9 @@ class QFormerTgtSpkWhisperDecoder_V2(AbsDecoder, BatchScorerInterface):
     def decode_prefill(self, ys: Tensor, memory: Tensor, spk_prompt: Tensor, max_new_tokens: int = 448) -> Tuple[Tensor, "DecodeCache"]:
         """Process [startofprev, prompt, ys] in one pass and build the caches.  -> (log-probs of the next token (n, V), cache)."""
         dec = self.decoders
+        if any(lora.has_lora(b.attn.query, b.attn.key, b.attn.value, b.attn.out, b.cross_attn.query, b.cross_attn.key, b.cross_attn.value,
+                             b.cross_attn.out) for b in dec.blocks):
+            raise RuntimeError("cached decoding reads the base projection weights: call lora.merge_lora(model) first (loralib merges on eval())")
         n = ys.size(0)
         if spk_prompt.size(0) != n:
             spk_prompt = spk_prompt.expand(n, -1, -1)

@@ -17,6 +17,7 @@ import torch
 from torch import Tensor, nn
 
 from . import functional as F
+from . import lora
 
 # name -> (n_state, n_head, n_layer)
 WHISPER_DIMS = {"tiny": (384, 6, 4), "base": (512, 8, 6), "small": (768, 12, 12), "medium": (1024, 16, 24)}
@@ -116,18 +117,24 @@ def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool
     if F.packed_attention_ok(x, p.n_head):   # training regime: packed projections around the fused attention kernel
         scale = (x.shape[-1] // p.n_head) ** -0.5
         if xa is None:
-            a = F.self_attention_packed(x, p.query.weight, p.query.bias, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale, causal)
+            if lora.has_lora(p.query, p.key, p.value):
+                a = lora.self_attention_packed(p, x, p.n_head, scale, causal)
+            else:
+                a = F.self_attention_packed(x, p.query.weight, p.query.bias, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale, causal)
         else:
-            q = F.linear(x, p.query.weight, p.query.bias)
-            a = F.cross_attention_packed(q, xa, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale)
-        return F.linear(a, p.out.weight, p.out.bias, residual=residual)
+            q = lora.linear(p.query, x)
+            if lora.has_lora(p.key, p.value):
+                a = lora.cross_attention_packed(p, q, xa, p.n_head, scale)
+            else:
+                a = F.cross_attention_packed(q, xa, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale)
+        return lora.linear(p.out, a, residual=residual)
     src = x if xa is None else xa
-    q = F.linear(x, p.query.weight, p.query.bias)
-    k = F.linear(src, p.key.weight, None)
-    v = F.linear(src, p.value.weight, p.value.bias)
+    q = lora.linear(p.query, x)
+    k = lora.linear(p.key, src)
+    v = lora.linear(p.value, src)
     dh = q.shape[-1] // p.n_head
     a = F.attention(q, k, v, p.n_head, dh ** -0.5, causal=causal)
-    return F.linear(a, p.out.weight, p.out.bias, residual=residual)
+    return lora.linear(p.out, a, residual=residual)
 
 
 def residual_block(p: BlockParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False) -> Tensor:
