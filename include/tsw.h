@@ -135,6 +135,16 @@ int tsw_add(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_str
 int tsw_gelu_fwd(const void* x, void* y, int dtype, int64_t n, tsw_stream_t stream);
 int tsw_gelu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, tsw_stream_t stream);
 
+/* SpecAug on the mixture log-mel (whisper_encoder.py:521-524 -> ESPnet SpecAug [upstream]): time warp, frequency masks,
+ * time masks in one pass.  in (B, n_mel, t_in) -> out (B, n_mel, t_out), t_out <= t_in (ESPnet re-pads a ragged batch to its
+ * longest item).  warp (B, 3) int32 = {centre, warped, length} per item or NULL: frames [0, warped) are the bicubic
+ * (A = -0.75, align_corners = False) resampling of [0, centre), frames [warped, length) that of [centre, length);
+ * centre <= 0 leaves the item un-warped.  fmask (B, n_fmask, 2) / tmask (B, n_tmask, 2) int32 = {start, width}: covered
+ * mel bins / frames become 0.  zero_tail != 0: frames >= length become 0 (pad_list after per-item warping), else copied.
+ * All draws are made by the caller with the reference's RNG call order (robustsq_whisper_b200/specaug.py). */
+int tsw_specaug_fwd(const void* in, void* out, int dtype, int64_t B, int64_t n_mel, int64_t t_in, int64_t t_out, const int32_t* warp,
+                    const int32_t* fmask, int n_fmask, const int32_t* tmask, int n_tmask, int zero_tail, tsw_stream_t stream);
+
 /* Conv stem staging (whisper_encoder.py:446-447,464-465): im2col for a k=3, pad=1 conv with the given stride.
  * in: channels_first ? (B, C, T) : (B, T, C) ; out (B*T_out, 3*C) with column index = k*C + c, T_out = (T+2-3)/stride+1. */
 int tsw_im2col_k3(const void* in, int dtype, int channels_first, int64_t B, int64_t C, int64_t T, int stride, void* out,

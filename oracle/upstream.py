@@ -368,3 +368,123 @@ class ESPnetASRModelBase(nn.Module):
 
     def _calc_ctc_loss(self, *a, **k):  # pragma: no cover - ctc_weight is 0 on this path
         raise NotImplementedError("CTC branch is outside the TS-ASR hot path (ctc_weight == 0)")
+
+
+# ------------------------------------------------------------------------------------------------ ESPnet SpecAug [upstream]
+# Restated from espnet2/asr/specaug/specaug.py, espnet2/layers/time_warp.py and espnet2/layers/mask_along_axis.py (ESPnet
+# is not installable offline: parity-unpinned against its sources).  Call site: whisper_encoder.py:66-69,521-524 — the
+# mixture log-mel, transposed to (B, T, 80), in training mode only.  The RNG call order below is what the B200 host
+# class (robustsq_whisper_b200/specaug.py) reproduces draw for draw.
+def time_warp(x: Tensor, window: int = 80, mode: str = "bicubic") -> Tensor:
+    org_size = x.size()
+    if x.dim() == 3:
+        x = x[:, None]                                   # (B, 1, T, F)
+    t = x.shape[2]
+    if t - window <= window:
+        return x.view(*org_size)
+    center = torch.randint(window, t - window, (1,))[0]
+    warped = torch.randint(center - window, center + window, (1,))[0] + 1
+    left = torch.nn.functional.interpolate(x[:, :, :center], (warped, x.shape[3]), mode=mode, align_corners=False)
+    right = torch.nn.functional.interpolate(x[:, :, center:], (t - warped, x.shape[3]), mode=mode, align_corners=False)
+    return torch.cat([left, right], dim=-2).view(*org_size)
+
+
+class TimeWarp(nn.Module):
+    def __init__(self, window: int = 80, mode: str = "bicubic"):
+        super().__init__()
+        self.window, self.mode = window, mode
+
+    def forward(self, x: Tensor, x_lengths: Optional[Tensor] = None):
+        if x_lengths is None or all(le == x_lengths[0] for le in x_lengths):
+            y = time_warp(x, window=self.window, mode=self.mode)     # one draw for the whole batch
+        else:
+            ys = [time_warp(x[i][None, : x_lengths[i]], window=self.window, mode=self.mode)[0] for i in range(x.size(0))]
+            y = pad_list(ys, 0.0)
+        return y, x_lengths
+
+
+def mask_along_axis(spec: Tensor, spec_lengths: Optional[Tensor], mask_width_range=(0, 30), dim: int = 1, num_mask: int = 2,
+                    replace_with_zero: bool = True):
+    org_size = spec.size()
+    if spec.dim() == 4:
+        spec = spec.view(-1, spec.size(2), spec.size(3))
+    B, D = spec.shape[0], spec.shape[dim]
+    mask_length = torch.randint(mask_width_range[0], mask_width_range[1], (B, num_mask), device=spec.device).unsqueeze(2)
+    mask_pos = torch.randint(0, max(1, D - int(mask_length.max())), (B, num_mask), device=spec.device).unsqueeze(2)
+    aran = torch.arange(D, device=spec.device)[None, None, :]
+    mask = ((mask_pos <= aran) * (aran < (mask_pos + mask_length))).any(dim=1)
+    mask = mask.unsqueeze(2) if dim == 1 else mask.unsqueeze(1)
+    value = 0.0 if replace_with_zero else spec.mean()
+    return spec.masked_fill(mask, value).view(*org_size), spec_lengths
+
+
+class MaskAlongAxis(nn.Module):
+    def __init__(self, mask_width_range=(0, 30), num_mask: int = 2, dim="time", replace_with_zero: bool = True):
+        super().__init__()
+        if isinstance(mask_width_range, int):
+            mask_width_range = (0, mask_width_range)
+        if len(mask_width_range) != 2:
+            raise TypeError(f"mask_width_range must be a tuple of int and int values: {mask_width_range}")
+        assert mask_width_range[1] > mask_width_range[0]
+        if isinstance(dim, str):
+            dim = {"time": 1, "freq": 2}[dim]
+        self.mask_width_range, self.num_mask, self.dim, self.replace_with_zero = tuple(mask_width_range), num_mask, dim, replace_with_zero
+
+    def forward(self, spec: Tensor, spec_lengths: Optional[Tensor] = None):
+        return mask_along_axis(spec, spec_lengths, self.mask_width_range, self.dim, self.num_mask, self.replace_with_zero)
+
+
+class MaskAlongAxisVariableMaxWidth(nn.Module):
+    def __init__(self, mask_width_ratio_range=(0.0, 0.05), num_mask: int = 2, dim="time", replace_with_zero: bool = True):
+        super().__init__()
+        if isinstance(mask_width_ratio_range, float):
+            mask_width_ratio_range = (0.0, mask_width_ratio_range)
+        if len(mask_width_ratio_range) != 2:
+            raise TypeError(f"mask_width_ratio_range must be a tuple of float and float values: {mask_width_ratio_range}")
+        assert mask_width_ratio_range[1] > mask_width_ratio_range[0]
+        if isinstance(dim, str):
+            dim = {"time": 1, "freq": 2}[dim]
+        self.mask_width_ratio_range, self.num_mask, self.dim, self.replace_with_zero = tuple(mask_width_ratio_range), num_mask, dim, replace_with_zero
+
+    def forward(self, spec: Tensor, spec_lengths: Optional[Tensor] = None):
+        max_seq_len = spec.shape[self.dim]
+        lo = max(0, math.floor(max_seq_len * self.mask_width_ratio_range[0]))
+        hi = min(max_seq_len, math.floor(max_seq_len * self.mask_width_ratio_range[1]))
+        if hi > lo:
+            return mask_along_axis(spec, spec_lengths, (lo, hi), self.dim, self.num_mask, self.replace_with_zero)
+        return spec, spec_lengths
+
+
+class SpecAug(nn.Module):
+    """time warp -> frequency mask -> time mask (ESPnet order)."""
+
+    def __init__(self, apply_time_warp: bool = True, time_warp_window: int = 5, time_warp_mode: str = "bicubic", apply_freq_mask: bool = True,
+                 freq_mask_width_range=(0, 20), num_freq_mask: int = 2, apply_time_mask: bool = True, time_mask_width_range=None,
+                 time_mask_width_ratio_range=None, num_time_mask: int = 2, replace_with_zero: bool = True):
+        if not apply_time_warp and not apply_time_mask and not apply_freq_mask:
+            raise ValueError("Either one of time_warp, time_mask, or freq_mask should be applied")
+        if apply_time_mask and (time_mask_width_range is not None) and (time_mask_width_ratio_range is not None):
+            raise ValueError('Either one of "time_mask_width_range" or "time_mask_width_ratio_range" can be used')
+        super().__init__()
+        self.time_warp = TimeWarp(window=time_warp_window, mode=time_warp_mode) if apply_time_warp else None
+        self.freq_mask = MaskAlongAxis(dim="freq", mask_width_range=freq_mask_width_range, num_mask=num_freq_mask,
+                                       replace_with_zero=replace_with_zero) if apply_freq_mask else None
+        if apply_time_mask:
+            if time_mask_width_range is not None:
+                self.time_mask = MaskAlongAxis(dim="time", mask_width_range=time_mask_width_range, num_mask=num_time_mask, replace_with_zero=replace_with_zero)
+            elif time_mask_width_ratio_range is not None:
+                self.time_mask = MaskAlongAxisVariableMaxWidth(dim="time", mask_width_ratio_range=time_mask_width_ratio_range, num_mask=num_time_mask,
+                                                               replace_with_zero=replace_with_zero)
+            else:
+                raise ValueError('Either one of "time_mask_width_range" or "time_mask_width_ratio_range" should be used.')
+        else:
+            self.time_mask = None
+
+    def forward(self, x: Tensor, x_lengths: Optional[Tensor] = None):
+        if self.time_warp is not None:
+            x, x_lengths = self.time_warp(x, x_lengths)
+        if self.freq_mask is not None:
+            x, x_lengths = self.freq_mask(x, x_lengths)
+        if self.time_mask is not None:
+            x, x_lengths = self.time_mask(x, x_lengths)
+        return x, x_lengths

@@ -492,6 +492,58 @@ static inline unsigned grid_for(int64_t n_items, int per_block) {
   return (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_items + per_block - 1) / per_block, (int64_t)sm_count() * 16));
 }
 
+
+// ------------------------------------------------------------------------------------------------ SpecAug on log-mel
+// ESPnet SpecAug [upstream espnet2/asr/specaug/specaug.py, called at whisper_encoder.py:521-524]: bicubic time warp
+// (F.interpolate(mode="bicubic", align_corners=False) of the two segments left / right of a random centre; the mel axis
+// keeps its size, so its cubic taps collapse to the identity and only the time axis is interpolated), then frequency
+// masks, then time masks (masked_fill 0).  All random draws are made by the host with the reference's RNG call
+// sequence; the kernel applies them in one pass over the (B, 80, T) mel: read <= 4 taps, write once.
+__device__ __forceinline__ float cubic1(float x) { const float A = -0.75f; return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x) { const float A = -0.75f; return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+specaug_kernel(const T* __restrict__ in, T* __restrict__ out, int n_mel, int64_t t_in, int64_t t_out, const int32_t* __restrict__ warp,
+               const int32_t* __restrict__ fmask, int n_fmask, const int32_t* __restrict__ tmask, int n_tmask, int zero_tail) {
+  const int b = blockIdx.z, f = blockIdx.y;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t_out) return;
+  const T* row = in + ((int64_t)b * n_mel + f) * t_in;
+  // the row's length / warp parameters: warp[b] = {centre, warped, length}; centre <= 0 means "no warp for this item"
+  const int64_t len = warp ? warp[3 * b + 2] : t_in;
+  float v;
+  bool masked = false;
+  for (int i = 0; i < n_fmask; ++i) { const int p0 = fmask[(b * n_fmask + i) * 2], w = fmask[(b * n_fmask + i) * 2 + 1]; masked |= (f >= p0 && f < p0 + w); }
+  for (int i = 0; i < n_tmask; ++i) { const int p0 = tmask[(b * n_tmask + i) * 2], w = tmask[(b * n_tmask + i) * 2 + 1]; masked |= (t >= p0 && t < p0 + w); }
+  if (masked) {
+    v = 0.f;
+  } else if (t >= len) {
+    v = zero_tail ? 0.f : (t < t_in ? to_f32(row[t]) : 0.f);   // ragged batches: pad_list(ys, 0.0) behind each warped item
+  } else if (warp && warp[3 * b] > 0) {
+    const int64_t centre = warp[3 * b], warped = warp[3 * b + 1];
+    int64_t base, n_src, n_dst, td;
+    if (t < warped) { base = 0; n_src = centre; n_dst = warped; td = t; }
+    else { base = centre; n_src = len - centre; n_dst = len - warped; td = t - warped; }
+    const float scale = (float)n_src / (float)n_dst;
+    const float src = scale * ((float)td + 0.5f) - 0.5f;
+    const float fl = floorf(src);
+    const float fr = src - fl;
+    const int64_t i0 = (int64_t)fl;
+    const float w[4] = {cubic2(fr + 1.f), cubic1(fr), cubic1(1.f - fr), cubic2(2.f - fr)};
+    v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int64_t idx = i0 - 1 + k;
+      idx = idx < 0 ? 0 : (idx > n_src - 1 ? n_src - 1 : idx);
+      v = fmaf(w[k], to_f32(row[base + idx]), v);
+    }
+  } else {
+    v = to_f32(row[t]);
+  }
+  out[((int64_t)b * n_mel + f) * t_out + t] = from_f32<T>(v);
+}
+
 }  // namespace tsw
 
 using namespace tsw;
@@ -634,6 +686,17 @@ extern "C" int tsw_scale(const void* x, void* y, int dtype, int64_t n, float s_h
 extern "C" int tsw_add(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_ADD>(a, b, y, dtype, n, stream); }
 extern "C" int tsw_gelu_fwd(const void* x, void* y, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_GELU>(x, nullptr, y, dtype, n, stream); }
 extern "C" int tsw_gelu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_DGELU>(x, dy, dx, dtype, n, stream); }
+
+extern "C" int tsw_specaug_fwd(const void* in, void* out, int dtype, int64_t B, int64_t n_mel, int64_t t_in, int64_t t_out, const int32_t* warp,
+                               const int32_t* fmask, int n_fmask, const int32_t* tmask, int n_tmask, int zero_tail, tsw_stream_t stream) {
+  TSW_CHECK_ARG(in && out && in != out && B > 0 && n_mel > 0 && t_in > 0 && t_out > 0 && t_out <= t_in, "specaug_fwd: bad argument");
+  TSW_CHECK_ARG(n_fmask >= 0 && n_tmask >= 0 && (n_fmask == 0 || fmask) && (n_tmask == 0 || tmask), "specaug_fwd: mask arrays missing");
+  TSW_CHECK_ARG(B <= 65535 && n_mel <= 65535, "specaug_fwd: batch / mel count too large");
+  dim3 grid((unsigned)((t_out + 255) / 256), (unsigned)n_mel, (unsigned)B);
+  DISPATCH_T(dtype, (specaug_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)in, (T*)out, (int)n_mel, t_in, t_out, warp, fmask, n_fmask, tmask, n_tmask, zero_tail)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
 
 extern "C" int tsw_im2col_k3(const void* in, int dtype, int channels_first, int64_t B, int64_t C, int64_t Tin, int stride, void* out,
                              tsw_stream_t stream) {

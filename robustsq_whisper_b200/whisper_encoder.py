@@ -20,6 +20,7 @@ from . import kernels as K
 from . import whisper_model as W
 from ._compat import AbsEncoder, compute_dtype
 from .qformer_adapter import QFormerAdapter
+from .specaug import SpecAug
 
 
 class QFormerTgtSpkWhisperEncoder_V2(AbsEncoder):
@@ -42,12 +43,10 @@ class QFormerTgtSpkWhisperEncoder_V2(AbsEncoder):
         assert whisper_model in W.available_models(), whisper_model
         if dropout_rate != 0.0:
             raise NotImplementedError("dropout_rate > 0 is not on the B200 path (Whisper itself uses none, whisper_encoder.py:54)")
-        if use_specaug:
-            raise NotImplementedError("SpecAug on log-mel is a 'next' row of SURVEY.md §8f, not built yet")
         self.n_fft, self.win_length, self.hop_length, self.n_mels = W.N_FFT, W.N_FFT, W.HOP_LENGTH, W.N_MELS
         self.encoders = W.build_audio_encoder(whisper_model, download_dir)
         self.encoders.train()
-        self.specaug = None
+        self.specaug = SpecAug(**(specaug_conf or {})) if use_specaug else None   # whisper_encoder.py:66-69
         self.do_pad_trim = do_pad_trim
         self.pad_samples = W.N_SAMPLES
         self.kernel, self.padding, self.stride = 3, 1, 2
@@ -122,4 +121,6 @@ class QFormerTgtSpkWhisperEncoder_V2(AbsEncoder):
         dt = compute_dtype(self.compute_dtype)
         feats, feats_lens = self.log_mel_spectrogram(xs_pad, ilens, dt)
         enroll_feats, enroll_feats_lens = self.log_mel_spectrogram(enroll, enroll_lens, dt)
+        if self.specaug is not None and self.encoders.training:   # :521-524 (mixture only; the kernel works on (B, 80, T) directly)
+            feats, feats_lens = self.specaug.apply_channels_first(feats, feats_lens)
         return self.whisper_encode(feats, feats_lens, enroll_feats, enroll_feats_lens)

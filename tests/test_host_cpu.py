@@ -94,7 +94,12 @@ def test_unsupported_configurations_fail_loudly():
                                        encoder=None, postencoder=None, decoder=None, ctc=None, joint_network=None, ctc_weight=0.3)
     from robustsq_whisper_b200.whisper_encoder import QFormerTgtSpkWhisperEncoder_V2
     with pytest.raises(NotImplementedError):
+        QFormerTgtSpkWhisperEncoder_V2(whisper_model="tiny", dropout_rate=0.1)
+    with pytest.raises(ValueError):   # ESPnet's SpecAug refuses a time mask without a width; so does the plugin's
         QFormerTgtSpkWhisperEncoder_V2(whisper_model="tiny", use_specaug=True)
+    enc = QFormerTgtSpkWhisperEncoder_V2(whisper_model="tiny", use_specaug=True, specaug_conf=dict(time_mask_width_range=(0, 20)))
+    with pytest.raises(Exception):    # no CPU fallback for the augmentation kernel either
+        enc.specaug.apply_channels_first(torch.zeros(1, 80, 100), None)
 
 
 def _gloo_worker(rank, world, port_no, q):
