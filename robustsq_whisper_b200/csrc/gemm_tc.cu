@@ -318,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int64_t ld = Rp ? ep.ldres : ep.ldd;
           const int64_t boff = Rp ? (bon * p.r_so + bin * p.r_si) : (bon * p.d_so + bin * p.d_si);
           // 128 rows x (BN * sizeof(DT)) bytes = rows of BN*sizeof(DT)/128 lines; 256 epilogue threads share them
-          constexpr int kLinesPerRow = BN * (int)sizeof(DT) / 128;
+          constexpr int kLinesPerRow = BN * (int)sizeof(DT) / 128 > 0 ? BN * (int)sizeof(DT) / 128 : 1;
           const int et = (warp - 4) * 32 + lane;
           for (int i = et; i < TBM * kLinesPerRow; i += TC_EPI_WARPS * 32) {
             const int row = i / kLinesPerRow, line = i - row * kLinesPerRow;
@@ -519,8 +519,12 @@ int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st)
   const int64_t tiles_m = (g.M + TBM - 1) / TBM;
   static const bool no_cluster = getenv("TSW_GEMM_NO_CLUSTER") != nullptr;
   const bool pair = wide && !no_cluster && (tiles_m >= 8 || (tiles_m >= 2 && tiles_m % 2 == 0));
+  // decode-time GEMMs (a handful of token rows against a whole weight matrix) are weight streaming: one row of tiles, so
+  // 32-column tiles spread the N x K weight over 8x more CTAs (N = 1024: 32 CTAs pulling 64 KB each instead of 4 pulling 512 KB)
+  const bool skinny = tiles_m == 1 && !g.b_mn_major && g.N >= 256 && g.batch_inner * g.batch_outer == 1;
 #define TC_DISPATCH(DT)                                                                                   \
   do {                                                                                                    \
+    if (skinny) return generic ? tc_go<32, 8, DT, true, 1>(g, ep, st) : tc_go<32, 8, DT, false, 1>(g, ep, st);   \
     if (pair) return generic ? tc_go<256, 4, DT, true, 2>(g, ep, st) : tc_go<256, 4, DT, false, 2>(g, ep, st);  \
     if (wide) return generic ? tc_go<256, 4, DT, true, 1>(g, ep, st) : tc_go<256, 4, DT, false, 1>(g, ep, st);  \
     return generic ? tc_go<128, 6, DT, true, 1>(g, ep, st) : tc_go<128, 6, DT, false, 1>(g, ep, st);            \

@@ -19,6 +19,9 @@ def timed(fn):
     torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); return time.perf_counter() - t0, r
 dec.greedy_decode(mem, prompt, 50257, -1, 4)
 t_c, ids = timed(lambda: dec.greedy_decode(mem, prompt, 50257, -1, steps))
+dec.greedy_decode(mem, prompt, 50257, -1, 9, use_graph=True)
+t_g, ids_g = timed(lambda: dec.greedy_decode(mem, prompt, 50257, -1, steps, use_graph=True))
+same = bool((ids == ids_g).all())
 def ref_loop():
     ys = torch.full((n, 1), 50257, dtype=torch.long, device="cuda")
     for _ in range(ref_steps):
@@ -28,4 +31,5 @@ def ref_loop():
 ref_loop()
 t_r, _ = timed(ref_loop)
 print(f"{name} n={n}: KV-cached greedy {steps} tokens in {1e3*t_c:.1f} ms = {n*steps/t_c:.0f} tok/s ({1e3*t_c/steps:.2f} ms/step); "
+      f"as a CUDA graph {1e3*t_g:.1f} ms = {n*steps/t_g:.0f} tok/s ({1e3*t_g/steps:.2f} ms/step, ids equal: {same}); "
       f"full-prefix recompute {ref_steps} tokens in {1e3*t_r:.1f} ms = {n*ref_steps/t_r:.0f} tok/s ({1e3*t_r/ref_steps:.2f} ms/step)")
