@@ -107,7 +107,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
 //   ln_bwd_dgb_kernel    column reductions dgamma = sum_rows dy * xhat, dbeta = sum_rows dy (32 column groups x 8 row lanes per
 //                        CTA, the last CTA of a column block folds the row-chunk partials in a fixed order)
 template <typename T, int NC>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
                  const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx, int64_t rows, int d) {
   constexpr int VN = Vec<T>::N;
@@ -129,6 +129,14 @@ ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float*
     const bool more = row + stride < rows;
     if (more) load_row(row + stride, nx, nd);
     const float mu = mean[row], rs = rstd[row];
+    uint4 rr[NC];   // residual-branch gradient of this row: requested now, consumed after the two warp reductions
+    if (dres != nullptr) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nvec) rr[c] = ldg16(dres + row * d + (int64_t)i * VN);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
@@ -156,7 +164,7 @@ ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float*
         for (int j = 0; j < VN; ++j) o[j] = rs * (dv[j] * gv[j] - s1 - (xv[j] - mu) * rs * s2);
         if (dres != nullptr) {
           float r[VN];
-          unpack16<T>(ldg16(dres + row * d + (int64_t)i * VN), r);
+          unpack16<T>(rr[c], r);
 #pragma unroll
           for (int j = 0; j < VN; ++j) o[j] += r[j];
         }
@@ -182,7 +190,25 @@ ln_bwd_dgb_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float
 #pragma unroll
   for (int j = 0; j < VN; ++j) ag[j] = ab[j] = 0.f;
   if (c0 < d) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {   // four rows per lane and trip: eight 16-byte loads in flight per thread
+      uint4 xr[4], dr[4];
+      float mu[4], rs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xr[u] = ldg16(x + (r + 8 * u) * d + c0);
+        dr[u] = ldg16(dy + (r + 8 * u) * d + c0);
+        mu[u] = __ldg(mean + r + 8 * u); rs[u] = __ldg(rstd + r + 8 * u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xv[VN], dv[VN];
+        unpack16<T>(xr[u], xv); unpack16<T>(dr[u], dv);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { ag[j] = fmaf(dv[j], (xv[j] - mu[u]) * rs[u], ag[j]); ab[j] += dv[j]; }
+      }
+    }
+    for (; r < r1; r += 8) {
       float xv[VN], dv[VN];
       Vec<T>::load(x + r * d + c0, xv);
       Vec<T>::load(dy + r * d + c0, dv);
@@ -252,12 +278,17 @@ colsum_partial_kernel(const T* __restrict__ x, int64_t rows, int64_t n, int64_t 
   if (c0 < n) {
     if (vec_ok && c0 + VN <= n) {
       int64_t r = r0 + ty;
-      for (; r + 8 < r1; r += 16) {  // two independent loads in flight
-        float a[VN], b[VN];
-        Vec<T>::load(x + r * ld + c0, a);
-        Vec<T>::load(x + (r + 8) * ld + c0, b);
+      for (; r + 56 < r1; r += 64) {  // eight independent 16-byte loads in flight per thread
+        uint4 v[8];
 #pragma unroll
-        for (int j = 0; j < VN; ++j) acc[j] += a[j] + b[j];
+        for (int u = 0; u < 8; ++u) v[u] = ldg16(x + (r + 8 * u) * ld + c0);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float a[VN];
+          unpack16<T>(v[u], a);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) acc[j] += a[j];
+        }
       }
       for (; r < r1; r += 8) {
         float a[VN];
@@ -596,7 +627,7 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!dres || aligned16(dres)), "layernorm_bwd: pointers must be 16-byte aligned");
   if (!workspace || workspace_bytes < tsw_layernorm_bwd_workspace_bytes(rows, d)) { set_error("layernorm_bwd: workspace too small"); return TSW_E_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
-  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 3);
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 2);
   const int nc = (int)((d / vn + 31) / 32);
   DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (ln_bwd_dx_kernel<T, NC><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d))));
   TSW_LAUNCH_CHECK();
