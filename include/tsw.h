@@ -62,6 +62,13 @@ size_t tsw_logmel_workspace_bytes(int64_t batch, int64_t n_samples, int out_dtyp
  * n_frames = n_samples / 160 (the last STFT frame is dropped, whisper_encoder.py:111). */
 int tsw_logmel_fwd(const float* audio, int64_t batch, int64_t n_samples, int64_t ld_audio, void* out, int out_dtype,
                    void* workspace, size_t workspace_bytes, tsw_stream_t stream);
+/* Same transform over windows gathered from a device-resident waveform bank (the training recipe's
+ * "crop10" — a random <= 10 s crop of a randomly chosen same-speaker enrollment utterance, done by ESPnet's preprocessor on
+ * the CPU and shipped over PCIe each step, datapre/create_enrollment_scp.py:76-78 "*utt spk").  Item b is the n_samples-long
+ * signal bank[item_off[b] + t] for t < item_len[b], zero beyond (crop + collate padding that never exists in memory); STFT
+ * reflection is taken at the window's own ends.  Workspace as tsw_logmel_workspace_bytes(batch, n_samples, out_dtype). */
+int tsw_logmel_gather_fwd(const float* bank, const int64_t* item_off, const int32_t* item_len, int64_t batch, int64_t n_samples,
+                          void* out, int out_dtype, void* workspace, size_t workspace_bytes, tsw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ K5 GEMM
  * Replaces every cuBLAS GEMM the reference reaches through nn.Linear / matmul / conv1d on the path

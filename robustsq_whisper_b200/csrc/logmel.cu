@@ -93,13 +93,17 @@ __device__ __forceinline__ void bulk_load_span(void* smem_dst, const void* gsrc,
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_frames_kernel(const float* __restrict__ audio, int64_t n_samples, int64_t ld_audio, int n_frames,
-                     OutT* __restrict__ out, float* __restrict__ raw, unsigned int* __restrict__ umax) {
+                     OutT* __restrict__ out, float* __restrict__ raw, unsigned int* __restrict__ umax,
+                     const int64_t* __restrict__ item_off, const int32_t* __restrict__ item_len) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LogmelSmem& s = *reinterpret_cast<LogmelSmem*>(smem_raw);
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * kFPB;
-  const float* a = audio + (int64_t)b * ld_audio;
+  // gather mode (tsw_logmel_gather_fwd): item b is the n_samples-long window that starts item_off[b] elements into a
+  // waveform bank, valid for item_len[b] samples and zero beyond — a crop + pad that never exists in memory
+  const float* a = item_off ? audio + item_off[b] : audio + (int64_t)b * ld_audio;
+  const int64_t n_valid = item_len ? min((int64_t)item_len[b], n_samples) : n_samples;
 
   // stage the shared segment: padded index p = 160*t0 + j  <->  sample p - 200, reflected at both ends
   const int64_t base = (int64_t)t0 * kHop - kHalf;
@@ -107,8 +111,9 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t n_samples, int64_t
   const int need = kHop * (nf_here - 1) + kNfft;
   // interior CTAs (no reflection, full tile, 16-byte aligned rows): the whole 21 KB segment arrives by ONE bulk copy
   // instead of 21 dependent load -> store rounds per thread (which were half of this kernel's time)
-  const bool bulk = base >= 0 && base + kSeg <= n_samples && nf_here == kFPB && (ld_audio & 3) == 0 &&
-                    (reinterpret_cast<uintptr_t>(audio) & 15u) == 0;
+  const bool bulk = base >= 0 && base + kSeg <= n_valid && nf_here == kFPB &&
+                    (item_off ? (reinterpret_cast<uintptr_t>(a) & 15u) == 0
+                              : ((ld_audio & 3) == 0 && (reinterpret_cast<uintptr_t>(audio) & 15u) == 0));
   if (bulk) {
     if (tid == 0) { mbar_init(&s.bar, 1); fence_barrier_init(); }
     __syncthreads();
@@ -127,7 +132,7 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t n_samples, int64_t
         int64_t i = base + j;
         if (i < 0) i = -i;
         if (i >= n_samples) i = 2 * (n_samples - 1) - i;
-        v = a[i];
+        v = i < n_valid ? a[i] : 0.f;
       }
       s.seg[j] = v;
     }
@@ -263,7 +268,7 @@ extern "C" size_t tsw_logmel_workspace_bytes(int64_t batch, int64_t n_samples, i
 
 template <typename OutT>
 static int logmel_launch(const float* audio, int64_t B, int64_t N, int64_t ld, OutT* out, float* raw, unsigned int* umax,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int64_t* item_off = nullptr, const int32_t* item_len = nullptr) {
   const int T = (int)(N / kHop);
   static bool attr_set[2] = {false, false};
   const size_t smem = sizeof(LogmelSmem);
@@ -274,7 +279,7 @@ static int logmel_launch(const float* audio, int64_t B, int64_t N, int64_t ld, O
   }
   TSW_CUDA(cudaMemsetAsync(umax, 0, sizeof(unsigned int) * B, st));
   dim3 grid((T + kFPB - 1) / kFPB, (unsigned)B);
-  logmel_frames_kernel<OutT><<<grid, kThreads, smem, st>>>(audio, N, ld, T, out, raw, umax);
+  logmel_frames_kernel<OutT><<<grid, kThreads, smem, st>>>(audio, N, ld, T, out, raw, umax, item_off, item_len);
   TSW_LAUNCH_CHECK();
   const int64_t per_utt = (int64_t)kMels * T;
   dim3 g2((unsigned)std::min<int64_t>((per_utt + 255) / 256, 148 * 4), (unsigned)B);
@@ -304,5 +309,27 @@ extern "C" int tsw_logmel_fwd(const float* audio, int64_t batch, int64_t n_sampl
     return logmel_launch<__nv_bfloat16>(audio, batch, n_samples, ld_audio, (__nv_bfloat16*)out, raw, umax, st);
   }
   set_error("logmel_fwd: bad out_dtype %d", out_dtype);
+  return TSW_E_INVALID;
+}
+
+extern "C" int tsw_logmel_gather_fwd(const float* bank, const int64_t* item_off, const int32_t* item_len, int64_t batch, int64_t n_samples,
+                                     void* out, int out_dtype, void* workspace, size_t workspace_bytes, tsw_stream_t stream) {
+  int dev = 0;
+  TSW_CUDA(cudaGetDevice(&dev));
+  TSW_CHECK_ARG(dev < 64 && g_inited[dev], "logmel_gather_fwd: tsw_logmel_init has not been called on device %d", dev);
+  TSW_CHECK_ARG(bank && item_off && item_len && out && batch > 0 && batch <= 65535, "logmel_gather_fwd: bad pointers/batch");
+  TSW_CHECK_ARG(n_samples >= kNfft, "logmel_gather_fwd: n_samples (%lld) must be >= 400", (long long)n_samples);
+  const int64_t T = n_samples / kHop;
+  const size_t head = logmel_ws_head(batch);
+  size_t need = head + (out_dtype == TSW_BF16 ? sizeof(float) * (size_t)(batch * kMels * T) : 0);
+  if (!workspace || workspace_bytes < need) { set_error("logmel_gather_fwd: workspace %zu < %zu", workspace_bytes, need); return TSW_E_WORKSPACE; }
+  unsigned int* umax = reinterpret_cast<unsigned int*>(workspace);
+  cudaStream_t st = as_stream(stream);
+  if (out_dtype == TSW_F32) return logmel_launch<float>(bank, batch, n_samples, 0, (float*)out, (float*)out, umax, st, item_off, item_len);
+  if (out_dtype == TSW_BF16) {
+    float* raw = reinterpret_cast<float*>((char*)workspace + head);
+    return logmel_launch<__nv_bfloat16>(bank, batch, n_samples, 0, (__nv_bfloat16*)out, raw, umax, st, item_off, item_len);
+  }
+  set_error("logmel_gather_fwd: bad out_dtype %d", out_dtype);
   return TSW_E_INVALID;
 }

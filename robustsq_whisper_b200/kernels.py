@@ -81,6 +81,31 @@ def logmel(audio: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
     return out
 
 
+def logmel_gather(bank: Tensor, item_off: Tensor, item_len: Tensor, n_samples: int, out_dtype: torch.dtype = torch.float32) -> Tensor:
+    """log-mel of B windows gathered from a device-resident fp32 waveform bank (tsw_logmel_gather_fwd): window b =
+    bank[item_off[b] : item_off[b] + item_len[b]] zero-padded to n_samples.  -> (B, 80, n_samples // 160)."""
+    require_cuda(bank, item_off, item_len)
+    lib = _C.load()
+    if bank.dtype != torch.float32 or bank.dim() != 1 or not bank.is_contiguous():
+        raise _C.TswError("logmel_gather: the bank must be a contiguous 1-D float32 tensor")
+    if item_off.dtype != torch.int64 or item_len.dtype != torch.int32 or item_off.shape != item_len.shape:
+        raise _C.TswError("logmel_gather: item_off int64 / item_len int32 of one shape")
+    dev = bank.device.index or 0
+    if dev not in _logmel_ready:
+        fb = whisper_mel_filterbank()
+        with torch.cuda.device(bank.device):
+            check(lib.tsw_logmel_init(fb.ctypes.data_as(ctypes.c_void_p), 80, 201), "tsw_logmel_init")
+        _logmel_ready.add(dev)
+    B = item_off.numel()
+    out = torch.empty((B, 80, n_samples // 160), dtype=out_dtype, device=bank.device)
+    code = dtype_code(out_dtype)
+    ws = _ws(lib.tsw_logmel_workspace_bytes(B, n_samples, code), bank.device)
+    check(lib.tsw_logmel_gather_fwd(ptr(bank), ptr(item_off.contiguous()), ptr(item_len.contiguous()), B, n_samples, ptr(out), code, ptr(ws),
+                                    ws.numel(), stream()), "tsw_logmel_gather_fwd")
+    _count(2)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------- K5 GEMM
 def gemm(
     a: Tensor, b: Tensor, *, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,

@@ -120,7 +120,10 @@ class QFormerTgtSpkWhisperEncoder_V2(AbsEncoder):
             xs_pad = self.pad_or_trim(xs_pad, self.pad_samples)
         dt = compute_dtype(self.compute_dtype)
         feats, feats_lens = self.log_mel_spectrogram(xs_pad, ilens, dt)
-        enroll_feats, enroll_feats_lens = self.log_mel_spectrogram(enroll, enroll_lens, dt)
+        if hasattr(enroll, "log_mel"):   # an EnrollmentBank: ``enroll_lens`` = (bank offsets, window lengths) of this batch's picks
+            enroll_feats, enroll_feats_lens = enroll.log_mel(enroll_lens[0], enroll_lens[1], dt)
+        else:
+            enroll_feats, enroll_feats_lens = self.log_mel_spectrogram(enroll, enroll_lens, dt)
         if self.specaug is not None and self.encoders.training:   # :521-524 (mixture only; the kernel works on (B, 80, T) directly)
             feats, feats_lens = self.specaug.apply_channels_first(feats, feats_lens)
         return self.whisper_encode(feats, feats_lens, enroll_feats, enroll_feats_lens)
