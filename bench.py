@@ -208,6 +208,7 @@ def run_b200(args):
 
     graphed = None
     if args.graph:
+        model.encoder.qformer.eval()   # dropout masks are host-keyed: not capturable (robustsq_whisper_b200.graph)
         # the step geometry is fixed: capture forward + backward (+ the overlapped gradient all-reduce) once, replay per step
         from robustsq_whisper_b200.graph import GraphedTrainStep
         ex = {k: v.to(dev) for k, v in pinned.items()}
@@ -306,7 +307,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"whisper-{args.model} TS-ASR training step (fwd+bwd), {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment, "
-                                   f"q=16, SQ-Former L=2, K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE"
+                                   f"q=16, SQ-Former L=2 (dropout 0.1 {'off' if args.graph else 'on'}), K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE"
                                    + (f", LoRA q/k/v/o r={args.lora} on the Whisper blocks with the base frozen" if args.lora > 0 else ""),
                        "launch": "eager (one launch per kernel)" if graphed is None else "one CUDA graph per step (forward + backward + gradient all-reduce), host-side utt-id parsing / negative sampling outside it",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",

@@ -142,6 +142,11 @@ int tsw_add(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_str
 int tsw_gelu_fwd(const void* x, void* y, int dtype, int64_t n, tsw_stream_t stream);
 int tsw_gelu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, tsw_stream_t stream);
 
+/* nn.Dropout of the SQ-Former in training mode (Qformer.py:86,237,266,353): y[i] = keep(i) ? x[i] / (1 - p) : 0 with
+ * keep(i) = word (i & 3) of Philox4x32-10(counter = (i >> 2, offset), key = seed) >= p * 2^32.  Re-applying the call with the
+ * same (seed, offset) to the output gradient is the backward pass; y may alias x. */
+int tsw_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, tsw_stream_t stream);
+
 /* SpecAug on the mixture log-mel (whisper_encoder.py:521-524 -> ESPnet SpecAug [upstream]): time warp, frequency masks,
  * time masks in one pass.  in (B, n_mel, t_in) -> out (B, n_mel, t_out), t_out <= t_in (ESPnet re-pads a ragged batch to its
  * longest item).  warp (B, 3) int32 = {centre, warped, length} per item or NULL: frames [0, warped) are the bicubic

@@ -8,8 +8,9 @@ self-attention over all tokens with a key-padding mask, cross-attention from the
 (key-padding mask), separate GELU FFNs for the query rows and the enrollment rows, every sub-block closed by
 LN(x + residual) with eps 1e-12.  The additive masks of the reference ((1-m)*-10000 and (1-m)*finfo.min) underflow
 to exactly zero probability in fp32, so they are applied as key lengths inside the softmax kernel.
-Not reproduced: dropout 0.1 of BertConfig in training mode (parity runs use p = 0) and the LM/MLM
-heads' forward (never called on this path) — the dead ``cls`` head is kept as frozen parameters for checkpoint keys.
+Dropout 0.1 of BertConfig is applied in training mode at the reference's four sites (:86, :237, :266, :353) with a
+counter-based mask (tsw_dropout; the attention-probability site takes the unfused attention path); parity runs put the
+SQ-Former in eval().  Not reproduced: the LM/MLM heads' forward (never called on this path) — the dead ``cls`` head is kept as frozen parameters for checkpoint keys.
 """
 from __future__ import annotations
 
@@ -102,22 +103,24 @@ class BertEncoder(nn.Module):
         self.layer = nn.ModuleList([BertLayer(cfg, i) for i in range(cfg.num_hidden_layers)])
 
 
-def _attention_block(p: _AttnParams, hidden: Tensor, n_head: int, key_len: Optional[Tensor], kv: Optional[Tensor] = None) -> Tensor:
-    """BertSelfAttention + BertSelfOutput (Qformer.py:148-268)."""
+def _attention_block(p: _AttnParams, hidden: Tensor, n_head: int, key_len: Optional[Tensor], kv: Optional[Tensor] = None,
+                     drop: tuple = (0.0, 0.0, False)) -> Tensor:
+    """BertSelfAttention + BertSelfOutput (Qformer.py:148-268).  drop = (hidden p, attention p, training)."""
     src = hidden if kv is None else kv
     q = F.linear(hidden, p.self.query.weight, p.self.query.bias)
     k = F.linear(src, p.self.key.weight, p.self.key.bias)
     v = F.linear(src, p.self.value.weight, p.self.value.bias)
     dh = q.shape[-1] // n_head
-    ctx = F.attention(q, k, v, n_head, dh ** -0.5, key_len=key_len)
-    out = F.linear(ctx, p.output.dense.weight, p.output.dense.bias)
+    ctx = F.attention(q, k, v, n_head, dh ** -0.5, key_len=key_len, dropout_p=drop[1], training=drop[2])      # :237
+    out = F.dropout(F.linear(ctx, p.output.dense.weight, p.output.dense.bias), drop[0], drop[2])                # :265-266
     ln = p.output.LayerNorm
     return F.layernorm(out, ln.weight, ln.bias, ln.eps, res=hidden)
 
 
-def _ffn(inter: _InterParams, outp: _OutParams, x: Tensor) -> Tensor:
+def _ffn(inter: _InterParams, outp: _OutParams, x: Tensor, drop: tuple = (0.0, 0.0, False)) -> Tensor:
     """BertIntermediate + BertOutput (Qformer.py:329-355)."""
     y = F.mlp(x, inter.dense.weight, inter.dense.bias, outp.dense.weight, outp.dense.bias, residual=None)
+    y = F.dropout(y, drop[0], drop[2])                                                                           # :353
     return F.layernorm(y, outp.LayerNorm.weight, outp.LayerNorm.bias, outp.LayerNorm.eps, res=x)
 
 
@@ -148,6 +151,8 @@ class BertModel(nn.Module):
         e = F.linear_pos(input_ids, emb.word_embeddings.weight, emb.word_embeddings.bias, pos, rows_per)
         h = torch.cat([query_embeds.to(dt), e], dim=1)
         h = F.layernorm(h, emb.LayerNorm.weight, emb.LayerNorm.bias, emb.LayerNorm.eps)
+        drop = (float(cfg.hidden_dropout_prob), float(cfg.attention_probs_dropout_prob), bool(self.training))
+        h = F.dropout(h, drop[0], drop[2])                                                                       # :86
         if key_lens is None:
             key_lens = attention_mask.to(torch.int32).sum(dim=1).to(torch.int32) if attention_mask is not None else None
         if encoder_key_lens is None:
@@ -155,13 +160,13 @@ class BertModel(nn.Module):
                                 if encoder_attention_mask is not None else None)
         nh = cfg.num_attention_heads
         for layer in self.encoder.layer:
-            a = _attention_block(layer.attention, h, nh, key_lens)
+            a = _attention_block(layer.attention, h, nh, key_lens, drop=drop)
             qa = a[:, :q].contiguous()
             if layer.has_cross_attention:
-                qa = _attention_block(layer.crossattention, qa, nh, encoder_key_lens, kv=encoder_hidden_states)
-            out_q = _ffn(layer.intermediate_query, layer.output_query, qa)
+                qa = _attention_block(layer.crossattention, qa, nh, encoder_key_lens, kv=encoder_hidden_states, drop=drop)
+            out_q = _ffn(layer.intermediate_query, layer.output_query, qa, drop)
             if a.shape[1] > q:
-                out_e = _ffn(layer.intermediate, layer.output, a[:, q:].contiguous())
+                out_e = _ffn(layer.intermediate, layer.output, a[:, q:].contiguous(), drop)
                 h = torch.cat([out_q, out_e], dim=1)
             else:
                 h = out_q

@@ -53,6 +53,7 @@ SIGNATURES = {
     "tsw_logmel_workspace_bytes": (_SZ, [_I64, _I64, _I]),
     "tsw_logmel_fwd": (c_int, [_P, _I64, _I64, _I64, _P, _I, _P, _SZ, _P]),
     "tsw_logmel_gather_fwd": (c_int, [_P, _P, _P, _I64, _I64, _P, _I, _P, _SZ, _P]),
+    "tsw_dropout": (c_int, [_P, _P, _I, _I64, _F, ctypes.c_uint64, ctypes.c_uint64, _P]),
     "tsw_specaug_fwd": (c_int, [_P, _P, _I, _I64, _I64, _I64, _I64, _P, _P, _I, _P, _I, _I, _P]),
     "tsw_gemm_workspace_bytes": (_SZ, [POINTER(GemmDesc)]),
     "tsw_gemm": (c_int, [POINTER(GemmDesc), _P, _SZ, _P]),

@@ -3,7 +3,7 @@
 // kernels with warp-shuffle reductions; grids are sized in multiples of the SM count where the work allows.
 #include <algorithm>
 
-#include "common.cuh"
+#include "gemm_common.cuh"   // common.cuh + the 4-element load4 / store4 helpers
 
 namespace tsw {
 
@@ -575,6 +575,42 @@ specaug_kernel(const T* __restrict__ in, T* __restrict__ out, int n_mel, int64_t
   out[((int64_t)b * n_mel + f) * t_out + t] = from_f32<T>(v);
 }
 
+// ------------------------------------------------------------------------------------------------ dropout (SQ-Former)
+// nn.Dropout of the Q-Former in training mode (Qformer.py:86,237,266,353; p = 0.1).  Counter-based: element i keeps its
+// value iff word (i & 3) of Philox4x32-10(counter = (i >> 2, offset), key = seed) >= p * 2^32, scaled by 1 / (1 - p).  The
+// mask is a pure function of (seed, offset, i), so backward re-applies the same call to the gradient: no mask in HBM.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, uint32_t threshold, float inv_keep, uint64_t seed, uint64_t offset) {
+  const int64_t n4 = (n + 3) >> 2;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    const int64_t i0 = g << 2;
+    if (i0 + 4 <= n) {
+      float v[4];
+      load4(x + i0, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = rr[j] >= threshold ? v[j] * inv_keep : 0.f;
+      store4(y + i0, v);
+    } else {
+      for (int j = 0; j < 4 && i0 + j < n; ++j) y[i0 + j] = from_f32<T>(rr[j] >= threshold ? to_f32(x[i0 + j]) * inv_keep : 0.f);
+    }
+  }
+}
+
 }  // namespace tsw
 
 using namespace tsw;
@@ -717,6 +753,19 @@ extern "C" int tsw_scale(const void* x, void* y, int dtype, int64_t n, float s_h
 extern "C" int tsw_add(const void* a, const void* b, void* y, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_ADD>(a, b, y, dtype, n, stream); }
 extern "C" int tsw_gelu_fwd(const void* x, void* y, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_GELU>(x, nullptr, y, dtype, n, stream); }
 extern "C" int tsw_gelu_bwd(const void* x, const void* dy, void* dx, int dtype, int64_t n, tsw_stream_t stream) { return ew_launch<EW_DGELU>(x, dy, dx, dtype, n, stream); }
+
+extern "C" int tsw_dropout(const void* x, void* y, int dtype, int64_t n, float p, uint64_t seed, uint64_t offset, tsw_stream_t stream) {
+  TSW_CHECK_ARG(x && y && n >= 0 && p >= 0.f && p < 1.f, "dropout: bad argument (p must be in [0, 1))");
+  if (n == 0) return TSW_OK;
+  const int al = dtype == TSW_F32 ? 15 : 7;
+  TSW_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & al) == 0, "dropout: pointers must be aligned for 4-element accesses");
+  const double th = (double)p * 4294967296.0;
+  const uint32_t threshold = th >= 4294967295.0 ? 4294967295u : (uint32_t)th;
+  const unsigned grid = grid_for((n + 3) / 4, 256);
+  DISPATCH_T(dtype, (dropout_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (T*)y, n, threshold, 1.f / (1.f - p), seed, offset)));
+  TSW_LAUNCH_CHECK();
+  return TSW_OK;
+}
 
 extern "C" int tsw_specaug_fwd(const void* in, void* out, int dtype, int64_t B, int64_t n_mel, int64_t t_in, int64_t t_out, const int32_t* warp,
                                const int32_t* fmask, int n_fmask, const int32_t* tmask, int n_tmask, int zero_tail, tsw_stream_t stream) {

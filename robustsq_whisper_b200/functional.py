@@ -240,6 +240,37 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, res: Op
     return _LayerNorm.apply(x, gamma, beta, eps, res)
 
 
+# ------------------------------------------------------------------------------------------------ dropout (SQ-Former)
+def next_dropout_key() -> Tuple[int, int]:
+    """(seed, offset) of the next dropout mask: a fresh 63-bit seed from torch's CPU generator per call, so that
+    ``torch.manual_seed`` makes a run reproducible (like nn.Dropout) and every call site gets its own mask; offset 0."""
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    return seed, 0
+
+
+class _Dropout(Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, p: float, seed: int, offset: int):
+        ctx.key = (p, seed, offset)
+        return K.dropout(x, p, seed, offset)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        p, seed, offset = ctx.key
+        return K.dropout(dy, p, seed, offset), None, None, None
+
+
+def dropout(x: Tensor, p: float, training: bool) -> Tensor:
+    """nn.Dropout (Qformer.py:86,266,353): identity unless training with p > 0."""
+    if not training or p <= 0.0:
+        return x
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("dropout masks are keyed by host-drawn seeds: a captured graph would replay one mask (put the SQ-Former in eval() "
+                           "for GraphedTrainStep, or run the eager step)")
+    seed, offset = next_dropout_key()
+    return _Dropout.apply(x, p, seed, offset)
+
+
 # ------------------------------------------------------------------------------------------------ residual add
 class _Add(Function):
     @staticmethod
@@ -280,7 +311,8 @@ class _Attention(Function):
     mask: key padding (key_len per batch item) and/or causal.  Probabilities are kept (compute dtype) for backward."""
 
     @staticmethod
-    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor], causal: bool):
+    def forward(ctx, q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor], causal: bool,
+                drop: Optional[Tuple[float, int, int]] = None):
         B, Sq, d = q.shape
         Sk = k.shape[1]
         dh = d // n_head
@@ -295,10 +327,12 @@ class _Attention(Function):
                out=p, ldd=Skp, d_strides=(n_head * Sq * Skp, Sq * Skp), impl=impl)
         K.softmax_fwd(p, B, n_head, Sq, Sk, scale, key_len=key_len, causal=1 if causal else 0, ld=Skp)
         o = torch.empty((B, Sq, d), dtype=dt, device=q.device)
-        K.gemm(p, v, M=Sq, N=dh, K=Sk, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=(n_head * Sq * Skp, Sq * Skp),
+        # attention-probability dropout (Qformer.py:237): the dropped copy feeds P V, the clean P is kept for the softmax backward
+        pd = p if drop is None else K.dropout(p, *drop)
+        K.gemm(pd, v, M=Sq, N=dh, K=Sk, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=(n_head * Sq * Skp, Sq * Skp),
                b_strides=(Sk * d, dh), out=o, ldd=d, d_strides=(Sq * d, dh), impl=impl)
         ctx.save_for_backward(q, k, v, p)
-        ctx.n_head, ctx.scale = n_head, scale
+        ctx.n_head, ctx.scale, ctx.drop = n_head, scale, drop
         return o
 
     @staticmethod
@@ -314,14 +348,19 @@ class _Attention(Function):
         do = do.contiguous()
         bs_p = (n_head * Sq * Skp, Sq * Skp)
         dv = torch.empty_like(v)
+        drop = ctx.drop
+        pd = p if drop is None else K.dropout(p, *drop)   # the mask is a function of (seed, offset): regenerated, not stored
         # dV = P^T dO : A = P stored [Sq][Skp] (MN-major for an (Sk x Sq) operand), B = dO stored [Sq][dh] (MN-major)
-        K.gemm(p, do, M=Sk, N=dh, K=Sq, a_mn=True, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sq * d, dh),
+        K.gemm(pd, do, M=Sk, N=dh, K=Sq, a_mn=True, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sq * d, dh),
                out=dv, ldd=d, d_strides=(Sk * d, dh), impl=impl)
         dp = torch.empty_like(p)
         if Skp != Sk:
             dp[..., Sk:].zero_()
         K.gemm(do, v, M=Sq, N=Sk, K=dh, lda=d, ldb=d, batch=(B, n_head), a_strides=(Sq * d, dh), b_strides=(Sk * d, dh),
                out=dp, ldd=Skp, d_strides=bs_p, impl=impl)
+        del pd
+        if drop is not None:
+            K.dropout(dp, *drop, out=dp)   # gradient through the dropout: same mask, same 1 / (1 - p)
         K.softmax_bwd(p, dp, B * n_head * Sq, Sk, scale, ld=Skp)  # dp <- dS (in place)
         dq = torch.empty_like(q)
         K.gemm(dp, k, M=Sq, N=dh, K=Sk, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sk * d, dh),
@@ -329,7 +368,7 @@ class _Attention(Function):
         dk = torch.empty_like(k)
         K.gemm(dp, q, M=Sk, N=dh, K=Sq, a_mn=True, lda=Skp, b_mn=True, ldb=d, batch=(B, n_head), a_strides=bs_p, b_strides=(Sq * d, dh),
                out=dk, ldd=d, d_strides=(Sk * d, dh), impl=impl)
-        return dq, dk, dv, None, None, None, None
+        return dq, dk, dv, None, None, None, None, None
 
 
 class _FusedAttention(Function):
@@ -441,10 +480,17 @@ def cross_attention_packed(q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Te
     return _PackedCrossAttention.apply(q, xa, wk, wv, bv, n_head, scale)
 
 
-def attention(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False) -> Tensor:
+def attention(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False,
+              dropout_p: float = 0.0, training: bool = False) -> Tensor:
+    """``dropout_p`` (with ``training``): dropout on the attention probabilities (BertSelfAttention, Qformer.py:237) — that path
+    materialises P (GEMM -> softmax -> dropout -> GEMM); the SQ-Former's two layers are ~2 % of the step's attention work."""
+    if training and dropout_p > 0.0:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("attention dropout is keyed by host-drawn seeds and cannot be captured into a CUDA graph")
+        return _Attention.apply(q, k, v, n_head, scale, key_len, causal, (dropout_p,) + next_dropout_key())
     if q.dtype == torch.bfloat16 and q.shape[-1] == n_head * 64:
         return _FusedAttention.apply(q, k, v, n_head, scale, key_len, causal)
-    return _Attention.apply(q, k, v, n_head, scale, key_len, causal)
+    return _Attention.apply(q, k, v, n_head, scale, key_len, causal, None)
 
 
 # ------------------------------------------------------------------------------------------------ conv stem (k=3, pad=1) as im2col + GEMM

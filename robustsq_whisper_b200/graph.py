@@ -37,6 +37,10 @@ class GraphedTrainStep:
         if dev.type != "cuda":
             raise RuntimeError("GraphedTrainStep needs the model on a CUDA device")
         self.device = dev
+        qf = getattr(model.encoder, "qformer", None)
+        if qf is not None and qf.training and (qf.qformer.config.hidden_dropout_prob > 0 or qf.qformer.config.attention_probs_dropout_prob > 0):
+            raise RuntimeError("GraphedTrainStep: the SQ-Former's dropout masks are keyed by host-drawn seeds and a graph would replay one "
+                               "mask forever; call model.encoder.qformer.eval() (no dropout) or use the eager step")
         self.static: Dict[str, Tensor] = {k: example[k].to(dev).clone() for k in _TENSOR_KEYS}
         self._pristine_text = self.static["text"].clone()   # forward rewrites -1 -> ignore_id in place (:557)
         B = self.static["speech"].shape[0]

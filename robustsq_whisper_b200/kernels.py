@@ -232,6 +232,18 @@ def colsum(x: Tensor, rows: int, n: int, ld: Optional[int] = None) -> Tensor:
     return out
 
 
+def dropout(x: Tensor, p: float, seed: int, offset: int, out: Optional[Tensor] = None) -> Tensor:
+    """y = x * keep / (1 - p) with the counter-based mask of tsw_dropout; the same (seed, offset) on the gradient is backward."""
+    require_cuda(x, out)
+    lib = _C.load()
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.tsw_dropout(ptr(x), ptr(out), dtype_code(x.dtype), x.numel(), float(p), int(seed), int(offset), stream()), "tsw_dropout")
+    _count(1)
+    return out
+
+
 def scale(x: Tensor, s_host: float = 1.0, s_dev: Optional[Tensor] = None, inplace: bool = False) -> Tensor:
     """y = x * s_host * s_dev (device scalar, e.g. the upstream loss gradient) without a host sync."""
     lib = _C.load()

@@ -27,6 +27,7 @@ def build_model(name, weight_seed=0, dtype=torch.float32, **kw):
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not unexpected and all(".cls." in k for k in missing)
     m = m.cuda()
+    m.encoder.qformer.eval()   # parity runs: BertConfig's dropout 0.1 off (the reference fixture was produced the same way)
     m.encoder.compute_dtype = dtype
     m.decoder.compute_dtype = dtype
     return m, cfg, sd
