@@ -181,12 +181,13 @@ class QFormerTgtSpkWhisperDecoder_V2(AbsDecoder, BatchScorerInterface):
 
     @torch.no_grad()
     def greedy_decode(self, memory: Tensor, spk_prompt: Tensor, sos: int, eos: int, max_len: int, ys0: Optional[Tensor] = None,
-                      use_graph: bool = False) -> Tensor:
+                      use_graph: bool = True) -> Tensor:
         """beam-1 decoding of a batch of utterances with the KV caches: -> (n, <= max_len) token ids (sos excluded);
         rows that have emitted ``eos`` keep emitting it.  One host sync per 8 tokens (the all-finished check).  With
         ``use_graph`` the per-token step (~270 launches of n-row kernels) is captured once as a CUDA graph and replayed:
-        position and cache length are device scalars the graph increments itself.  Measured on B200 (medium, n = 32): the
-        step is GPU-bound either way (~9 ms: the n-row GEMMs occupy 4-16 SMs each), so the graph is off by default."""
+        position and cache length are device scalars the graph increments itself.  Measured on B200 (medium, bf16): the
+        step's kernels take 3.2 ms at n = 32 while launching them one by one from Python takes 8.4 ms, so the graph is on
+        by default (n = 32: 3.9 ms / token = 8.2 k tok/s; n = 128: 6.8 ms = 18.8 k tok/s; token ids identical to eager)."""
         n = memory.size(0)
         ys = ys0 if ys0 is not None else torch.full((n, 1), sos, dtype=torch.long, device=memory.device)
         logp, cache = self.decode_prefill(ys, memory, spk_prompt, max_new_tokens=max_len)
