@@ -109,6 +109,11 @@ typedef struct {
    * dx = dy W + (dy s B) A ride in the main loop of the base GEMM as one extra k-block instead of a second pass over y.
    * NULL / 0 when unused.  Both kernels take it with every epilogue. */
   const void* A2; const void* B2; int64_t K2, lda2, ldb2;
+  /* Optional (N) fp32: receives the column sums over m of the stored result (before rounding to d_dtype) — the bias
+   * gradient of the layer whose output gradient this GEMM produces (the fc1 bias of an MLP: its dY is the MUL_AUX dgrad
+   * of fc2), so no separate pass re-reads D.  tcgen05 kernel, epilogue NONE or MUL_AUX without residual / aux_out / beta,
+   * N % 4 == 0, unbatched; zeroed by the call, accumulated with fp32 atomics (summation order not fixed).  NULL when unused. */
+  float* colsum_out;
 } tsw_gemm_desc;
 
 size_t tsw_gemm_workspace_bytes(const tsw_gemm_desc* d);

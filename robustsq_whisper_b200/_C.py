@@ -39,6 +39,7 @@ class GemmDesc(Structure):
         ("alpha", c_float), ("beta", c_float),
         ("alpha_dev", c_void_p),
         ("A2", c_void_p), ("B2", c_void_p), ("K2", c_int64), ("lda2", c_int64), ("ldb2", c_int64),
+        ("colsum_out", c_void_p),
     ]
 
 

@@ -29,6 +29,7 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   ep.aux_in = g.aux_in; ep.aux_out = g.aux_out;
   ep.epilogue = g.epilogue;
   ep.alpha = g.alpha; ep.beta = g.beta; ep.alpha_dev = g.alpha_dev;
+  ep.colsum = g.colsum_out;
   ep.M = g.M; ep.N = g.N;
   const int vn = g.d_dtype == TSW_F32 ? 4 : 8;
   auto ok = [&](const void* p, int64_t ld, int64_t so, int64_t si) {
@@ -45,6 +46,10 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
                ok4(g.residual, g.ldres, g.res_stride_outer, g.res_stride_inner) && (!g.bias || aligned16(g.bias));
 
   cudaStream_t st = as_stream(stream);
+  if (g.colsum_out && (g.impl == TSW_GEMM_SIMT || !gemm_tc_supported(g, nullptr))) {
+    set_error("gemm: colsum_out is a feature of the tcgen05 kernel (bf16 operands that satisfy the TMA constraints)");
+    return TSW_E_UNSUPPORTED;
+  }
   if (g.impl == TSW_GEMM_SIMT) return gemm_simt_launch(g, ep, st);
   if (g.impl == TSW_GEMM_TCGEN05) return gemm_tc_launch(g, ep, st);
   TSW_CHECK_ARG(g.impl == TSW_GEMM_AUTO, "gemm: bad impl %d", g.impl);

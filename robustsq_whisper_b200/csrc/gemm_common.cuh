@@ -15,6 +15,7 @@ struct EpiParams {
   int64_t M, N;
   int vec_ok;  // D/residual/aux rows are 16-byte aligned at 8-element (bf16) / 4-element (fp32) column granularity
   int vec4_ok; // ... aligned for 4-element accesses (8 B bf16 / 16 B fp32): the coalesced tcgen05 epilogue
+  float* colsum;  // optional (N) fp32: column sums of the epilogue's result are atomically added here (tcgen05 kernel only)
 };
 
 // 4 consecutive elements <-> fp32 registers

@@ -95,8 +95,10 @@ __device__ __forceinline__ int epi_kind_of(const EpiParams& ep) {
 template <typename DT, int KIND>
 __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic, const float* srow, int u, int rsub, int rows_ok, float alpha,
                                          float4 b4, DT* Dp, const DT* Rp, const DT* AIp, DT* AOp, int64_t off, int64_t row4, int64_t roff,
-                                         int64_t rrow4, int) {
+                                         int64_t rrow4, int n, unsigned lanes) {
   typename RawVec<DT>::type pre[8];
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};   // column sums of this lane's rows (bias gradient riding in the producer's epilogue)
+  const bool do_cs = (KIND == EK_PLAIN || KIND == EK_MUL_AUX) && ep.colsum != nullptr;   // uniform for the launch
   if (KIND == EK_RES || KIND == EK_MUL_AUX || KIND == EK_MUL_DGELU) {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -133,6 +135,7 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
         const float dg[4] = {d01.x, d01.y, d23.x, d23.y};
         store4(AOp + off + (int64_t)i * row4, dg);
       }
+      if (do_cs) { cs[0] += o[0]; cs[1] += o[1]; cs[2] += o[2]; cs[3] += o[3]; }
       DT* dst = Dp + off + (int64_t)i * row4;
       if constexpr (sizeof(DT) == 4) {
         if (KIND == EK_PLAIN && split_atomic) atomicAdd(reinterpret_cast<float4*>(dst), make_float4(o[0], o[1], o[2], o[3]));
@@ -141,6 +144,11 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
         store4(dst, o);
       }
     }
+  }
+  if (do_cs) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { cs[j] += __shfl_xor_sync(lanes, cs[j], 8); cs[j] += __shfl_xor_sync(lanes, cs[j], 16); }   // partners share u
+    if (rsub == 0) atomicAdd(reinterpret_cast<float4*>(ep.colsum + n), make_float4(cs[0], cs[1], cs[2], cs[3]));
   }
 }
 
@@ -344,23 +352,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         const int n = n_first + c;
         const bool vec = ep.vec4_ok && (n + 4 <= p.N);
+        const unsigned vlanes = __ballot_sync(0xffffffffu, vec);   // on the last column tile only the lanes inside N take the vector path
         if (vec) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ep.bias && first_split) b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n));
           const int64_t off = off0 + c;
           const float* srow = stg + rsub * 32;
           if (!GENERIC) {
-            epi_rows<DT, EK_PLAIN>(ep, p.splits > 1, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, nullptr, off, row4, 0, 0, 0);
+            epi_rows<DT, EK_PLAIN>(ep, p.splits > 1, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, nullptr, off, row4, 0, 0, n, vlanes);
           } else {
             // one specialised, branch-free row loop per fused-epilogue kind: the kind is uniform for the whole launch, so
             // only one compact loop is ever resident in the instruction cache
             const int64_t roff = Rp ? r_off + m_first * ep.ldres + n : 0;
             switch (epi_kind) {
-              case EK_RES: epi_rows<DT, EK_RES>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, Rp, nullptr, nullptr, off, row4, roff, 4 * ep.ldres, 0); break;
-              case EK_GELU: epi_rows<DT, EK_GELU>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, AOp, off, row4, 0, 0, 0); break;
-              case EK_GELU_GRAD: epi_rows<DT, EK_GELU_GRAD>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, AOp, off, row4, 0, 0, 0); break;
-              case EK_MUL_AUX: epi_rows<DT, EK_MUL_AUX>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, AIp, nullptr, off, row4, 0, 0, 0); break;
-              case EK_MUL_DGELU: epi_rows<DT, EK_MUL_DGELU>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, AIp, nullptr, off, row4, 0, 0, 0); break;
+              case EK_RES: epi_rows<DT, EK_RES>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, Rp, nullptr, nullptr, off, row4, roff, 4 * ep.ldres, n, vlanes); break;
+              case EK_GELU: epi_rows<DT, EK_GELU>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, AOp, off, row4, 0, 0, n, vlanes); break;
+              case EK_GELU_GRAD: epi_rows<DT, EK_GELU_GRAD>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, nullptr, AOp, off, row4, 0, 0, n, vlanes); break;
+              case EK_MUL_AUX: epi_rows<DT, EK_MUL_AUX>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, AIp, nullptr, off, row4, 0, 0, n, vlanes); break;
+              case EK_MUL_DGELU: epi_rows<DT, EK_MUL_DGELU>(ep, false, srow, u, rsub, rows_ok, alpha, b4, Dp, nullptr, AIp, nullptr, off, row4, 0, 0, n, vlanes); break;
               default:
 #pragma unroll 1
                 for (int i = 0; i < rows_ok; ++i) {
@@ -487,6 +496,14 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.total_work = p.total_tiles * p.splits;
   if (p.splits > 1) TSW_CUDA(cudaMemset2DAsync(g.D, (size_t)g.ldd * 4, 0, (size_t)g.N * 4, (size_t)g.M, st));
+  if (ep.colsum) {
+    const bool kind_ok = (g.epilogue == TSW_EPI_NONE || g.epilogue == TSW_EPI_MUL_AUX) && !g.residual && !g.aux_out && g.beta == 0.f && g.res_row_mod == 0;
+    if (!kind_ok || !ep.vec4_ok || g.N % 4 != 0 || p.splits > 1 || p.batches != 1) {
+      set_error("gemm(tcgen05): colsum_out needs a plain or MUL_AUX epilogue, 4-element aligned rows, N %% 4 == 0, one batch, no split-K");
+      return TSW_E_UNSUPPORTED;
+    }
+    TSW_CUDA(cudaMemsetAsync(ep.colsum, 0, sizeof(float) * (size_t)g.N, st));
+  }
   auto kern = gemm_tc_kernel<BN, STAGES, DT, GENERIC, CL>;
   static bool attr_done = false;
   if (!attr_done) {

@@ -2,6 +2,7 @@
 // staging, attention softmax, decoder token embedding).  All are coalesced, 16-byte-vectorised, fp32-statistics
 // kernels with warp-shuffle reductions; grids are sized in multiples of the SM count where the work allows.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gemm_common.cuh"   // common.cuh + the 4-element load4 / store4 helpers
 
@@ -174,6 +175,120 @@ ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float*
 #pragma unroll
     for (int c = 0; c < NC; ++c) { cx[c] = nx[c]; cd[c] = nd[c]; }
   }
+}
+
+// Single-pass variant for d <= 32 lanes * 4 vectors (every Whisper / SQ-Former width in bf16): the same warp-per-row sweep also
+// accumulates the lane's 4 x VN columns of dgamma = sum dy * xhat and dbeta = sum dy in registers, so dy and x are read ONCE
+// (the two-pass form re-reads both for the parameter gradients: 6 instead of 4 tensor passes).  One CTA per SM at ~170
+// registers; the next row's x / dy and this row's dres are in flight during the two warp reductions.  The 8 warps fold
+// their column sums through shared memory in warp order, each CTA writes one partial row, and ln_bwd_fold_kernel adds the
+// partial rows in CTA order (deterministic).
+template <typename T, int NC>
+__global__ void __launch_bounds__(256, 1)
+ln_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx, int64_t rows, int d,
+                    float* __restrict__ partial) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float sm_acc[];   // [2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  const int nvec = d / VN;
+  float ag[NC][VN], ab[NC][VN];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < VN; ++j) ag[c][j] = ab[c][j] = 0.f;
+  uint4 cx[NC], cd[NC], nx[NC], nd[NC];
+  auto load_row = [&](int64_t r, uint4* xd, uint4* dd) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) { xd[c] = ldg16(x + r * d + (int64_t)i * VN); dd[c] = ldg16(dy + r * d + (int64_t)i * VN); }
+    }
+  };
+  if (row < rows) load_row(row, cx, cd);
+  for (; row < rows; row += stride) {
+    const bool more = row + stride < rows;
+    if (more) load_row(row + stride, nx, nd);
+    const float mu = mean[row], rs = rstd[row];
+    uint4 rr[NC];
+    if (dres != nullptr) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nvec) rr[c] = ldg16(dres + row * d + (int64_t)i * VN);
+      }
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float xv[VN], dv[VN], gv[VN];
+        unpack16<T>(cx[c], xv); unpack16<T>(cd[c], dv);
+#pragma unroll
+        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const float xh = (xv[j] - mu) * rs, g = dv[j] * gv[j];
+          s1 += g; s2 = fmaf(g, xh, s2);
+          ag[c][j] = fmaf(dv[j], xh, ag[c][j]); ab[c][j] += dv[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int i = lane + 32 * c;
+      if (i < nvec) {
+        float xv[VN], dv[VN], gv[VN], o[VN];
+        unpack16<T>(cx[c], xv); unpack16<T>(cd[c], dv);
+#pragma unroll
+        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] = rs * (dv[j] * gv[j] - s1 - (xv[j] - mu) * rs * s2);
+        if (dres != nullptr) {
+          float r[VN];
+          unpack16<T>(rr[c], r);
+#pragma unroll
+          for (int j = 0; j < VN; ++j) o[j] += r[j];
+        }
+        Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { cx[c] = nx[c]; cd[c] = nd[c]; }
+  }
+  // fold the 8 warps' column sums in warp order, then one partial row per CTA
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int i = lane + 32 * c;
+        if (i < nvec) {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) {
+            const int col = i * VN + j;
+            sm_acc[col] = (w == 0 ? 0.f : sm_acc[col]) + ag[c][j];
+            sm_acc[d + col] = (w == 0 ? 0.f : sm_acc[d + col]) + ab[c][j];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < 2 * d; c += 256) partial[(int64_t)blockIdx.x * 2 * d + c] = sm_acc[c];
+}
+
+__global__ void __launch_bounds__(256)
+ln_bwd_fold_kernel(const float* __restrict__ partial, int n_parts, int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= 2 * d) return;
+  float t = 0.f;
+  for (int p = 0; p < n_parts; ++p) t += partial[(int64_t)p * 2 * d + c];
+  if (c < d) dgamma[c] = t; else dbeta[c - d] = t;
 }
 
 template <typename T>
@@ -650,7 +765,8 @@ static unsigned int* colsum_counters();
 static int64_t colsum_chunks(int64_t rows, int64_t n, int vn);
 
 extern "C" size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d) {
-  return sizeof(float) * 2 * (size_t)d * (size_t)std::max(colsum_chunks(rows, d, 4), colsum_chunks(rows, d, 8));
+  const size_t parts = (size_t)std::max<int64_t>(std::max(colsum_chunks(rows, d, 4), colsum_chunks(rows, d, 8)), sm_count());
+  return sizeof(float) * 2 * (size_t)d * parts;
 }
 
 extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
@@ -663,8 +779,23 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   TSW_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && (!dres || aligned16(dres)), "layernorm_bwd: pointers must be 16-byte aligned");
   if (!workspace || workspace_bytes < tsw_layernorm_bwd_workspace_bytes(rows, d)) { set_error("layernorm_bwd: workspace too small"); return TSW_E_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
-  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 2);
   const int nc = (int)((d / vn + 31) / 32);
+  static const bool two_pass = getenv("TSW_LN_BWD_TWO_PASS") != nullptr;
+  if (dgamma && nc <= 4 && rows >= 4096 && !two_pass) {
+    // single pass: dx and the parameter gradients from one sweep (large activations; small ones stay on the two-pass form,
+    // whose parameter pass spreads over more CTAs than there are 8-row groups)
+    const unsigned g1 = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count());
+    float* partial = (float*)workspace;
+    const size_t smem = sizeof(float) * 2 * (size_t)d;
+#define LN_FUSED(NCV) DISPATCH_T(dtype, (ln_bwd_fused_kernel<T, NCV><<<g1, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d, partial)))
+    if (nc <= 1) { LN_FUSED(1); } else if (nc <= 2) { LN_FUSED(2); } else if (nc <= 3) { LN_FUSED(3); } else { LN_FUSED(4); }
+#undef LN_FUSED
+    TSW_LAUNCH_CHECK();
+    ln_bwd_fold_kernel<<<(unsigned)((2 * d + 255) / 256), 256, 0, st>>>(partial, (int)g1, (int)d, dgamma, dbeta);
+    TSW_LAUNCH_CHECK();
+    return TSW_OK;
+  }
+  const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 2);
   DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (ln_bwd_dx_kernel<T, NC><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d))));
   TSW_LAUNCH_CHECK();
   if (!dgamma) return TSW_OK;   // frozen affine parameters: no parameter-gradient pass

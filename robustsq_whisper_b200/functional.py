@@ -179,10 +179,15 @@ class _MLP(Function):
             db2 = K.colsum(dy2, rows, N)
         if not (need[0] or need[1] or need[2]):
             return None, None, None, dw2, db2, (dy if ctx.has_res else None)
-        dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_AUX, out_dtype=dt, impl=impl)
+        # fc1's bias gradient = column sums of dh: in the bf16 regime they ride in the epilogue of the GEMM that produces dh
+        fuse_db1 = need[2] and dt == torch.bfloat16 and H % 8 == 0 and N % 8 == 0
+        if fuse_db1:
+            db1 = torch.empty(H, dtype=torch.float32, device=dy2.device)
+        dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_AUX, out_dtype=dt, impl=impl,
+                    colsum_out=db1 if fuse_db1 else None)
         if need[1]:
             dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl)
-        if need[2]:
+        if need[2] and not fuse_db1:
             db1 = K.colsum(dh, rows, H)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -427,8 +432,9 @@ class _PackedSelfAttention(Function):
         w = shadow_cat((wq, wk, wv), x2.dtype)
         dx = K.gemm(dy2, w, M=rows, N=d, K=d3, b_mn=True, ldb=d, out_dtype=x2.dtype).view(B, S, d) if ctx.needs_input_grad[0] else None
         dw = K.gemm(dy2, x2, M=d3, N=d, K=rows, a_mn=True, b_mn=True, lda=d3, ldb=d, out_dtype=torch.float32)
-        db = K.colsum(dy2, rows, d3)
-        return dx, dw[:d], db[:d], dw[d:2 * d], dw[2 * d:], db[2 * d:], None, None, None
+        # bias gradients of q and v only (Whisper's key projection has none): two d-wide column sums over slices of dqkv
+        dbq, dbv = K.colsum(dy2[:, :d], rows, d, ld=d3), K.colsum(dy2[:, 2 * d:], rows, d, ld=d3)
+        return dx, dw[:d], dbq, dw[d:2 * d], dw[2 * d:], dbv, None, None, None
 
 
 class _PackedCrossAttention(Function):
@@ -463,8 +469,8 @@ class _PackedCrossAttention(Function):
         w = shadow_cat((wk, wv), xa2.dtype)
         dxa = K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, out_dtype=xa2.dtype).view(B, Sk, d) if ctx.needs_input_grad[1] else None
         dw = K.gemm(dy2, xa2, M=d2, N=d, K=rows, a_mn=True, b_mn=True, lda=d2, ldb=d, out_dtype=torch.float32)
-        db = K.colsum(dy2, rows, d2)
-        return dq, dxa, dw[:d], dw[d:], db[d:], None, None
+        dbv = K.colsum(dy2[:, d:], rows, d, ld=d2)   # the value half only: the key projection has no bias
+        return dq, dxa, dw[:d], dw[d:], dbv, None, None
 
 
 def packed_attention_ok(x: Tensor, n_head: int) -> bool:

@@ -119,6 +119,7 @@ def gemm(
     aux_in: Optional[Tensor] = None, aux_out: Optional[Tensor] = None, epilogue: int = _C.EPI_NONE,
     alpha: float = 1.0, beta: float = 0.0, impl: int = _C.GEMM_AUTO, alpha_dev: Optional[Tensor] = None,
     a2: Optional[Tensor] = None, b2: Optional[Tensor] = None, K2: int = 0, lda2: Optional[int] = None, ldb2: Optional[int] = None,
+    colsum_out: Optional[Tensor] = None,
 ) -> Tensor:
     """D = epilogue(alpha * A @ B) with the operand layouts of include/tsw.h.  ``a``/``b`` are only used for their
     storage (data_ptr, dtype): the logical shapes come from M/N/K, the majors and the leading dimensions.
@@ -156,6 +157,10 @@ def gemm(
     if alpha_dev is not None and (alpha_dev.dtype != torch.float32 or not alpha_dev.is_cuda):
         raise _C.TswError("gemm: alpha_dev must be a float32 cuda scalar")
     g.alpha_dev = ptr(alpha_dev)
+    if colsum_out is not None:
+        if colsum_out.dtype != torch.float32 or colsum_out.numel() != N or not colsum_out.is_cuda:
+            raise _C.TswError("gemm: colsum_out must be a float32 cuda tensor of N elements")
+        g.colsum_out = ptr(colsum_out)
     if a2 is not None:
         if b2 is None or K2 <= 0 or a2.dtype != a.dtype or b2.dtype != b.dtype:
             raise _C.TswError("gemm: a2/b2 need K2 > 0 and the dtypes of a/b")

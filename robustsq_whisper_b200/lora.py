@@ -258,8 +258,7 @@ class _PackedSelfAttentionLoRA(Function):
             dw = K.gemm(dy2, x2, M=d3, N=d, K=rows, a_mn=True, b_mn=True, lda=d3, ldb=d, out_dtype=torch.float32)
             dwq, dwk, dwv = dw[:d], dw[d:2 * d], dw[2 * d:]
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[5]:
-            db = K.colsum(dy2, rows, d3)
-            dbq, dbv = db[:d], db[2 * d:]
+            dbq, dbv = K.colsum(dy2[:, :d], rows, d, ld=d3), K.colsum(dy2[:, 2 * d:], rows, d, ld=d3)
         return (dx, dwq, dbq, dwk, dwv, dbv, dAs[0], dBs[0], dAs[1], dBs[1], dAs[2], dBs[2], None, None, None, None)
 
 
@@ -307,7 +306,7 @@ class _PackedCrossAttentionLoRA(Function):
             dw = K.gemm(dy2, xa2, M=d2, N=d, K=rows, a_mn=True, b_mn=True, lda=d2, ldb=d, out_dtype=torch.float32)
             dwk, dwv = dw[:d], dw[d:]
         if ctx.needs_input_grad[4]:
-            dbv = K.colsum(dy2, rows, d2)[d:]
+            dbv = K.colsum(dy2[:, d:], rows, d, ld=d2)
         return (dq, dxa, dwk, dwv, dbv, dAs[0], dBs[0], dAs[1], dBs[1], None, None, None)
 
 

@@ -81,6 +81,30 @@ def test_layernorm_fwd_bwd(K, dtype, d, rows):
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("d,rows", [(1024, 5003), (768, 9001), (384, 4100), (512, 4096)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layernorm_bwd_single_pass(K, d, rows, with_res):
+    """rows >= 4096 in bf16 take the single-pass kernel (dx + dgamma / dbeta from one sweep over dy and x)."""
+    torch.manual_seed(3)
+    dt = torch.bfloat16
+    x = (torch.randn(rows, d) * 2 + 0.3).to(dt)
+    gamma, beta = torch.randn(d) * 0.5 + 1, torch.randn(d) * 0.1
+    dy = torch.randn(rows, d).to(dt)
+    dres = torch.randn(rows, d).to(dt) if with_res else None
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy.float())
+    y, _, mean, rstd = K.layernorm_fwd(x.cuda(), gamma.cuda(), beta.cuda(), 1e-5)
+    dx, dg, db = K.layernorm_bwd(dy.cuda(), x.cuda(), gamma.cuda(), mean, rstd, dres=None if dres is None else dres.cuda())
+    want_dx = xr.grad + (dres.float() if with_res else 0.0)
+    assert rel_err(dx.float(), want_dx) < 1e-2
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    dx2, dg2, db2 = K.layernorm_bwd(dy.cuda(), x.cuda(), gamma.cuda(), mean, rstd, dres=None if dres is None else dres.cuda())
+    assert torch.equal(dg, dg2) and torch.equal(db, db2) and torch.equal(dx, dx2)      # fixed summation order
+    dx3, dg3, _ = K.layernorm_bwd(dy.cuda(), x.cuda(), gamma.cuda(), mean, rstd, param_grads=False)
+    assert dg3 is None and (with_res or torch.equal(dx3, dx))
+
+
 def test_layernorm_fused_residual(K):
     torch.manual_seed(1)
     x, r = torch.randn(50, 768), torch.randn(50, 768)
@@ -404,6 +428,30 @@ def test_gemm_batched_attention_shapes(K, impl):
     K.gemm(pp.cuda(), v.cuda(), M=S, N=dh, K=S, lda=Sp, b_mn=True, ldb=d, batch=(B, H), a_strides=(H * S * Sp, S * Sp), b_strides=(S * d, dh),
            out=out, ldd=d, d_strides=(S * d, dh), impl=impl)
     assert rel_err(out.float(), o_ref) < 1e-2
+
+
+@pytest.mark.parametrize("shape", [(1516, 1024, 256), (300, 520, 200), (128, 2048, 64), (77, 64, 72)])
+def test_gemm_column_sums_in_the_epilogue(K, shape):
+    """colsum_out = sum over rows of the stored result (the bias gradient of the layer whose dY the GEMM produces)."""
+    from robustsq_whisper_b200 import _C
+    torch.manual_seed(18)
+    M, N, Kd = shape
+    dt = torch.bfloat16
+    a, w = (torch.randn(M, Kd) * 0.5).to(dt), (torch.randn(Kd, N) * 0.2).to(dt)       # B stored [K][N] (the dgrad layout)
+    aux = torch.randn(M, N).to(dt)
+    cs = torch.full((N,), 7.0, device="cuda")                                          # must be overwritten, not added to
+    out = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, b_mn=True, ldb=N, aux_in=aux.cuda(), epilogue=_C.EPI_MUL_AUX, out_dtype=dt, impl=2,
+                 colsum_out=cs)
+    ref = (a.float() @ w.float()) * aux.float()
+    assert rel_err(out.float(), ref) < 1e-2
+    assert rel_err(cs, ref.sum(0)) < 2e-4
+    cs2 = torch.empty(N, device="cuda")
+    out2 = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, b_mn=True, ldb=N, out_dtype=dt, impl=2, colsum_out=cs2)
+    assert rel_err(cs2, (a.float() @ w.float()).sum(0)) < 2e-4
+    with pytest.raises(_C.TswError):
+        K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, b_mn=True, ldb=N, out_dtype=dt, impl=1, colsum_out=cs2)      # SIMT kernel: unsupported
+    with pytest.raises(_C.TswError):
+        K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, b_mn=True, ldb=N, epilogue=_C.EPI_GELU, out_dtype=dt, impl=2, colsum_out=cs2)
 
 
 def test_gemm_auto_falls_back_to_simt_for_unaligned(K):

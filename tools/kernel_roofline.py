@@ -41,7 +41,7 @@ x = torch.randn(B * S, d, device="cuda").to(bf); g = torch.ones(d, device="cuda"
 hbm("K6 layernorm fwd (48512 x 1024 bf16)", 2 * 2 * B * S * d, lambda: K.layernorm_fwd(x, g, b_, 1e-5))
 y, _, mean, rstd = K.layernorm_fwd(x, g, b_, 1e-5)
 dy = torch.randn_like(x)
-hbm("K6 layernorm bwd (+residual grad)", 4 * 2 * B * S * d, lambda: K.layernorm_bwd(dy, x, g, mean, rstd, dres=dy), "dy, x, dres in, dx out; dgamma pass re-reads x, dy (not counted)")
+hbm("K6 layernorm bwd (+residual grad)", 4 * 2 * B * S * d, lambda: K.layernorm_bwd(dy, x, g, mean, rstd, dres=dy), "dy, x, dres in, dx out; dgamma / dbeta from the same sweep")
 hbm("colsum (bias grad, 48512 x 4096 bf16)", 2 * B * S * 4096, lambda: K.colsum(torch.empty(B * S, 4096, device="cuda", dtype=bf), B * S, 4096))
 # K7 ASP
 xe = torch.randn(B, 500, d, device="cuda").to(bf)
