@@ -247,8 +247,10 @@ def run_b200(args):
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    torch.cuda.profiler.start()   # cudaProfilerStart: `ncu --profile-from-start off` captures exactly the timed steps (all threads:
+    for i in range(args.steps):   # backward kernels are launched by autograd's worker thread); a no-op without a profiler
         step(staged[i])
+    torch.cuda.profiler.stop()
     e1.record()
     sync_all()
     ms_dev = e0.elapsed_time(e1) / args.steps
