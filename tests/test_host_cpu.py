@@ -155,3 +155,70 @@ def test_data_parallel_helpers_world_size_2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True, True), (1, True, True)]
+
+
+# ------------------------------------------------------------------------------------------------ §8f host logic (no GPU)
+def test_lora_adapter_management_on_cpu():
+    """apply / freeze / merge / unmerge are pure host logic: names follow loralib (``<linear>.lora_A|lora_B``), only the
+    Whisper blocks are adapted, the randomly initialised SQ-Former and the speaker heads keep training."""
+    from robustsq_whisper_b200 import lora
+    m = _build("tiny")
+    m.materialize_heads(device="cpu")
+    n_before = len(m.state_dict())
+    names = lora.apply_lora(m, rank=8, alpha=16.0, target_modules=("query", "value"))
+    assert len(names) == 2 * 4 + 4 * 4 and all(n.split(".")[-1] in ("query", "value") for n in names)
+    assert len(m.state_dict()) == n_before + 2 * len(names)
+    q = m.encoder.encoders.blocks[0].attn.query
+    assert q.lora_A.shape == (8, 384) and q.lora_B.shape == (384, 8) and q.lora_scaling == 2.0 and not q.lora_B.any()
+    trainable = {n for n, p in m.named_parameters() if p.requires_grad}
+    assert all("lora_" in n or n.startswith(("encoder.qformer.", "encoder.prompt_proj", "asp_pooling.", "aam_classifier")) for n in trainable)
+    assert any(n.startswith("encoder.qformer.") for n in trainable) and "decoder.decoders.token_embedding.weight" not in trainable
+    w0 = q.weight.detach().clone()
+    with torch.no_grad():
+        q.lora_B.normal_(0, 0.1)
+    assert lora.merge_lora(m) == len(names) and lora.merge_lora(m) == 0
+    assert torch.allclose(q.weight, w0 + 2.0 * q.lora_B @ q.lora_A, atol=1e-6) and lora.lora_of(q) is None
+    assert lora.unmerge_lora(m) == len(names) and torch.allclose(q.weight, w0, atol=1e-6) and lora.lora_of(q) is not None
+    with pytest.raises(ValueError):
+        lora.apply_lora(m, rank=8)                        # already adapted
+    with pytest.raises(ValueError):
+        lora.apply_lora(_build("tiny"), rank=4, target_modules=("nothing",))
+    x = torch.randn(5, 384)
+    assert torch.allclose(port.lora_linear(x, w0, None, q.lora_A, q.lora_B, 2.0), x @ (w0 + 2.0 * q.lora_B @ q.lora_A).t(), atol=1e-4)
+
+
+def test_specaug_draws_follow_the_espnet_call_order():
+    """The host class consumes torch's RNG exactly like the ESPnet restatement: same centre / warped frame, same masks."""
+    from robustsq_whisper_b200.specaug import SpecAug
+    conf = dict(time_warp_window=5, freq_mask_width_range=(0, 27), num_freq_mask=2, time_mask_width_ratio_range=(0.0, 0.1), num_time_mask=3)
+    ours = SpecAug(**conf)
+    B, T, Fm = 3, 200, 80
+    torch.manual_seed(11)
+    warp, t_out, zero_tail = ours._draw_warp(B, T, None)
+    fmask = ours._draw_mask(B, Fm, ours.freq_range, ours.num_freq_mask, torch.device("cpu"))
+    tmask = ours._draw_mask(B, t_out, (0, 20), ours.num_time_mask, torch.device("cpu"))
+    state_after = torch.get_rng_state()
+    x = torch.randn(B, T, Fm, generator=torch.Generator().manual_seed(1)) + 5.0
+    torch.manual_seed(11)
+    y, _ = upstream.SpecAug(**conf)(x.clone(), None)
+    assert torch.equal(torch.get_rng_state(), state_after)                       # same number and kind of draws
+    assert t_out == T and not zero_tail and warp.shape == (B, 3) and bool((warp[:, 0] == warp[0, 0]).all())
+    zero = y == 0
+    for b in range(B):
+        cols = torch.zeros(Fm, dtype=torch.bool); rows = torch.zeros(T, dtype=torch.bool)
+        for s, w in fmask[b].tolist():
+            cols[s:s + w] = True
+        for s, w in tmask[b].tolist():
+            rows[s:s + w] = True
+        assert torch.equal(zero[b], rows[:, None] | cols[None, :])
+    # ragged batch: one draw pair per item, padded back to the longest item
+    torch.manual_seed(12)
+    warp2, t2, zt2 = ours._draw_warp(3, 200, [200, 150, 9])
+    assert t2 == 200 and zt2 and warp2[:, 2].tolist() == [200, 150, 9] and warp2[2, 0] == 0   # 9 frames: too short to warp
+
+
+def test_enrollment_pattern_parsing():
+    from robustsq_whisper_b200.enroll_pipeline import parse_enroll_pattern
+    assert parse_enroll_pattern("*1034-121119-0049 1034") == ("1034-121119-0049", "1034")   # datapre/create_enrollment_scp.py:78
+    with pytest.raises(ValueError):
+        parse_enroll_pattern("/path/to/enroll.wav")
