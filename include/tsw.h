@@ -81,12 +81,14 @@ int tsw_logmel_gather_fwd(const float* bank, const int64_t* item_off, const int3
  * the nn.Linear weight layout) or [K][N] (b_mn_major = 1).  D, residual and aux are stored [M][N].
  * Epilogue order: v = alpha*acc (+ bias[n]) ; if aux_out: aux_out = v (gelu'(v) for GELU_SAVE_GRAD) ; v = act(v) | v * gelu'(aux_in) | v * aux_in ;
  * (+ residual[(m % res_row_mod)][n]) ; (+ D if beta != 0) ; D = v.
- * impl: 0 = auto (tcgen05 for bf16 operands that satisfy TMA alignment, else SIMT), 1 = SIMT fp32-accumulate
- * kernel, 2 = tcgen05/TMEM/TMA kernel (fails if unsupported). */
+ * impl: 0 = auto (the skinny weight-streaming kernel for M <= 32 rows against a K-major bf16 weight, tcgen05 for other bf16
+ * operands that satisfy TMA alignment, else SIMT), 1 = SIMT fp32-accumulate kernel, 2 = tcgen05/TMEM/TMA kernel, 3 = skinny
+ * kernel (2 and 3 fail if unsupported). */
 enum { TSW_EPI_NONE = 0, TSW_EPI_GELU = 1, TSW_EPI_MUL_DGELU = 2,
        TSW_EPI_GELU_SAVE_GRAD = 3, /* D = gelu(v), aux_out = gelu'(v)  (forward of an MLP that will be differentiated) */
        TSW_EPI_MUL_AUX = 4         /* D = v * aux_in               (its backward: one multiply instead of erf/exp) */ };
-enum { TSW_GEMM_AUTO = 0, TSW_GEMM_SIMT = 1, TSW_GEMM_TCGEN05 = 2 };
+enum { TSW_GEMM_AUTO = 0, TSW_GEMM_SIMT = 1, TSW_GEMM_TCGEN05 = 2,
+       TSW_GEMM_SKINNY = 3 /* weight-streaming kernel for M <= 32 token rows (KV-cached decoding); auto picks it when it applies */ };
 
 typedef struct {
   int64_t M, N, K;

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libtsw_sm100.so")
 F32, BF16 = 0, 1
 ABI_VERSION = 2
 EPI_NONE, EPI_GELU, EPI_MUL_DGELU, EPI_GELU_SAVE_GRAD, EPI_MUL_AUX = 0, 1, 2, 3, 4
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
 
 
 class TswError(RuntimeError):

@@ -1,5 +1,6 @@
 // Shared helpers for libtsw_sm100.so kernels (sm_100a only).
 #pragma once
+#include <cstdlib>
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -195,6 +196,30 @@ template <> struct Vec<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor in the stream is still running; everything it does before pdl_wait() must be independent of the
+// predecessor's output (weight prefetch, index math).  pdl_wait() returns once the predecessor grid has completed and its
+// writes are visible; pdl_launch_dependents() lets the successor start launching.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// <<<>>> with the attribute set: used by the short kernels of a KV-cached decode step, which form one dependent chain of
+// ~270 launches per token — the launch latency and the next kernel's weight loads overlap the tail of the previous one.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+inline bool pdl_enabled() {
+  static const bool on = getenv("TSW_NO_PDL") == nullptr;
+  return on;
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -39,6 +39,8 @@ decode_attention_kernel(const T* __restrict__ q, int64_t ldq, T* kc, T* vc, int6
   const int b = blockIdx.x / H, h = blockIdx.x - b * H, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int sub = lane % LPR, grp = warp * RPW + lane / LPR;
+  pdl_launch_dependents();   // decode chain: the projection GEMM that follows may start streaming its weights
+  pdl_wait();                // q, k_new / v_new and L_dev come from the kernels before this one
   const int L = L_dev ? *L_dev : L_host;
   T* kb = kc + (int64_t)b * kv_batch_stride + h * DA_D;
   T* vb = vc + (int64_t)b * kv_batch_stride + h * DA_D;
@@ -136,7 +138,11 @@ extern "C" int tsw_decode_attention(const void* q, int64_t ldq, void* k_cache, v
   TSW_CHECK_ARG(!k_new || (ld_new % vn == 0 && aligned16(k_new) && aligned16(v_new) && kv_batch_stride > 0),
                 "decode_attention: appended rows need 16-byte alignment and a per-hypothesis cache");
   const unsigned grid = (unsigned)(B * H);
-  if (dtype == TSW_F32)
+  if (dtype == TSW_BF16 && pdl_enabled())
+    TSW_CUDA(launch_pdl(decode_attention_kernel<__nv_bfloat16>, dim3(grid), dim3(DA_THREADS), 0, as_stream(stream), (const __nv_bfloat16*)q, ldq,
+                        (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, ldkv, kv_batch_stride, (int)L, L_dev, (int)H, scale, (__nv_bfloat16*)o, ldo,
+                        (const __nv_bfloat16*)k_new, (const __nv_bfloat16*)v_new, ld_new));
+  else if (dtype == TSW_F32)
     decode_attention_kernel<float><<<grid, DA_THREADS, 0, as_stream(stream)>>>((const float*)q, ldq, (float*)k_cache, (float*)v_cache, ldkv, kv_batch_stride, (int)L, L_dev, (int)H, scale, (float*)o, ldo, (const float*)k_new, (const float*)v_new, ld_new);
   else if (dtype == TSW_BF16)
     decode_attention_kernel<__nv_bfloat16><<<grid, DA_THREADS, 0, as_stream(stream)>>>((const __nv_bfloat16*)q, ldq, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, ldkv, kv_batch_stride, (int)L, L_dev, (int)H, scale, (__nv_bfloat16*)o, ldo, (const __nv_bfloat16*)k_new, (const __nv_bfloat16*)v_new, ld_new);

@@ -1,5 +1,7 @@
 // tsw_gemm: argument validation + dispatch between the tcgen05 kernel (gemm_tc.cu) and the fp32-accumulate SIMT
 // kernel (gemm_simt.cu).  See include/tsw.h for the contract.
+#include <cstdlib>
+
 #include "gemm_common.cuh"
 
 using namespace tsw;
@@ -52,7 +54,13 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   }
   if (g.impl == TSW_GEMM_SIMT) return gemm_simt_launch(g, ep, st);
   if (g.impl == TSW_GEMM_TCGEN05) return gemm_tc_launch(g, ep, st);
+  if (g.impl == TSW_GEMM_SKINNY) {
+    if (!gemm_skinny_supported(g)) { set_error("gemm(skinny): needs bf16 K-major operands, M <= 32, 256 <= N <= 8192, K %% 8 == 0, a NONE / GELU epilogue"); return TSW_E_UNSUPPORTED; }
+    return gemm_skinny_launch(g, ep, st);
+  }
   TSW_CHECK_ARG(g.impl == TSW_GEMM_AUTO, "gemm: bad impl %d", g.impl);
+  static const bool no_skinny = getenv("TSW_GEMM_NO_SKINNY") != nullptr;
+  if (!no_skinny && gemm_skinny_supported(g)) return gemm_skinny_launch(g, ep, st);
   if (gemm_tc_supported(g, nullptr)) return gemm_tc_launch(g, ep, st);
   return gemm_simt_launch(g, ep, st);
 }

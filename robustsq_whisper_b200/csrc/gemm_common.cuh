@@ -182,5 +182,8 @@ int gemm_simt_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t s
 // returns TSW_E_UNSUPPORTED (with the reason in tsw_last_error) when the operands do not meet the TMA constraints
 int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st);
 bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why);
+// weight-streaming kernel for decode-time GEMMs (M <= 32 token rows against an nn.Linear weight); chosen by TSW_GEMM_AUTO
+bool gemm_skinny_supported(const tsw_gemm_desc& g);
+int gemm_skinny_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st);
 
 }  // namespace tsw

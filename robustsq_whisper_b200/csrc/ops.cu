@@ -36,6 +36,8 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const f
   const int lane = threadIdx.x & 31;
   const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
   int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_launch_dependents();   // (decode chain, see common.cuh) no-ops for plain launches
+  pdl_wait();
   if (row >= rows) return;
   const int nvec = d / VN;
   uint4 cx[NC], nx[NC];
@@ -755,6 +757,14 @@ extern "C" int tsw_layernorm_fwd(const void* x, const void* res, const float* ga
   TSW_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!res || aligned16(res)) && (!sum_out || aligned16(sum_out)), "layernorm_fwd: pointers must be 16-byte aligned");
   const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 4);
   const int nc = (int)((d / vn + 31) / 32);
+  if (rows <= 256 && pdl_enabled()) {   // a decode step's LayerNorms: part of the programmatic-dependent-launch chain
+    cudaError_t pe = cudaSuccess;
+    DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (pe = launch_pdl(layernorm_fwd_kernel<T, NC>, dim3(grid), dim3(256), 0, as_stream(stream), (const T*)x,
+                                                          (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, (int)d, eps))));
+    TSW_CUDA(pe);
+    TSW_LAUNCH_CHECK();
+    return TSW_OK;
+  }
   DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (layernorm_fwd_kernel<T, NC><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, (const T*)res, gamma, beta, (T*)y,
                                                                                  (T*)sum_out, mean, rstd, rows, (int)d, eps))));
   TSW_LAUNCH_CHECK();

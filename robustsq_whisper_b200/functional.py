@@ -151,12 +151,17 @@ class _MLP(Function):
         N = w2.shape[0]
         dt = x.dtype
         impl = _impl_for(dt)
-        h = torch.empty((rows, H), dtype=dt, device=x.device)
-        # h receives gelu'(pre-activation): backward becomes one multiply in the dgrad epilogue
-        g = K.gemm(x2, shadow(w1, dt), M=rows, N=H, K=d, bias=b1.detach(), aux_out=h, epilogue=_C.EPI_GELU_SAVE_GRAD, out_dtype=dt, impl=impl)
+        if any(ctx.needs_input_grad):
+            h = torch.empty((rows, H), dtype=dt, device=x.device)
+            # h receives gelu'(pre-activation): backward becomes one multiply in the dgrad epilogue
+            g = K.gemm(x2, shadow(w1, dt), M=rows, N=H, K=d, bias=b1.detach(), aux_out=h, epilogue=_C.EPI_GELU_SAVE_GRAD, out_dtype=dt, impl=impl)
+        else:   # inference (decoding): nothing to save
+            h = None
+            g = K.gemm(x2, shadow(w1, dt), M=rows, N=H, K=d, bias=b1.detach(), epilogue=_C.EPI_GELU, out_dtype=dt, impl=impl)
         res2 = None if residual is None else residual.reshape(rows, N).contiguous()
         y = K.gemm(g, shadow(w2, dt), M=rows, N=N, K=H, bias=b2.detach(), residual=res2, out_dtype=dt, impl=impl)
-        ctx.save_for_backward(x2, h, g, w1, w2)
+        if h is not None:
+            ctx.save_for_backward(x2, h, g, w1, w2)
         ctx.has_res = residual is not None
         ctx.in_shape = x.shape
         return y.view(*x.shape[:-1], N)

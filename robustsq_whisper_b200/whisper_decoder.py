@@ -187,7 +187,7 @@ class QFormerTgtSpkWhisperDecoder_V2(AbsDecoder, BatchScorerInterface):
         ``use_graph`` the per-token step (~270 launches of n-row kernels) is captured once as a CUDA graph and replayed:
         position and cache length are device scalars the graph increments itself.  Measured on B200 (medium, bf16): the
         step's kernels take 3.2 ms at n = 32 while launching them one by one from Python takes 8.4 ms, so the graph is on
-        by default (n = 32: 3.9 ms / token = 8.2 k tok/s; n = 128: 6.8 ms = 18.8 k tok/s; token ids identical to eager)."""
+        by default (n = 32: 3.2 ms / token = 10.1 k tok/s; n = 128: 6.9 ms = 18.6 k tok/s; token ids identical to eager)."""
         n = memory.size(0)
         ys = ys0 if ys0 is not None else torch.full((n, 1), sos, dtype=torch.long, device=memory.device)
         logp, cache = self.decode_prefill(ys, memory, spk_prompt, max_new_tokens=max_len)

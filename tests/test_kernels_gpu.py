@@ -454,6 +454,31 @@ def test_gemm_column_sums_in_the_epilogue(K, shape):
         K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, b_mn=True, ldb=N, epilogue=_C.EPI_GELU, out_dtype=dt, impl=2, colsum_out=cs2)
 
 
+@pytest.mark.parametrize("M", [1, 5, 8, 9, 16, 17, 32])
+@pytest.mark.parametrize("NK", [(1024, 1024), (3072, 1024), (1024, 4096), (260, 200), (384, 1536)])
+def test_gemm_skinny_weight_streaming(K, M, NK):
+    """Decode-time GEMMs (a few token rows against a whole weight): impl 3, also what AUTO picks for these shapes."""
+    from robustsq_whisper_b200 import _C
+    torch.manual_seed(19)
+    N, Kd = NK
+    dt = torch.bfloat16
+    a, w = (torch.randn(M, Kd) * 0.5).to(dt), (torch.randn(N, Kd) * 0.05).to(dt)
+    bias, res = torch.randn(N), torch.randn(M, N).to(dt)
+    pre = 0.5 * (a.float() @ w.float().t()) + bias
+    out = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, bias=bias.cuda(), residual=res.cuda(), alpha=0.5, out_dtype=dt, impl=_C.GEMM_SKINNY)
+    assert rel_err(out.float(), pre + res.float()) < 1e-2
+    out32 = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, bias=bias.cuda(), alpha=0.5, out_dtype=torch.float32, impl=_C.GEMM_SKINNY)
+    assert rel_err(out32, pre) < 2e-5
+    outg = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, bias=bias.cuda(), alpha=0.5, epilogue=_C.EPI_GELU, out_dtype=torch.float32, impl=_C.GEMM_SKINNY)
+    assert rel_err(outg, F.gelu(pre)) < 1e-4
+    auto = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, bias=bias.cuda(), alpha=0.5, out_dtype=torch.float32)
+    assert torch.equal(auto, out32)                                  # AUTO took the same kernel
+    tc = K.gemm(a.cuda(), w.cuda(), M=M, N=N, K=Kd, bias=bias.cuda(), alpha=0.5, out_dtype=torch.float32, impl=_C.GEMM_TCGEN05)
+    assert rel_err(tc, out32) < 2e-5
+    with pytest.raises(_C.TswError):
+        K.gemm(a.cuda(), w.t().contiguous().cuda(), M=M, N=N, K=Kd, b_mn=True, ldb=N, out_dtype=dt, impl=_C.GEMM_SKINNY)
+
+
 def test_gemm_auto_falls_back_to_simt_for_unaligned(K):
     torch.manual_seed(15)
     a, b = torch.randn(33, 45).bfloat16(), torch.randn(21, 45).bfloat16()  # ld = 45 breaks the TMA 16-byte rule
