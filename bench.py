@@ -145,7 +145,7 @@ def cpu_baseline(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from oracle import synth  # synthetic batch generator only (test infrastructure shared with the parity tests)
+    from robustsq_whisper_b200 import synth  # SURVEY 8d synthetic batch generator (the oracle re-exports the same module)
     from robustsq_whisper_b200 import kernels as K
     from robustsq_whisper_b200.factory import build_ts_model
     from robustsq_whisper_b200.parallel import GradientAllReducer

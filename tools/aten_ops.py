@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import profile, ProfilerActivity
-from oracle import synth
+from robustsq_whisper_b200 import synth
 from robustsq_whisper_b200.factory import build_ts_model
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
