@@ -71,6 +71,17 @@ def has_lora(*lins: Optional[nn.Module]) -> bool:
     return any(l is not None and lora_of(l) is not None for l in lins)
 
 
+def _add_low_rank(weight: Tensor, Bm: Tensor, A: Tensor, s: float) -> None:
+    """weight (out, in) += s * B (out, r) @ A (r, in), in place.  On the device this is one accumulate-epilogue call of the
+    fp32 GEMM kernel (A is read as the MN-major [K][N] operand); a model still on the host is merged with torch."""
+    if weight.is_cuda:
+        out_f, in_f = weight.shape
+        K.gemm(Bm.detach().float().contiguous(), A.detach().float().contiguous(), M=out_f, N=in_f, K=A.shape[0], b_mn=True, ldb=in_f,
+               out=weight.data, alpha=s, beta=1.0, impl=F._C.GEMM_SIMT)
+    else:
+        weight.add_(s * (Bm.float() @ A.float()).to(weight.dtype))
+
+
 @torch.no_grad()
 def merge_lora(model: nn.Module) -> int:
     """Fold W += (alpha / r) B A into the fp32 master weights (loralib ``merge_weights`` on ``eval()``): decoding then runs
@@ -78,9 +89,10 @@ def merge_lora(model: nn.Module) -> int:
     n = 0
     for mod in model.modules():
         if getattr(mod, "lora_A", None) is not None and not mod.lora_merged:
-            mod.weight.add_(mod.lora_scaling * (mod.lora_B.float() @ mod.lora_A.float()).to(mod.weight.dtype))
+            _add_low_rank(mod.weight, mod.lora_B, mod.lora_A, mod.lora_scaling)
             mod.lora_merged = True
             n += 1
+    F.clear_shadow_cache()   # the kernel wrote the masters through raw pointers: their bf16 shadows are stale
     return n
 
 
@@ -89,9 +101,10 @@ def unmerge_lora(model: nn.Module) -> int:
     n = 0
     for mod in model.modules():
         if getattr(mod, "lora_A", None) is not None and mod.lora_merged:
-            mod.weight.sub_(mod.lora_scaling * (mod.lora_B.float() @ mod.lora_A.float()).to(mod.weight.dtype))
+            _add_low_rank(mod.weight, mod.lora_B, mod.lora_A, -mod.lora_scaling)
             mod.lora_merged = False
             n += 1
+    F.clear_shadow_cache()
     return n
 
 
