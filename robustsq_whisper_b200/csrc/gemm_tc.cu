@@ -39,6 +39,7 @@ struct TcParams {
   int64_t total_tiles;   // output tiles
   int splits, kb_per_split;  // split-K: work item = (tile, split); partial sums are atomically added into fp32 D
   int kb_main, kb_total;     // k-blocks of A x B, and including the appended low-rank pair A2 x B2 (LoRA term)
+  int epi_limit;             // columns of each tile the epilogue drains (= BN; lowered only by the TSW_GEMM_EPI_LIMIT experiment knob)
   int64_t total_work;    // total_tiles * splits
 };
 
@@ -193,26 +194,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
+  // programmatic dependent launch (common.cuh): everything above — barrier init, TMEM allocation, descriptor prefetch — touched
+  // nothing the previous kernel writes, so with the launch attribute it overlaps that kernel's tail; the operands are first
+  // read below.  The trigger lets the NEXT kernel do the same under this one's last, partially filled wave of tiles.
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = *tmem_slot;
   const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int64_t w_first = blockIdx.x / CL, w_step = gridDim.x / CL;   // work items are walked per cluster
+  const int w_first = blockIdx.x / CL, w_step = gridDim.x / CL;   // work items are walked per cluster
+  const int total_work = (int)p.total_work;                         // < 2^31 (checked by the host)
 
   // the contraction runs over the k-blocks of A x B followed by those of the optional second pair A2 x B2 (same majors):
   // D = epilogue(alpha (A B + A2 B2)) — the low-rank LoRA update rides in the main loop as one extra k-block
   const int num_kb = p.kb_total;
-  const int64_t tiles_per_batch = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n;   // work items (tiles, or vertical tile pairs) per batch
+  const int tiles_per_batch = ((p.tiles_m + CL - 1) / CL) * p.tiles_n;   // work items (tiles, or vertical tile pairs) per batch
 
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t w = w_first; w < p.total_work; w += w_step) {
-        const int64_t t = w / p.splits;
-        const int sp = (int)(w - t * p.splits);
+      for (int w = w_first; w < total_work; w += w_step) {   // 32-bit tile arithmetic: the 64-bit divisions cost ~1 us per tile switch
+        const int t = w / p.splits;
+        const int sp = w - t * p.splits;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-        const int bt = (int)(t / tiles_per_batch);
-        const int64_t r = t - (int64_t)bt * tiles_per_batch;
-        const int mt = (int)(r / p.tiles_n) * CL + crank, nt = (int)(r % p.tiles_n);
+        const int bt = t / tiles_per_batch;
+        const int r = t - bt * tiles_per_batch;
+        const int mt = (r / p.tiles_n) * CL + crank, nt = r % p.tiles_n;
         const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
         const int m0 = mt * TBM, n0 = nt * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -260,8 +267,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;  // bytes per UMMA_K = 16
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int64_t w = w_first; w < p.total_work; w += w_step) {
-        const int sp = (int)(w % p.splits);
+      for (int w = w_first; w < total_work; w += w_step) {
+        const int sp = w % p.splits;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
@@ -299,12 +306,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     DT* const AOp = reinterpret_cast<DT*>(ep.aux_out);
     const int64_t row4 = 4 * ep.ldd;
     int as = 0; uint32_t aphase = 0;
-    for (int64_t w = w_first; w < p.total_work; w += w_step) {
-      const int64_t t = w / p.splits;
+    for (int w = w_first; w < total_work; w += w_step) {
+      const int t = w / p.splits;
       const bool first_split = (w - t * p.splits) == 0;
-      const int bt = (int)(t / tiles_per_batch);
-      const int64_t r = t - (int64_t)bt * tiles_per_batch;
-      const int mt = (int)(r / p.tiles_n) * CL + crank, nt = (int)(r % p.tiles_n);
+      const int bt = t / tiles_per_batch;
+      const int r = t - bt * tiles_per_batch;
+      const int mt = (r / p.tiles_n) * CL + crank, nt = r % p.tiles_n;
       const int bo = bt / p.batch_inner, bi = bt - bo * p.batch_inner;
       const int64_t d_off = bo * p.d_so + bi * p.d_si, r_off = bo * p.r_so + bi * p.r_si;
       const int64_t m_first = (int64_t)mt * TBM + q * 32 + rsub;  // this lane's rows: m_first + 4 i, i < 8
@@ -315,13 +322,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (GENERIC) {
         // pull the NEXT tile's extra epilogue operand (residual | aux_in | old D) into L2 now: its loads then hit L2
         // (~250 cycles) instead of DRAM (~800) when that tile's epilogue runs one main loop later
-        const int64_t wn = w + w_step;
+        const int wn = w + w_step;
         const DT* src = Rp ? Rp : ((ep.epilogue == TSW_EPI_MUL_DGELU || ep.epilogue == TSW_EPI_MUL_AUX) ? AIp : (ep.beta != 0.f ? Dp : nullptr));
-        if (src != nullptr && wn < p.total_work && ep.res_row_mod == 0) {
-          const int64_t tn = wn / p.splits;
-          const int btn = (int)(tn / tiles_per_batch);
-          const int64_t rn = tn - (int64_t)btn * tiles_per_batch;
-          const int mtn = (int)(rn / p.tiles_n) * CL + crank, ntn = (int)(rn % p.tiles_n);
+        if (src != nullptr && wn < total_work && ep.res_row_mod == 0) {
+          const int tn = wn / p.splits;
+          const int btn = tn / tiles_per_batch;
+          const int rn = tn - btn * tiles_per_batch;
+          const int mtn = (rn / p.tiles_n) * CL + crank, ntn = rn % p.tiles_n;
           const int bon = btn / p.batch_inner, bin = btn - bon * p.batch_inner;
           const int64_t ld = Rp ? ep.ldres : ep.ldd;
           const int64_t boff = Rp ? (bon * p.r_so + bin * p.r_si) : (bon * p.d_so + bin * p.d_si);
@@ -341,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
       for (int c = half * 32; c < BN; c += 64) {
-        if (nt * BN + c >= p.N) break;  // warp-uniform
+        if (nt * BN + c >= p.N || c >= p.epi_limit) break;  // warp-uniform
         float v[32];
         tmem_ld32(taddr + c, v);        // lane = tile row, 32 consecutive columns
         // transpose through shared memory so global accesses run along rows; 16-byte unit j of row r lives at unit
@@ -492,9 +499,12 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
       if (cost < best * 0.98) { best = cost; p.splits = sct; }
     }
   }
+  static const int epi_limit_env = getenv("TSW_GEMM_EPI_LIMIT") ? atoi(getenv("TSW_GEMM_EPI_LIMIT")) : 0;   // timing experiments only: wrong results
+  p.epi_limit = epi_limit_env > 0 ? epi_limit_env : BN;
   p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
   p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.total_work = p.total_tiles * p.splits;
+  if (p.total_work >= (1ll << 31) - 4096) { set_error("gemm(tcgen05): %lld work items exceed the 32-bit tile arithmetic", (long long)p.total_work); return TSW_E_UNSUPPORTED; }
   if (p.splits > 1) TSW_CUDA(cudaMemset2DAsync(g.D, (size_t)g.ldd * 4, 0, (size_t)g.N * 4, (size_t)g.M, st));
   if (ep.colsum) {
     const bool kind_ok = (g.epilogue == TSW_EPI_NONE || g.epilogue == TSW_EPI_MUL_AUX) && !g.residual && !g.aux_out && g.beta == 0.f && g.res_row_mod == 0;
@@ -511,15 +521,25 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
     attr_done = true;
   }
   const int grid = (int)std::min<int64_t>(p.total_work, units) * CL;
-  if (CL == 1) {
-    kern<<<grid, TC_THREADS, S::kBytes, st>>>(tmA, tmB, tmA2, tmB2, p, ep);
-  } else {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::kBytes; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CL > 1) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    // measured on the medium training step: 195.3 / 196.7 ms with, 196.1 ms without (the step is throughput-bound under the
+    // power cap, not gap-bound), so the attribute is opt-in here; the decode chain's short kernels do use it (3.9 -> 3.2 ms)
+    static const bool gemm_pdl = pdl_enabled() && getenv("TSW_GEMM_PDL") != nullptr;
+    if (gemm_pdl && p.splits == 1 && !ep.colsum) {   // not behind this call's own memsets (split-K / colsum zero-fill): those are not grids
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     TSW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, p, ep));
   }
   TSW_LAUNCH_CHECK();
