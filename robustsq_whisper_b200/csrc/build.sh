@@ -5,7 +5,6 @@ cd "$(dirname "$0")"
 OUT=../libtsw_sm100.so
 OBJ=../../build/obj
 mkdir -p "$OBJ"
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --use_fast_math"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 pids=()
 for f in errors logmel ops heads gemm gemm_simt gemm_tc fmha decode ${TSW_EXTRA_SRCS:-}; do
