@@ -328,7 +328,7 @@ def run_b200(args):
                          "launches_timed": len(tc), "share_of_step": gemm_share, "ms_per_step_while_timed": ms_prof},
             "clocks": sampler.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported baseline: rank 0 at N = 1 only
             try:
                 out["cpu_baseline"] = cpu_baseline(args)
             except Exception as ex:  # pragma: no cover
