@@ -55,6 +55,20 @@ def clear_shadow_cache() -> None:
     _shadow_cache.clear()
 
 
+# Data-parallel runs: id(master weight) -> that weight's fp32 slice of its all-reduce bucket (parallel.GradientAllReducer).
+# A weight-gradient GEMM then writes straight into the bucket (DDP's ``gradient_as_bucket_view``) and the reducer's staging
+# copy disappears.  Handed out only for a fresh gradient (``w.grad is None``): accumulation into an existing ``.grad`` must
+# not alias it.  The returned tensor is a new view object, so autograd's AccumulateGrad adopts it instead of cloning.
+GRAD_SLOTS = {}
+
+
+def grad_out(w: Tensor) -> Optional[Tensor]:
+    slot = GRAD_SLOTS.get(id(w))
+    if slot is None or w.grad is not None or slot.shape != w.shape or slot.device != w.device:
+        return None
+    return slot.view_as(slot)
+
+
 def _impl_for(dtype: torch.dtype) -> int:
     return _C.GEMM_AUTO if dtype == torch.bfloat16 else _C.GEMM_SIMT
 
@@ -93,7 +107,7 @@ class _Linear(Function):
         if ctx.needs_input_grad[0]:
             dx = K.gemm(dy2, shadow(w, x2.dtype), M=rows, N=Kd, K=N, b_mn=True, ldb=Kd, out_dtype=x2.dtype, impl=impl).view(ctx.in_shape)
         if ctx.needs_input_grad[1]:
-            dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl)
+            dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl, out=grad_out(w))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = K.colsum(dy2, rows, N)
         dres = dy if ctx.has_res else None
@@ -179,7 +193,7 @@ class _MLP(Function):
         need = ctx.needs_input_grad   # frozen parameters (LoRA fine-tuning) skip their weight-gradient GEMM / column sum
         dw1 = db1 = dw2 = db2 = None
         if need[3]:
-            dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl)
+            dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl, out=grad_out(w2))
         if need[4]:
             db2 = K.colsum(dy2, rows, N)
         if not (need[0] or need[1] or need[2]):
@@ -191,7 +205,7 @@ class _MLP(Function):
         dh = K.gemm(dy2, shadow(w2, dt), M=rows, N=H, K=N, b_mn=True, ldb=H, aux_in=h, epilogue=_C.EPI_MUL_AUX, out_dtype=dt, impl=impl,
                     colsum_out=db1 if fuse_db1 else None)
         if need[1]:
-            dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl)
+            dw1 = K.gemm(dh, x2, M=H, N=d, K=rows, a_mn=True, b_mn=True, lda=H, ldb=d, out_dtype=torch.float32, impl=impl, out=grad_out(w1))
         if need[2] and not fuse_db1:
             db1 = K.colsum(dh, rows, H)
         dx = None

@@ -71,6 +71,7 @@ class GradientAllReducer:
         self._buckets: Optional[List[_Bucket]] = None   # built from the parameters that had a gradient in the first step
         self._where = {}                                 # id(param) -> (bucket, index)
         self._hooks = []
+        self._slots_published = False
         if overlap and hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -141,3 +142,12 @@ class GradientAllReducer:
             for i, p in enumerate(b.params):
                 p.grad = b.flat[b.offsets[i]:b.offsets[i] + p.numel()].view_as(p)
             b.work, b.ready = None, 0
+        if not self._slots_published:
+            # from the next step on, weight-gradient GEMMs of the matrices write into their bucket slice directly
+            # (functional.grad_out): no staging copy for them
+            from . import functional as F
+            for b in self._buckets:
+                for i, p in enumerate(b.params):
+                    if p.dim() == 2 and p.dtype == torch.float32:
+                        F.GRAD_SLOTS[id(p)] = b.flat[b.offsets[i]:b.offsets[i] + p.numel()].view_as(p)
+            self._slots_published = True

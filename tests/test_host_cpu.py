@@ -139,7 +139,34 @@ def _gloo_worker(rank, world, port_no, q):
             want = [w_ + g_ / world for w_, g_ in zip(want, g)]
         ok_overlap &= all(torch.allclose(prm.grad, w_, atol=1e-6) for prm, w_ in zip(params[:4], want))
         ok_overlap &= all(prm.grad is None for prm in unused.parameters())
-    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_overlap)))
+    # gradient_as_bucket_view: after the first reduce() the 2-D fp32 parameters have a slice of their bucket published; a
+    # backward that writes its weight gradient there (functional.grad_out) is adopted by autograd without a copy
+    from robustsq_whisper_b200 import functional as Fn
+
+    class _WriteIntoSlot(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            return x @ w.t()
+
+        @staticmethod
+        def backward(ctx, gy):
+            x, w = ctx.saved_tensors
+            out = Fn.grad_out(w)
+            dw = gy.t() @ x
+            if out is not None:
+                out.copy_(dw)
+                dw = out
+            return gy @ w, dw
+
+    slot = Fn.GRAD_SLOTS.get(id(lin1.weight))
+    ok_slot = slot is not None and slot.shape == lin1.weight.shape and Fn.grad_out(lin1.weight) is None    # .grad still set: no aliasing
+    for prm in params:
+        prm.grad = None
+    xin = torch.full((2, 4), float(rank + 1))
+    _WriteIntoSlot.apply(xin, lin1.weight).sum().backward()
+    ok_slot &= lin1.weight.grad is not None and lin1.weight.grad.data_ptr() == slot.data_ptr()
+    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_overlap and ok_slot)))
     dist.destroy_process_group()
 
 
