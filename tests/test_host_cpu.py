@@ -249,3 +249,35 @@ def test_enrollment_pattern_parsing():
     assert parse_enroll_pattern("*1034-121119-0049 1034") == ("1034-121119-0049", "1034")   # datapre/create_enrollment_scp.py:78
     with pytest.raises(ValueError):
         parse_enroll_pattern("/path/to/enroll.wav")
+
+
+@pytest.mark.skipif(not harness.reference_available(), reason="reference checkout not present")
+def test_reference_specaug_call_site_matches_how_the_plugin_applies_it():
+    """whisper_encoder.py:521-524 run for real (unmodified reference encoder, ESPnet's SpecAug restated in oracle/upstream.py):
+    the augmentation hits the mixture log-mel only, transposed to (B, T, 80), in training mode only — the same place and
+    layout robustsq_whisper_b200.whisper_encoder applies its one-pass kernel (on (B, 80, T) directly)."""
+    ref = harness.load_reference()
+    conf = dict(time_warp_window=5, freq_mask_width_range=(0, 30), num_freq_mask=2, time_mask_width_range=(0, 25), num_time_mask=2)
+    torch.manual_seed(0)
+    enc = ref.whisper_encoder.QFormerTgtSpkWhisperEncoder_V2(whisper_model="tiny", download_dir="", num_query_tokens=4, num_hidden_layers=1,
+                                                             use_specaug=True, specaug_conf=conf)
+    enc.qformer.eval()
+    g = torch.Generator().manual_seed(3)
+    speech, enroll = 0.1 * torch.randn(2, 32000, generator=g), 0.1 * torch.randn(2, 16000, generator=g)
+    il, el = torch.tensor([32000, 32000]), torch.tensor([16000, 16000])
+    with torch.no_grad():
+        torch.manual_seed(42)
+        got = enc(speech, il, enroll, el)
+        feats, fl = enc.log_mel_spectrogram(speech, il)
+        efeats, efl = enc.log_mel_spectrogram(enroll, el)
+        torch.manual_seed(42)
+        aug, _ = upstream.SpecAug(**conf)(feats.transpose(1, 2), fl)
+        want = enc.whisper_encode(aug.transpose(1, 2), fl, efeats, efl)
+        assert (aug.transpose(1, 2) == 0).any() and not torch.equal(aug.transpose(1, 2), feats)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        enc.encoders.eval()                     # `self.encoders.training` gates it (:521)
+        plain = enc(speech, il, enroll, el)
+        want_plain = enc.whisper_encode(feats, fl, efeats, efl)
+        for a, b in zip(plain, want_plain):
+            assert torch.equal(a, b)
