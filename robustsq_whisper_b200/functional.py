@@ -9,6 +9,7 @@ Precision regimes (one per model instance, chosen by the activation dtype):
 from __future__ import annotations
 
 import math
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -21,17 +22,24 @@ from . import kernels as K
 _shadow_cache = {}
 
 
+def _alive(refs, ps) -> bool:
+    """The cached entry was built for exactly these tensor objects (``id`` alone can be reused after a model is freed)."""
+    return all((r is None and p is None) or (r is not None and r() is p) for r, p in zip(refs, ps))
+
+
 def shadow(p: Tensor, dtype: torch.dtype) -> Tensor:
-    """bf16 shadow of an fp32 master parameter, refreshed when the parameter is updated in place (optimizer step)."""
+    """bf16 shadow of an fp32 master parameter, refreshed when the parameter is updated in place (optimizer step).
+    Writes through ``p.data`` (ESPnet initialisers, legacy optimizers) do not bump ``_version``: call
+    ``clear_shadow_cache()`` after them."""
     if p.dtype == dtype:
         return p.detach()
     key = (id(p), dtype)
     ent = _shadow_cache.get(key)
     ver = p._version
-    if ent is not None and ent[0] == ver and ent[1].data_ptr() != 0 and ent[2] == p.data_ptr():
+    if ent is not None and ent[0] == ver and ent[1].data_ptr() != 0 and ent[2] == p.data_ptr() and ent[3]() is p:
         return ent[1]
     s = K.cast(p.detach(), dtype)
-    _shadow_cache[key] = (ver, s, p.data_ptr())
+    _shadow_cache[key] = (ver, s, p.data_ptr(), weakref.ref(p, lambda _r, key=key: _shadow_cache.pop(key, None)))
     return s
 
 
@@ -41,13 +49,14 @@ def shadow_cat(ps: Tuple[Optional[Tensor], ...], dtype: torch.dtype, rows_each: 
     key = ("cat", tuple(id(p) for p in ps), dtype)
     ver = tuple((p._version, p.data_ptr()) if p is not None else None for p in ps)
     ent = _shadow_cache.get(key)
-    if ent is not None and ent[0] == ver:
+    if ent is not None and ent[0] == ver and _alive(ent[2], ps):
         return ent[1]
     ref = next(p for p in ps if p is not None)
     parts = [p.detach() if p is not None else ref.new_zeros((rows_each,) + tuple(ref.shape[1:])) for p in ps]
     full = torch.cat(parts, dim=0)
     s = full if full.dtype == dtype else K.cast(full, dtype)
-    _shadow_cache[key] = (ver, s)
+    drop = lambda _r, key=key: _shadow_cache.pop(key, None)
+    _shadow_cache[key] = (ver, s, tuple(None if p is None else weakref.ref(p, drop) for p in ps))
     return s
 
 
@@ -55,17 +64,41 @@ def clear_shadow_cache() -> None:
     _shadow_cache.clear()
 
 
-# Data-parallel runs: id(master weight) -> that weight's fp32 slice of its all-reduce bucket (parallel.GradientAllReducer).
-# A weight-gradient GEMM then writes straight into the bucket (DDP's ``gradient_as_bucket_view``) and the reducer's staging
-# copy disappears.  Handed out only for a fresh gradient (``w.grad is None``): accumulation into an existing ``.grad`` must
-# not alias it.  The returned tensor is a new view object, so autograd's AccumulateGrad adopts it instead of cloning.
+# Data-parallel runs: id(master weight) -> (weakref, that weight's fp32 slice of its all-reduce bucket)
+# (parallel.GradientAllReducer).  A weight-gradient GEMM then writes straight into the bucket (DDP's
+# ``gradient_as_bucket_view``) and the reducer's staging copy disappears.  Handed out only for a fresh gradient
+# (``w.grad is None``) and AT MOST ONCE per backward: a weight used twice in one step (encoder.prompt_proj,
+# whisper_encoder.py:105-106) gets the slot for its first weight-gradient GEMM and a fresh tensor for the others, so
+# autograd sums distinct buffers (two aliases of one slot would give 2x the last contribution).  The reducer clears the
+# mark when the parameter's gradient has been accumulated.  The returned tensor is a new view object, so autograd's
+# AccumulateGrad adopts it instead of cloning.
 GRAD_SLOTS = {}
+GRAD_TAKEN = set()
+
+
+def publish_grad_slot(w: Tensor, slot: Tensor) -> None:
+    key = id(w)
+    GRAD_SLOTS[key] = (weakref.ref(w, lambda _r, key=key: (GRAD_SLOTS.pop(key, None), GRAD_TAKEN.discard(key))), slot)
+
+
+def release_grad_slot(w: Tensor) -> None:
+    GRAD_TAKEN.discard(id(w))
+
+
+def clear_grad_slots() -> None:
+    GRAD_SLOTS.clear()
+    GRAD_TAKEN.clear()
 
 
 def grad_out(w: Tensor) -> Optional[Tensor]:
-    slot = GRAD_SLOTS.get(id(w))
-    if slot is None or w.grad is not None or slot.shape != w.shape or slot.device != w.device:
+    key = id(w)
+    ent = GRAD_SLOTS.get(key)
+    if ent is None or ent[0]() is not w or key in GRAD_TAKEN:
         return None
+    slot = ent[1]
+    if w.grad is not None or slot.shape != w.shape or slot.device != w.device:
+        return None
+    GRAD_TAKEN.add(key)
     return slot.view_as(slot)
 
 
@@ -142,8 +175,12 @@ class _LinearPos(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = K.gemm(dy2, shadow(w, x2.dtype), M=rows, N=Kd, K=N, b_mn=True, ldb=Kd, out_dtype=x2.dtype, impl=impl).view(ctx.in_shape)
-        dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl)
-        return dx, dw, K.colsum(dy2, rows, N), None, None
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl, out=grad_out(w))
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(dy2, rows, N)
+        return dx, dw, db, None, None
 
 
 def linear_pos(x: Tensor, w: Tensor, b: Tensor, table: Tensor, period: int) -> Tensor:
@@ -450,10 +487,17 @@ class _PackedSelfAttention(Function):
         dy2 = dqkv.view(rows, d3)
         w = shadow_cat((wq, wk, wv), x2.dtype)
         dx = K.gemm(dy2, w, M=rows, N=d, K=d3, b_mn=True, ldb=d, out_dtype=x2.dtype).view(B, S, d) if ctx.needs_input_grad[0] else None
-        dw = K.gemm(dy2, x2, M=d3, N=d, K=rows, a_mn=True, b_mn=True, lda=d3, ldb=d, out_dtype=torch.float32)
+        need = ctx.needs_input_grad   # a frozen base (LoRA fine-tuning) skips the weight-gradient GEMM and the column sums
+        dwq = dwk = dwv = dbq = dbv = None
+        if need[1] or need[3] or need[4]:
+            dw = K.gemm(dy2, x2, M=d3, N=d, K=rows, a_mn=True, b_mn=True, lda=d3, ldb=d, out_dtype=torch.float32)
+            dwq, dwk, dwv = dw[:d], dw[d:2 * d], dw[2 * d:]
         # bias gradients of q and v only (Whisper's key projection has none): two d-wide column sums over slices of dqkv
-        dbq, dbv = K.colsum(dy2[:, :d], rows, d, ld=d3), K.colsum(dy2[:, 2 * d:], rows, d, ld=d3)
-        return dx, dw[:d], dbq, dw[d:2 * d], dw[2 * d:], dbv, None, None, None
+        if need[2]:
+            dbq = K.colsum(dy2[:, :d], rows, d, ld=d3)
+        if need[5]:
+            dbv = K.colsum(dy2[:, 2 * d:], rows, d, ld=d3)
+        return dx, dwq, dbq, dwk, dwv, dbv, None, None, None
 
 
 class _PackedCrossAttention(Function):
@@ -487,9 +531,14 @@ class _PackedCrossAttention(Function):
         dy2 = dkv.view(rows, d2)
         w = shadow_cat((wk, wv), xa2.dtype)
         dxa = K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, out_dtype=xa2.dtype).view(B, Sk, d) if ctx.needs_input_grad[1] else None
-        dw = K.gemm(dy2, xa2, M=d2, N=d, K=rows, a_mn=True, b_mn=True, lda=d2, ldb=d, out_dtype=torch.float32)
-        dbv = K.colsum(dy2[:, d:], rows, d, ld=d2)   # the value half only: the key projection has no bias
-        return dq, dxa, dw[:d], dw[d:], dbv, None, None
+        need = ctx.needs_input_grad
+        dwk = dwv = dbv = None
+        if need[2] or need[3]:
+            dw = K.gemm(dy2, xa2, M=d2, N=d, K=rows, a_mn=True, b_mn=True, lda=d2, ldb=d, out_dtype=torch.float32)
+            dwk, dwv = dw[:d], dw[d:]
+        if need[4]:
+            dbv = K.colsum(dy2[:, d:], rows, d, ld=d2)   # the value half only: the key projection has no bias
+        return dq, dxa, dwk, dwv, dbv, None, None
 
 
 def packed_attention_ok(x: Tensor, n_head: int) -> bool:
@@ -554,9 +603,11 @@ class _ConvK3Gelu(Function):
         impl = _impl_for(dt)
         rows = B * To
         dpre = K.gelu_bwd(pre, dy.reshape(rows, D))
-        dw = K.gemm(dpre, col, M=D, N=3 * C, K=rows, a_mn=True, b_mn=True, lda=D, ldb=3 * C, out_dtype=torch.float32, impl=impl).view(D, C, 3)
-        db = K.colsum(dpre, rows, D)
-        dx = None
+        dw = db = dx = None
+        if ctx.needs_input_grad[1]:
+            dw = K.gemm(dpre, col, M=D, N=3 * C, K=rows, a_mn=True, b_mn=True, lda=D, ldb=3 * C, out_dtype=torch.float32, impl=impl).view(D, C, 3)
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(dpre, rows, D)
         if ctx.needs_input_grad[0]:
             assert not channels_first, "input gradient is only needed for the time-major (second) conv"
             dcol = K.gemm(dpre, shadow(w, dt).view(D, 3 * C), M=rows, N=3 * C, K=D, b_mn=True, ldb=3 * C, out_dtype=dt, impl=impl)

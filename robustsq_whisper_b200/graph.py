@@ -7,6 +7,8 @@ replayed: the host's per-step work shrinks to the utt-id parsing + negative samp
 async copies into the graph's static input buffers and one ``cudaGraphLaunch``.
 
 Contract (what a trainer must know):
+  * host batches passed in pinned memory are copied asynchronously: do not rewrite a pinned input buffer until the step
+    that consumed it has run (rotate buffers as ``enroll_pipeline.DevicePrefetcher`` does, or pass device tensors);
   * every batch must have the captured shapes (ESPnet's collate pads to the batch maximum; pad/bucket to fixed lengths);
   * ``.grad`` tensors live inside the graph's memory pool and are *overwritten* by each replay (the semantics of
     ``zero_grad(set_to_none=True); loss.backward()``), do not ``zero_grad()`` them away;
@@ -46,8 +48,13 @@ class GraphedTrainStep:
         B = self.static["speech"].shape[0]
         self.neg_idx = torch.zeros((B, model.num_negatives), dtype=torch.int64, device=dev)
         self.labels = torch.zeros((B,), dtype=torch.int64, device=dev)
-        self._pin_neg = torch.zeros((B, model.num_negatives), dtype=torch.int64).pin_memory()
-        self._pin_lab = torch.zeros((B,), dtype=torch.int64).pin_memory()
+        # pinned staging for the two host-made tables: a ring of slots, each guarded by the event recorded after its
+        # H2D copies.  The host runs ahead of the stream (no sync between steps), so a single staging buffer would be
+        # rewritten with step i+1's tables before the copy of step i has executed
+        self._ring = [(torch.zeros((B, model.num_negatives), dtype=torch.int64).pin_memory(), torch.zeros((B,), dtype=torch.int64).pin_memory(),
+                       torch.cuda.Event()) for _ in range(3)]
+        self._ring_pos = 0
+        self._ring_used = [False] * len(self._ring)
         self._host_side(example["utt_id"], example.get("neg_idx"))
         # warm-up on a side stream: lazy heads, allocator steady state, kernel attributes, the reducer's bucket layout
         side = torch.cuda.Stream(device=dev)
@@ -87,13 +94,26 @@ class GraphedTrainStep:
     def _host_side(self, utt_id: List[str], neg_idx: Optional[Tensor] = None) -> None:
         """The reference's host work: utt-id parsing -> batch-local speaker labels and the sampled negative indices."""
         m = self.model
+        labels = None
         if neg_idx is None and m.contrastive_weight > 0.0:
-            _, neg_idx = m._negatives(utt_id)
+            if m._gathering():
+                _, neg_idx, labels = m._global_negatives(utt_id)
+            else:
+                _, neg_idx = m._negatives(utt_id)
+        if labels is None:
+            labels = get_speaker_labels(utt_id, m.is_wsj2mix, m.is_ami)
+        i = self._ring_pos
+        self._ring_pos = (i + 1) % len(self._ring)
+        pin_neg, pin_lab, done = self._ring[i]
+        if self._ring_used[i]:
+            done.synchronize()   # the copies that last read this slot have executed (they were queued len(ring) steps ago)
         if neg_idx is not None:
-            self._pin_neg.copy_(neg_idx)
-            self.neg_idx.copy_(self._pin_neg, non_blocking=True)
-        self._pin_lab.copy_(get_speaker_labels(utt_id, m.is_wsj2mix, m.is_ami))
-        self.labels.copy_(self._pin_lab, non_blocking=True)
+            pin_neg.copy_(neg_idx)
+            self.neg_idx.copy_(pin_neg, non_blocking=True)
+        pin_lab.copy_(labels)
+        self.labels.copy_(pin_lab, non_blocking=True)
+        done.record()
+        self._ring_used[i] = True
 
     # ------------------------------------------------------------------ the step
     def __call__(self, speech: Tensor, speech_lengths: Tensor, text: Tensor, text_lengths: Tensor, enroll: Tensor, enroll_lengths: Tensor,

@@ -14,6 +14,8 @@ import torch.distributed as dist
 from torch import Tensor
 from torch.autograd import Function
 
+from . import functional as _F
+
 
 class _AllGatherWithGrad(Function):
     @staticmethod
@@ -117,6 +119,7 @@ class GradientAllReducer:
             return
         b, i = ent
         self._stage(b, i)
+        _F.release_grad_slot(p)   # the slot may be handed to next step's first weight-gradient GEMM again
         b.ready += 1
         if b.ready == len(b.params):
             self._launch(b)
@@ -141,13 +144,26 @@ class GradientAllReducer:
                 b.flat.div_(world)
             for i, p in enumerate(b.params):
                 p.grad = b.flat[b.offsets[i]:b.offsets[i] + p.numel()].view_as(p)
+                _F.release_grad_slot(p)
             b.work, b.ready = None, 0
         if not self._slots_published:
             # from the next step on, weight-gradient GEMMs of the matrices write into their bucket slice directly
             # (functional.grad_out): no staging copy for them
-            from . import functional as F
             for b in self._buckets:
                 for i, p in enumerate(b.params):
                     if p.dim() == 2 and p.dtype == torch.float32:
-                        F.GRAD_SLOTS[id(p)] = b.flat[b.offsets[i]:b.offsets[i] + p.numel()].view_as(p)
+                        _F.publish_grad_slot(p, b.flat[b.offsets[i]:b.offsets[i] + p.numel()].view_as(p))
             self._slots_published = True
+
+    def close(self) -> None:
+        """Detach from the parameters: remove the hooks and withdraw the published bucket slices (call before building
+        another reducer over the same model)."""
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        if self._buckets is not None:
+            for b in self._buckets:
+                for p in b.params:
+                    _F.GRAD_SLOTS.pop(id(p), None)
+                    _F.release_grad_slot(p)
+        self._slots_published = False

@@ -258,6 +258,41 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
         neg_weight = torch.softmax(torch.ones_like(sim).masked_fill_(sim == 1, -10000), dim=1)
         return neg_weight, torch.multinomial(neg_weight, self.num_negatives, replacement=True)
 
+    def _gathering(self) -> bool:
+        dist = torch.distributed
+        return self.gather_negatives and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _host_group(self):
+        """Process group for the per-step host-side exchange of speaker strings: gloo (CPU objects, no device sync); under
+        an NCCL default group a gloo side group is created once, collectively, on the first gathered step."""
+        dist = torch.distributed
+        if dist.get_backend() == "gloo":
+            return None
+        if getattr(self, "_gloo_group", None) is None:
+            self._gloo_group = dist.new_group(backend="gloo")
+        return self._gloo_group
+
+    def _global_negatives(self, utt_id: List[str]) -> Tuple[Tensor, Tensor, Tensor]:
+        """Data-parallel extension: the speakers of every rank's utterances are exchanged on the host, the
+        same-speaker mask is built against the GLOBAL pool (world * B items, rank-major like the all-gathered embeddings)
+        and the negatives are drawn in the global index space.  -> (neg_weight (B, world*B), neg_idx (B, K), speaker labels
+        (B,) in first-seen order over the global batch).  With equal per-rank batches this is the reference's computation
+        (:563-570,:693-697,:73-94) on the concatenated global batch, restricted to this rank's rows."""
+        dist = torch.distributed
+        world, rank = dist.get_world_size(), dist.get_rank()
+        mine = [_speaker_of(u, self.is_wsj2mix, self.is_ami) for u in utt_id]
+        gathered: List[Optional[List[str]]] = [None] * world
+        dist.all_gather_object(gathered, mine, group=self._host_group())
+        B = len(mine)
+        if any(len(g) != B for g in gathered):
+            raise ValueError("gather_negatives needs the same per-rank batch size on every rank")
+        table: Dict[str, int] = {}
+        codes = np.fromiter((table.setdefault(s, len(table)) for g in gathered for s in g), dtype=np.int64, count=world * B)
+        sim = torch.from_numpy((codes[rank * B:(rank + 1) * B, None] == codes[None, :]).astype(np.float32))
+        neg_weight = torch.softmax(torch.ones_like(sim).masked_fill_(sim == 1, -10000), dim=1)
+        neg_idx = torch.multinomial(neg_weight, self.num_negatives, replacement=True)
+        return neg_weight, neg_idx, torch.from_numpy(codes[rank * B:(rank + 1) * B].copy())
+
     def _calc_w2v2_contrastive_loss(self, spk_prompt: Tensor, enroll_emb: Tensor, neg_weight: Tensor, neg_idx: Optional[Tensor] = None,
                                     pooled: Optional[Tensor] = None):
         """Arc-InfoNCE (:659-736)."""
@@ -269,10 +304,12 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
         dev = pooled.device
         pos_index = torch.arange(B, device=dev)
         pool = pooled
-        if self.gather_negatives and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+        if self._gathering():
             from .parallel import all_gather_with_grad
             pool = all_gather_with_grad(pooled)
             pos_index = pos_index + torch.distributed.get_rank() * B
+        if not neg_idx.is_cuda and neg_idx.numel() and (int(neg_idx.min()) < 0 or int(neg_idx.max()) >= pool.size(0)):
+            raise IndexError(f"neg_idx must index the candidate pool of {pool.size(0)} embeddings (got [{int(neg_idx.min())}, {int(neg_idx.max())}])")
         loss, nc = F.arc_infonce(spk_prompt, pool, pos_index, neg_idx.to(dev), self.infonce_margin, self.contrastive_temp)
         return loss, nc.float() / float(B)
 
@@ -299,14 +336,19 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
         utt_id = kwargs.get("utt_id")
 
         neg_idx = kwargs.get("neg_idx")
+        speaker_labels = kwargs.get("speaker_labels")   # precomputed on the host by graph.GraphedTrainStep
         neg_weight = None
-        if self.contrastive_weight > 0.0:
-            if neg_idx is None:
+        if self.contrastive_weight > 0.0 and neg_idx is None:
+            if self._gathering():   # negatives and speaker labels over the global batch
+                neg_weight, neg_idx, labels_global = self._global_negatives(utt_id)
+                if speaker_labels is None:
+                    speaker_labels = labels_global
+            else:
                 neg_weight, neg_idx = self._negatives(utt_id)
         encoder_out, encoder_out_lens, spk_prompt, enroll_embedding = self.encode(speech, speech_lengths, enroll, enroll_lengths)
-        speaker_labels = kwargs.get("speaker_labels")   # precomputed on the host by graph.GraphedTrainStep
         if speaker_labels is None:
-            speaker_labels = get_speaker_labels(utt_id, self.is_wsj2mix, self.is_ami).to(enroll_embedding.device)
+            speaker_labels = get_speaker_labels(utt_id, self.is_wsj2mix, self.is_ami)
+        speaker_labels = speaker_labels.to(enroll_embedding.device, non_blocking=True)
 
         stats: Dict[str, Optional[Tensor]] = dict()
         loss_con = loss_aam = None

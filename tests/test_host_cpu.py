@@ -159,14 +159,50 @@ def _gloo_worker(rank, world, port_no, q):
                 dw = out
             return gy @ w, dw
 
-    slot = Fn.GRAD_SLOTS.get(id(lin1.weight))
+    ent = Fn.GRAD_SLOTS.get(id(lin1.weight))
+    slot = None if ent is None else ent[1]
     ok_slot = slot is not None and slot.shape == lin1.weight.shape and Fn.grad_out(lin1.weight) is None    # .grad still set: no aliasing
     for prm in params:
         prm.grad = None
     xin = torch.full((2, 4), float(rank + 1))
-    _WriteIntoSlot.apply(xin, lin1.weight).sum().backward()
+    (_WriteIntoSlot.apply(xin, lin1.weight).sum() + lin1.bias.sum() + lin2(xin).sum()).backward()
     ok_slot &= lin1.weight.grad is not None and lin1.weight.grad.data_ptr() == slot.data_ptr()
-    q.put((rank, bool(ok_gather), bool(ok_reduce and ok_overlap and ok_slot)))
+    red.reduce()
+    # a weight applied TWICE in one step (encoder.prompt_proj, whisper_encoder.py:105-106): the slot goes to one use only,
+    # the other use gets its own buffer, and the all-reduced gradient is the mean over ranks of the SUM of both uses
+    for step in range(2):
+        for prm in params:
+            prm.grad = None
+        xa = torch.full((2, 4), float(rank + 1 + step))
+        xb = torch.arange(8, dtype=torch.float32).view(2, 4) * (rank + 2)
+        (_WriteIntoSlot.apply(xa, lin1.weight).sum() + 3.0 * _WriteIntoSlot.apply(xb, lin1.weight).sum() + lin1.bias.sum()
+         + lin2(xa).sum()).backward()
+        red.reduce()
+        want = torch.zeros_like(lin1.weight)
+        for r in range(world):
+            ra = torch.full((2, 4), float(r + 1 + step))
+            rb = torch.arange(8, dtype=torch.float32).view(2, 4) * (r + 2)
+            want += (torch.ones(4, 2) @ ra + 3.0 * torch.ones(4, 2) @ rb) / world
+        ok_slot &= torch.allclose(lin1.weight.grad, want, atol=1e-5)
+        ok_slot &= id(lin1.weight) not in Fn.GRAD_TAKEN
+    # Arc-InfoNCE negatives over the GLOBAL pool (gather_negatives): mask and indices in the global index space, speaker
+    # labels in first-seen order over the concatenated batch == the single-process parse of all ranks' utt ids
+    from types import SimpleNamespace
+    from robustsq_whisper_b200 import synth as _synth
+    from robustsq_whisper_b200 import ts_qformer_espnet_model as M
+    Bl = 6
+    stub = SimpleNamespace(is_wsj2mix=False, is_ami=False, num_negatives=40, _host_group=lambda: None)
+    all_ids = _synth.make_utt_ids(world * Bl)
+    torch.manual_seed(100 + rank)
+    nw, ni, labels = M.TgtSpkQformerESPnetASRModel_V4._global_negatives(stub, all_ids[rank * Bl:(rank + 1) * Bl])
+    glob_w = M.get_similarity_weight(all_ids)[rank * Bl:(rank + 1) * Bl]
+    glob_lab = M.get_speaker_labels(all_ids)
+    ok_neg = nw.shape == (Bl, world * Bl) and ni.shape == (Bl, 40) and int(ni.min()) >= 0 and int(ni.max()) < world * Bl
+    ok_neg &= bool(((nw == 0) == (glob_w == 1)).all())
+    ok_neg &= not bool(torch.gather(glob_w, 1, ni).any())            # no same-speaker false negative, on any rank
+    ok_neg &= bool((ni >= Bl).any()) and bool((ni < Bl).any())       # negatives really come from both ranks' items
+    ok_neg &= torch.equal(labels, glob_lab[rank * Bl:(rank + 1) * Bl])
+    q.put((rank, bool(ok_gather and ok_neg), bool(ok_reduce and ok_overlap and ok_slot)))
     dist.destroy_process_group()
 
 
