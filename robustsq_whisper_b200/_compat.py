@@ -27,6 +27,54 @@ except Exception:
         pass
 
 
+try:  # pragma: no cover - ESPnet is absent in the build image (tests install a stand-in under this module name)
+    from espnet2.asr.espnet_model import ESPnetASRModel as ESPnetASRModelBase  # type: ignore
+    HAVE_ESPNET_MODEL = True
+except Exception:
+    HAVE_ESPNET_MODEL = False
+
+    class ESPnetASRModelBase(nn.Module):
+        """Stand-in for ``espnet2.asr.espnet_model.ESPnetASRModel`` (⊂ ``AbsESPnetModel``) when ESPnet is not
+        installed: the constructor attributes and the two feature helpers the TS-ASR models inherit from it
+        (reference model/ts_qformer_espnet_model.py:131-157 passes exactly these keywords up;
+        ``collect_feats`` / ``_extract_feats`` are what asr.sh stage 10 (collect_stats) and ``encode`` :272 call)."""
+
+        def __init__(self, vocab_size, token_list, frontend, specaug, normalize, preencoder, encoder, postencoder, decoder, ctc,
+                     joint_network, aux_ctc=None, ctc_weight=0.5, interctc_weight=0.0, ignore_id=-1, lsm_weight=0.0,
+                     length_normalized_loss=False, report_cer=True, report_wer=True, sym_space="<space>", sym_blank="<blank>",
+                     sym_sos="<sos/eos>", sym_eos="<sos/eos>", extract_feats_in_collect_stats=True, lang_token_id=-1):
+            assert 0.0 <= ctc_weight <= 1.0, ctc_weight
+            super().__init__()
+            token_list = list(token_list)
+            self.blank_id = token_list.index(sym_blank) if sym_blank in token_list else 0
+            self.sos = token_list.index(sym_sos) if sym_sos in token_list else vocab_size - 1
+            self.eos = token_list.index(sym_eos) if sym_eos in token_list else vocab_size - 1
+            self.vocab_size = vocab_size
+            self.ignore_id = ignore_id
+            self.ctc_weight = ctc_weight
+            self.interctc_weight = interctc_weight
+            self.aux_ctc = aux_ctc
+            self.token_list = token_list
+            self.frontend, self.specaug, self.normalize = frontend, specaug, normalize
+            self.preencoder, self.postencoder = preencoder, postencoder
+            self.encoder, self.decoder = encoder, decoder
+            self.ctc = None if ctc_weight == 0.0 else ctc
+            self.error_calculator = None   # report_cer / report_wer need a tokenizer: evaluation-time only
+            self.extract_feats_in_collect_stats = extract_feats_in_collect_stats
+            self.lang_token_id = None if lang_token_id == -1 else torch.tensor([[lang_token_id]])
+
+        def _extract_feats(self, speech, speech_lengths):
+            assert speech_lengths.dim() == 1, speech_lengths.shape
+            speech = speech[:, : int(speech_lengths.max())]   # for data-parallel
+            if self.frontend is not None:
+                return self.frontend(speech, speech_lengths)
+            return speech, speech_lengths                      # no frontend: raw audio is the feature
+
+        def collect_feats(self, speech, speech_lengths, text, text_lengths, **kwargs):
+            feats, feats_lengths = self._extract_feats(speech, speech_lengths)
+            return {"feats": feats, "feats_lengths": feats_lengths}
+
+
 def compute_dtype(explicit) -> torch.dtype:
     """bf16 when the trainer runs the step under CUDA autocast (ESPnet ``use_amp``), else fp32; an explicit
     ``module.compute_dtype`` wins."""

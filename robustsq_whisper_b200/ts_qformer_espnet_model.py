@@ -25,7 +25,7 @@ from torch import Tensor, nn
 
 from . import functional as F
 from . import kernels as K
-from ._compat import compute_dtype, force_gatherable
+from ._compat import ESPnetASRModelBase, compute_dtype, force_gatherable
 
 
 def _capturing(t: Tensor) -> bool:
@@ -101,8 +101,103 @@ class AttentiveStatisticsPooling(nn.Module):
         return F.asp_pool(x, self.gamma, self.projection.weight, self.projection.bias)
 
 
-class TgtSpkQformerESPnetASRModel_V4(nn.Module):
-    """CTC-attention hybrid Encoder-Decoder model (TS-ASR, SQ-Former prompt, ASP + AAM-Softmax + Arc-InfoNCE)."""
+class TgtSpkQformerESPnetASRModel_V2(ESPnetASRModelBase):
+    """CTC-attention hybrid Encoder-Decoder model (TS-ASR with the SQ-Former prompt; attention loss only, :97-335).
+    Subclasses ``espnet2.asr.espnet_model.ESPnetASRModel`` (⊂ ``AbsESPnetModel``) when ESPnet is importable, so that
+    ESPnet's task accepts it and ``collect_feats`` (asr.sh stage 10) is inherited; a stand-in with the same attributes
+    otherwise (_compat.py)."""
+
+    def __init__(
+        self,
+        vocab_size: int,
+        token_list: Union[Tuple[str, ...], List[str]],
+        frontend,
+        specaug,
+        normalize,
+        preencoder,
+        encoder,
+        postencoder,
+        decoder,
+        ctc,
+        joint_network,
+        aux_ctc: dict = None,
+        ctc_weight: float = 0.5,
+        interctc_weight: float = 0.0,
+        ignore_id: int = -1,
+        lsm_weight: float = 0.0,
+        length_normalized_loss: bool = False,
+        report_cer: bool = True,
+        report_wer: bool = True,
+        sym_space: str = "<space>",
+        sym_blank: str = "<blank>",
+        sym_sos: str = "<sos/eos>",
+        sym_eos: str = "<sos/eos>",
+        extract_feats_in_collect_stats: bool = True,
+        lang_token_id: int = -1,
+        **kwargs,
+    ):
+        assert 0.0 <= ctc_weight <= 1.0, ctc_weight
+        if ctc_weight != 0.0:
+            raise NotImplementedError("the CTC branch is outside the TS-ASR hot path (Whisper recipes train with ctc_weight = 0)")
+        for name, mod in (("frontend", frontend), ("specaug", specaug), ("normalize", normalize), ("preencoder", preencoder), ("postencoder", postencoder)):
+            if mod is not None:
+                raise NotImplementedError(f"{name} must be None on this path (raw 16 kHz audio goes straight to the Whisper encoder)")
+        super().__init__(
+            vocab_size=vocab_size, token_list=token_list, frontend=frontend, specaug=specaug, normalize=normalize, preencoder=preencoder,
+            encoder=encoder, postencoder=postencoder, decoder=decoder, ctc=ctc, joint_network=joint_network, aux_ctc=aux_ctc,
+            ctc_weight=ctc_weight, interctc_weight=interctc_weight, ignore_id=ignore_id, lsm_weight=lsm_weight,
+            length_normalized_loss=length_normalized_loss, report_cer=report_cer, report_wer=report_wer, sym_space=sym_space,
+            sym_blank=sym_blank, sym_sos=sym_sos, sym_eos=sym_eos, extract_feats_in_collect_stats=extract_feats_in_collect_stats,
+            lang_token_id=lang_token_id)
+        self.token_list = list(token_list)
+        self.lsm_weight = lsm_weight                      # the fused tied-logits + label-smoothed CE kernel takes these directly
+        self.length_normalized_loss = length_normalized_loss
+        self.error_calculator = None                      # CER / WER reporting is evaluation-time host work (tokenizer), not on this path
+
+    # ------------------------------------------------------------------ encode
+    def encode(self, speech: Tensor, speech_lengths: Tensor, enroll: Tensor, enroll_lengths: Tensor):
+        """Frontend (identity: frontend=None) + encoder (:254-302)."""
+        assert speech_lengths.dim() == 1, speech_lengths.shape
+        if not _capturing(speech):   # under CUDA-graph capture the batch geometry is static (and .max() would be a host sync)
+            speech = speech[:, : int(speech_lengths.max())]
+            enroll = enroll[:, : int(enroll_lengths.max())]
+        return self.encoder(speech, speech_lengths, enroll, enroll_lengths)
+
+    def _calc_att_loss(self, encoder_out: Tensor, encoder_out_lens: Tensor, ys_pad: Tensor, ys_pad_lens: Tensor, spk_prompt: Tensor):
+        """:304-335 with the decoder's vocabulary GEMM, LabelSmoothingLoss and th_accuracy fused (K10)."""
+        ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
+        hidden = self.decoder.hidden_for_loss(encoder_out, ys_in_pad, spk_prompt)
+        loss_sum, counts = F.tied_logits_lsce(hidden, self.decoder.decoders.token_embedding.weight, ys_out_pad, self.ignore_id, self.lsm_weight)
+        if self.length_normalized_loss:
+            loss_att = loss_sum / counts[1].clamp(min=1).float()
+        else:
+            loss_att = F.scale(loss_sum, 1.0 / ys_pad.size(0))
+        acc_att = counts[0].float() / counts[1].clamp(min=1).float()
+        return loss_att, acc_att, None, None
+
+    @staticmethod
+    def _check_batch(speech, speech_lengths, text, text_lengths, enroll, enroll_lengths):
+        assert text_lengths.dim() == 1, text_lengths.shape
+        assert (speech.shape[0] == speech_lengths.shape[0] == text.shape[0] == text_lengths.shape[0] == enroll.shape[0]
+                == enroll_lengths.shape[0]), (speech.shape, speech_lengths.shape, text.shape, text_lengths.shape, enroll.shape, enroll_lengths.shape)
+
+    def forward(self, speech: Tensor, speech_lengths: Tensor, text: Tensor, text_lengths: Tensor, enroll: Tensor,
+                enroll_lengths: Tensor, **kwargs) -> Tuple[Tensor, Dict[str, Tensor], Tensor]:
+        """Frontend + Encoder + Decoder + attention loss (:160-252; the CTC branch :214-226 is not built)."""
+        self._check_batch(speech, speech_lengths, text, text_lengths, enroll, enroll_lengths)
+        batch_size = speech.shape[0]
+        text[text == -1] = self.ignore_id          # in place, like the reference (:200)
+        if not _capturing(text):
+            text = text[:, : int(text_lengths.max())]  # for data-parallel (:203)
+        encoder_out, encoder_out_lens, spk_prompt, _ = self.encode(speech, speech_lengths, enroll, enroll_lengths)
+        loss_att, acc_att, cer_att, wer_att = self._calc_att_loss(encoder_out, encoder_out_lens, text, text_lengths, spk_prompt)
+        stats: Dict[str, Optional[Tensor]] = dict(loss_att=loss_att.detach(), acc=acc_att, cer=cer_att, wer=wer_att, loss=loss_att.detach())
+        loss, stats, weight = force_gatherable((loss_att, stats, batch_size), loss_att.device)
+        return loss, stats, weight
+
+
+class TgtSpkQformerESPnetASRModel_V4(TgtSpkQformerESPnetASRModel_V2):
+    """V2 + ASP / AAM-Softmax / Arc-InfoNCE enrollment losses (:408-750)."""
 
     def __init__(
         self,
@@ -149,30 +244,13 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
         gather_negatives: bool = False,
         **kwargs,
     ):
-        assert 0.0 <= ctc_weight <= 1.0, ctc_weight
-        super().__init__()
-        if ctc_weight != 0.0:
-            raise NotImplementedError("the CTC branch is outside the TS-ASR hot path (Whisper recipes train with ctc_weight = 0)")
-        for name, mod in (("frontend", frontend), ("specaug", specaug), ("normalize", normalize), ("preencoder", preencoder), ("postencoder", postencoder)):
-            if mod is not None:
-                raise NotImplementedError(f"{name} must be None on this path (raw 16 kHz audio goes straight to the Whisper encoder)")
-        token_list = list(token_list)
-        self.blank_id = token_list.index(sym_blank) if sym_blank in token_list else 0
-        self.sos = token_list.index(sym_sos) if sym_sos in token_list else vocab_size - 1
-        self.eos = token_list.index(sym_eos) if sym_eos in token_list else vocab_size - 1
-        self.vocab_size = vocab_size
-        self.ignore_id = ignore_id
-        self.ctc_weight = ctc_weight
-        self.interctc_weight = interctc_weight
-        self.token_list = token_list
-        self.frontend = self.specaug = self.normalize = self.preencoder = self.postencoder = None
-        self.encoder = encoder
-        self.decoder = decoder
-        self.ctc = None
-        self.lsm_weight = lsm_weight
-        self.length_normalized_loss = length_normalized_loss
-        self.error_calculator = None
-        self.extract_feats_in_collect_stats = extract_feats_in_collect_stats
+        super().__init__(
+            vocab_size=vocab_size, token_list=token_list, frontend=frontend, specaug=specaug, normalize=normalize, preencoder=preencoder,
+            encoder=encoder, postencoder=postencoder, decoder=decoder, ctc=ctc, joint_network=joint_network, aux_ctc=aux_ctc,
+            ctc_weight=ctc_weight, interctc_weight=interctc_weight, ignore_id=ignore_id, lsm_weight=lsm_weight,
+            length_normalized_loss=length_normalized_loss, report_cer=report_cer, report_wer=report_wer, sym_space=sym_space,
+            sym_blank=sym_blank, sym_sos=sym_sos, sym_eos=sym_eos, extract_feats_in_collect_stats=extract_feats_in_collect_stats,
+            lang_token_id=lang_token_id)
 
         self.contrastive_type = contrastive_type
         self.contrastive_weight = contrastive_weight
@@ -225,28 +303,7 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
             self.asp_pooling.gamma = self.get_current_asp_gamma()
         return self.asp_pooling(enroll_emb)
 
-    # ------------------------------------------------------------------ encode
-    def encode(self, speech: Tensor, speech_lengths: Tensor, enroll: Tensor, enroll_lengths: Tensor):
-        """Frontend (identity: frontend=None) + encoder (:254-302)."""
-        assert speech_lengths.dim() == 1, speech_lengths.shape
-        if not _capturing(speech):   # under CUDA-graph capture the batch geometry is static (and .max() would be a host sync)
-            speech = speech[:, : int(speech_lengths.max())]
-            enroll = enroll[:, : int(enroll_lengths.max())]
-        return self.encoder(speech, speech_lengths, enroll, enroll_lengths)
-
     # ------------------------------------------------------------------ losses
-    def _calc_att_loss(self, encoder_out: Tensor, encoder_out_lens: Tensor, ys_pad: Tensor, ys_pad_lens: Tensor, spk_prompt: Tensor):
-        """:304-335 with the decoder's vocabulary GEMM, LabelSmoothingLoss and th_accuracy fused (K10)."""
-        ys_in_pad, ys_out_pad = add_sos_eos(ys_pad, self.sos, self.eos, self.ignore_id)
-        hidden = self.decoder.hidden_for_loss(encoder_out, ys_in_pad, spk_prompt)
-        loss_sum, counts = F.tied_logits_lsce(hidden, self.decoder.decoders.token_embedding.weight, ys_out_pad, self.ignore_id, self.lsm_weight)
-        if self.length_normalized_loss:
-            loss_att = loss_sum / counts[1].clamp(min=1).float()
-        else:
-            loss_att = F.scale(loss_sum, 1.0 / ys_pad.size(0))
-        acc_att = counts[0].float() / counts[1].clamp(min=1).float()
-        return loss_att, acc_att, None, None
-
     def _negatives(self, utt_id: List[str]) -> Tuple[Tensor, Tensor]:
         """neg_weight (:563-570) and the sampled indices (:693-697) — CPU RNG, one batched draw (bit-identical)."""
         if self.is_wsj2mix:
@@ -326,9 +383,7 @@ class TgtSpkQformerESPnetASRModel_V4(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, speech: Tensor, speech_lengths: Tensor, text: Tensor, text_lengths: Tensor, enroll: Tensor,
                 enroll_lengths: Tensor, **kwargs) -> Tuple[Tensor, Dict[str, Tensor], Tensor]:
-        assert text_lengths.dim() == 1, text_lengths.shape
-        assert (speech.shape[0] == speech_lengths.shape[0] == text.shape[0] == text_lengths.shape[0] == enroll.shape[0]
-                == enroll_lengths.shape[0]), (speech.shape, speech_lengths.shape, text.shape, text_lengths.shape, enroll.shape, enroll_lengths.shape)
+        self._check_batch(speech, speech_lengths, text, text_lengths, enroll, enroll_lengths)
         batch_size = speech.shape[0]
         text[text == -1] = self.ignore_id          # in place, like the reference (:557)
         if not _capturing(text):
