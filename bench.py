@@ -25,6 +25,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "audio-sec/sec, Whisper-medium TS fwd+bwd"
 UNIT = "audio-s/s"
+# per-GPU batch, mixture seconds, enrollment seconds of BASELINE.json's configs: cfg 4 = the headline
+# (medium), cfg 3 (small, 64 x 30 s), cfg 2 (base, 16 x 20 s), cfg 1 (tiny, 4 x 10 s + 3 s)
+SHAPES = {"medium": (32, 30.0, 10.0), "small": (64, 30.0, 10.0), "base": (16, 20.0, 10.0), "tiny": (4, 10.0, 3.0)}
+
+
+def metric_name(args) -> str:
+    if args.workload == "decode":
+        return f"audio-sec/sec, Whisper-{args.model} TS greedy decode"
+    return f"audio-sec/sec, Whisper-{args.model} TS fwd+bwd"
 
 
 def parse_args():
@@ -33,10 +42,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="medium")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("TSW_BENCH_BATCH", "32")), help="utterances per GPU per step")
-    ap.add_argument("--mix-s", type=float, default=30.0)
-    ap.add_argument("--enr-s", type=float, default=10.0)
+    ap.add_argument("--model", default="medium", choices=sorted(SHAPES), help="medium = the headline (BASELINE configs[3]); small / base / tiny run "
+                    "configs[2] / [1] / [0]'s shapes unless --batch / --mix-s / --enr-s say otherwise")
+    ap.add_argument("--workload", default="train", choices=["train", "decode"], help="train = fwd+bwd step (the headline metric); decode = BASELINE "
+                    "configs[4]'s second half: log-mel -> encoder -> KV-cached beam-1 decoding of --batch utterances per step")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU per step (default: the model's BASELINE config; decode: 128)")
+    ap.add_argument("--mix-s", type=float, default=None)
+    ap.add_argument("--enr-s", type=float, default=None)
+    ap.add_argument("--tokens", type=int, default=None, help="decode: tokens generated per utterance (default 3 per mixture second, the training text length)")
+    ap.add_argument("--selfcheck", action="store_true", help="under torchrun (N > 1): check that N ranks x B == one process on the concatenated "
+                    "batch (losses and all-reduced gradients, robustsq_whisper_b200.selfcheck) and print the errors as one JSON line")
     ap.add_argument("--negatives", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batch", type=int, default=1)
@@ -44,7 +59,15 @@ def parse_args():
                     "(robustsq_whisper_b200.lora); the default 0 is the full fine-tune the headline metric is quoted on")
     ap.add_argument("--graph", action="store_true", help="replay the whole step as one CUDA graph (robustsq_whisper_b200.graph) instead of the eager plugin call; "
                     "measured equal on this host (the step is GPU-bound, inter-kernel gaps ~1 us), so the default stays the reference-facing eager call")
-    return ap.parse_args()
+    args = ap.parse_args()
+    b, m, e = SHAPES[args.model]
+    if args.batch is None:
+        args.batch = int(os.environ.get("TSW_BENCH_BATCH", "0")) or (128 if args.workload == "decode" else b)
+    args.mix_s = m if args.mix_s is None else args.mix_s
+    args.enr_s = e if args.enr_s is None else args.enr_s
+    if args.tokens is None:
+        args.tokens = max(4, int(3 * args.mix_s))
+    return args
 
 
 def peaks():
@@ -115,7 +138,7 @@ def run_reference(args):
     value = args.cpu_batch * args.mix_s / dt
     sample = f"{args.cpu_batch} x ({args.mix_s:g} s + {args.enr_s:g} s) utterances per step, fwd+bwd, fp32, torch CPU, {cores} threads"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"whisper-{args.model} TS-ASR fwd+bwd, {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment", "batch_per_step": args.cpu_batch},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -123,7 +146,176 @@ def run_reference(args):
     }), flush=True)
 
 
+def run_reference_decode(args):
+    """configs[4] decode half on the host CPU: the reference algorithm (port) encodes one utterance and greedy-decodes it
+    by full-prefix recompute (whisper_decoder.py:297-380 has no cache), args.tokens tokens."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import port, synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = port.TSConfig(whisper_model=args.model)
+    sd = port.init_state_dict(cfg, 0)
+    n = args.cpu_batch
+    batch = synth.make_batch(n, args.mix_s, args.enr_s, ragged=False)
+
+    def step():
+        with torch.no_grad():
+            xs, _, prompt, _ = port.encoder_forward(sd, cfg, batch["speech"], batch["speech_lengths"], batch["enroll"], batch["enroll_lengths"])
+            return port.greedy_decode(sd, cfg, xs, prompt, args.tokens)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = n * args.mix_s / dt
+    sample = f"{n} x {args.mix_s:g} s utterance(s) per step: encode + {args.tokens} greedy tokens by full-prefix recompute, fp32, torch CPU, {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"whisper-{args.model} TS-ASR greedy decode, {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment, {args.tokens} tokens / utterance",
+                   "batch_per_step": n, "tokens_per_s": n * args.tokens / dt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
 # ----------------------------------------------------------------------------------------------------------------- CUDA arm
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, torch.device("cuda", local)
+
+
+def run_selfcheck(args):
+    """N ranks x B == one process on the concatenated batch, on the kernels; fp32 regime (tight) and bf16."""
+    import torch
+    import torch.distributed as dist
+    from robustsq_whisper_b200.selfcheck import data_parallel_selfcheck
+    rank, world, local, dev = _dist_setup()
+    if world < 2:
+        raise SystemExit("--selfcheck needs N > 1 ranks (torchrun --nproc-per-node N bench.py --gpus N --selfcheck)")
+    name = args.model if args.model in ("tiny", "base") else "base"   # small enough for a second, single-process pass over N x B
+    out = {"selfcheck": "N ranks x B == one process on the concatenated N*B batch (same sampled negatives)", "n_gpus": world, "model": name}
+    ok = True
+    for dtype, tol_loss, tol_grad in ((torch.float32, 1e-5, 1e-4), (torch.bfloat16, 1e-2, 3e-2)):
+        r = data_parallel_selfcheck(name, batch_per_rank=4, mix_s=6.0, enr_s=3.0, dtype=dtype, num_negatives=6)
+        key = "f32" if dtype == torch.float32 else "bf16"
+        out[key] = {k: v for k, v in r.items() if isinstance(v, (float, str))}
+        good = all(r["rel_" + k] < tol_loss for k in ("loss", "loss_att", "loss_con", "loss_aam")) and r["grad_rel_l2"] < tol_grad
+        out[key]["pass"] = bool(good)
+        ok &= good
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["pass_all_ranks"] = bool(flag.item() == 1.0)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    dist.destroy_process_group()
+    if not out["pass_all_ranks"]:
+        raise SystemExit(1)
+
+
+def run_decode(args):
+    """BASELINE configs[4], decode half: each step decodes --batch utterances (per GPU; 1 024 utterances over 8 GPUs = 128 per
+    GPU) end to end: 16 kHz PCM -> log-mel -> conv stem -> SQ-Former -> encoder -> KV-cached beam-1 decoding of --tokens
+    tokens (prefill + one CUDA-graph replay per token).  The utterances are independent: ranks share nothing (no collective)."""
+    import torch
+    import torch.distributed as dist
+    from robustsq_whisper_b200 import synth
+    from robustsq_whisper_b200 import kernels as K
+    from robustsq_whisper_b200.factory import build_ts_model
+    rank, world, local, dev = _dist_setup()
+    torch.manual_seed(0)
+    model = build_ts_model(args.model, 16, 2).to(dev).eval()
+    model.encoder.compute_dtype = model.decoder.compute_dtype = torch.bfloat16
+    n, T = args.batch, args.tokens
+    batch = synth.make_batch(n, args.mix_s, args.enr_s, seed=1234 + rank, utt_offset=rank * n)
+    keys = ("speech", "speech_lengths", "enroll", "enroll_lengths")
+    pinned = {k: batch[k].pin_memory() for k in keys}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+    out_host = torch.empty((n, T), dtype=torch.long).pin_memory()
+
+    def step(inp):
+        with torch.no_grad():
+            xs, olens, prompt, _ = model.encode(inp["speech"], inp["speech_lengths"], inp["enroll"], inp["enroll_lengths"])
+            return model.decoder.greedy_decode(xs, prompt, model.sos, -1, T)   # eos = -1: every utterance runs its T tokens
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    res = {k: v.to(dev) for k, v in pinned.items()}
+    staged = [{k: v.clone() for k, v in res.items()} for _ in range(args.steps)]
+    for _ in range(max(args.warmup, 3)):
+        step({k: v.clone() for k, v in res.items()})
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    K.LAUNCHES["n"] = 0
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        ids = step(staged[i])
+    e1.record()
+    sync_all()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    launches = K.LAUNCHES["n"] // max(args.steps, 1)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        ids = step({k: v.to(dev, non_blocking=True) for k, v in pinned.items()})
+        out_host[:, : ids.shape[1]].copy_(ids, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the token ids are the result the caller waits for
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3) / args.steps
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    # dominant kernels of the token loop are HBM-bound weight / KV streaming: one token step reads every decoder weight once
+    # (bf16) + the cross-attention K/V of n x 1516 memory rows + the self-attention cache (SURVEY.md §8f n1)
+    d, _, L = {"tiny": (384, 6, 4), "base": (512, 8, 6), "small": (768, 12, 12), "medium": (1024, 16, 24)}[args.model]
+    w_bytes = 2 * (L * (4 * d * d + 4 * d * d + 8 * d * d) + 51865 * d)
+    kv_bytes = 2 * L * 2 * n * (16 + int(args.mix_s * 50)) * d
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+    audio_s = n * world * args.mix_s
+    if rank == 0:
+        pk = peaks()
+        out = {
+            "metric": metric_name(args), "value": audio_s / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"whisper-{args.model} TS-ASR beam-1 decode: log-mel + encoder + {T} KV-cached tokens per utterance, "
+                                   f"{args.mix_s:g}s mixture + {args.enr_s:g}s enrollment", "batch_per_gpu": n, "global_batch": n * world,
+                       "parallelism": f"dp{world} (independent utterances, no collective)", "tokens_per_s": n * world * T / (ms_dev * 1e-3),
+                       "l2_policy": "per-step K/V caches and activations exceed the 126 MB L2; fresh input copies each step"},
+            "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": n * T * 8, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "token step (skinny weight-streaming GEMMs + decode attention), floor = decoder weights + cross/self K/V read once per token",
+                         "bound": "hbm", "achieved": None, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None,
+                         "algorithmic_bytes_per_token_step": w_bytes + kv_bytes, "peak_source": pk["source"]},
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(args):
     """Oracle port timed on this box's host cores on a bounded sample: 1 fwd+bwd step of cpu_batch utterances."""
     import torch
@@ -186,22 +378,11 @@ def run_b200(args):
     h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
     torch.manual_seed(7 + rank)
     K_neg = args.negatives
-
-    def make_negatives():
-        P = B * world
-        # global pool: exclude same-speaker items; utt ids cycle through 8 speakers identically on every rank
-        ids = []
-        for r in range(world):
-            ids += synth.make_utt_ids(B, r * B)
-        from robustsq_whisper_b200.ts_qformer_espnet_model import get_similarity_weight
-        sim = get_similarity_weight(ids)[rank * B:(rank + 1) * B]
-        w = torch.softmax(torch.ones_like(sim).masked_fill_(sim == 1, -10000), dim=1)
-        return torch.multinomial(w, K_neg, replacement=True)
-
     def eager_step(inputs):
         for p in model.parameters():
             p.grad = None
-        loss, stats, weight = model(**inputs, utt_id=batch["utt_id"], neg_idx=make_negatives())
+        # the public call: utt-id parsing, the host exchange of speakers at N > 1 and the negative sampling happen inside
+        loss, stats, weight = model(**inputs, utt_id=batch["utt_id"])
         loss.backward()
         reducer.reduce()
         return loss
@@ -213,13 +394,12 @@ def run_b200(args):
         from robustsq_whisper_b200.graph import GraphedTrainStep
         ex = {k: v.to(dev) for k, v in pinned.items()}
         ex["utt_id"] = batch["utt_id"]
-        ex["neg_idx"] = make_negatives()
         graphed = GraphedTrainStep(model, ex, reducer=reducer if world > 1 else None, warmup=max(args.warmup, 3))
 
     def step(inputs):
         if graphed is None:
             return eager_step(inputs)
-        loss, stats, weight = graphed(**inputs, utt_id=batch["utt_id"], neg_idx=make_negatives())
+        loss, stats, weight = graphed(**inputs, utt_id=batch["utt_id"])
         return loss
 
     def resident_inputs():
@@ -306,7 +486,7 @@ def run_b200(args):
         pk = peaks()
         achieved_tf = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"whisper-{args.model} TS-ASR training step (fwd+bwd), {args.mix_s:g}s mixture + {args.enr_s:g}s enrollment, "
                                    f"q=16, SQ-Former L=2 (dropout 0.1 {'off' if args.graph else 'on'}), K={K_neg} negatives, ASP+AAM+Arc-InfoNCE+LS-CE"
@@ -323,7 +503,8 @@ def run_b200(args):
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on its most frequent shape
                          # (48512 x 1024 x 1024, 288 launches / step) from profiles/r1_gemm_tc_48512x1024x1024.ncu-rep;
                          # algorithmic A + B + D of that launch = 200.9 MB
-                         "traffic": 160.2e6, "traffic_shape": "M=48512 N=1024 K=1024 bf16 (one launch, ncu --set full)",
+                         "traffic": 160.2e6 if args.model == "medium" else None,
+                         "traffic_shape": "M=48512 N=1024 K=1024 bf16 (one launch, ncu --set full)" if args.model == "medium" else None,
                          "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                          "launches_timed": len(tc), "share_of_step": gemm_share, "ms_per_step_while_timed": ms_prof},
             "clocks": sampler.summary(),
@@ -341,7 +522,11 @@ def run_b200(args):
 def main():
     args = parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_decode if args.workload == "decode" else run_reference)(args)
+    elif args.selfcheck:
+        run_selfcheck(args)
+    elif args.workload == "decode":
+        run_decode(args)
     else:
         run_b200(args)
 

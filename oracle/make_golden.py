@@ -41,6 +41,7 @@ GRAD_KEYS = [
     "decoder.decoders.blocks.0.cross_attn.key.weight", "decoder.decoders.blocks.2.attn.out.bias",
     "decoder.decoders.ln.bias", "asp_pooling.projection.weight", "asp_pooling.projection.bias", "aam_classifier.weight",
 ]
+TRAIN_DROPOUT_SEED = 5000   # key of the i-th dropout call in the train-mode fixture: (TRAIN_DROPOUT_SEED + i, 0)
 GRAD_SLICE = lambda g: g.reshape(-1)[:: max(1, g.numel() // 257)][:257]
 
 
@@ -157,6 +158,43 @@ def gen_tiny_model():
     np.savez_compressed(os.path.join(OUT, "tiny_model.npz"), **out)
 
 
+def gen_tiny_model_train():
+    """The same tiny case with the SQ-Former in train() (BertConfig dropout 0.1 active, Qformer.py:86,237,266,353): the
+    real reference draws its nn.Dropout masks from oracle/philox.py (torch.nn.functional.dropout patched for the run), so
+    the port's ``dropout=`` hook and the CUDA kernels (Philox masks by construction) can be checked at the same masks."""
+    from . import philox
+    c = TINY_CASE
+    cfg = port.TSConfig(whisper_model=c["whisper_model"], num_negatives=c["num_negatives"])
+    batch = synth.make_batch(c["batch"], c["mix_s"], c["enr_s"], text_len=c["text_len"], seed=c["seed"])
+    m, sd = reference_model_with_port_weights(cfg, c["weight_seed"], batch, c["epoch"])
+    m.train()
+    drop = philox.PhiloxDropout(0.1, 0.1, TRAIN_DROPOUT_SEED)
+    real = torch.nn.functional.dropout
+    torch.nn.functional.dropout = drop.as_functional_dropout()
+    try:
+        torch.manual_seed(c["rng_seed"])
+        loss, stats, weight = m(**_clone(batch))
+        n_fwd = drop.calls
+        loss.backward()
+        out = {"loss": loss.detach().numpy(), "dropout_calls": np.int64(n_fwd)}
+        for k, v in stats.items():
+            if v is not None:
+                out["stat_" + k] = v.detach().numpy()
+        with torch.no_grad():
+            drop.reset()
+            xs, olens, prompt, enr = m.encode(batch["speech"], batch["speech_lengths"], batch["enroll"], batch["enroll_lengths"])
+            named = dict(enc_out=xs, spk_prompt=prompt, enroll_emb=enr)
+            for k in named:
+                out["act_" + k] = named[k][SLICES[k]].numpy()
+    finally:
+        torch.nn.functional.dropout = real
+    params = dict(m.named_parameters())
+    for k in GRAD_KEYS:
+        out["grad_" + k] = GRAD_SLICE(params[k].grad).numpy()
+        out["gnorm_" + k] = params[k].grad.norm().numpy()
+    np.savez_compressed(os.path.join(OUT, "tiny_model_train.npz"), **out)
+
+
 def gen_parsers():
     ref = harness.load_reference()
     utt = synth.make_utt_ids(12) + ["1088-1240-0099_103-135887-0099_spk2"]
@@ -171,7 +209,13 @@ def gen_parsers():
 
 
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:   # regenerate only the named fixtures, e.g. ``python -m oracle.make_golden tiny_model_train``
+        for name in sys.argv[1:]:
+            globals()["gen_" + name](); print(name, "ok")
+        return
+    gen_tiny_model_train(); print("tiny model (train mode) ok")
     gen_logmel(); print("logmel ok")
     gen_heads(); print("heads ok")
     gen_parsers(); print("parsers ok")

@@ -150,25 +150,35 @@ def conv_out_lens(lens: Tensor, max_pos: int = upstream.N_AUDIO_CTX) -> Tensor:
 
 
 # ----------------------------------------------------------------------------- a3-a7 SQ-Former
-def _bert_attention(p: P, pre: str, hidden: Tensor, add_mask: Tensor, n_head: int, kv: Optional[Tensor] = None) -> Tensor:
-    """Qformer.py:148-268 (BertSelfAttention + BertSelfOutput), dropout off."""
+def _bert_attention(p: P, pre: str, hidden: Tensor, add_mask: Tensor, n_head: int, kv: Optional[Tensor] = None, dropout=None) -> Tensor:
+    """Qformer.py:148-268 (BertSelfAttention + BertSelfOutput).  ``dropout(x, kind)``: the training-mode nn.Dropout of
+    the attention probabilities (:237, kind "attn") and of the output projection (:266, kind "hidden"); None = eval()."""
     src = hidden if kv is None else kv
     q = _heads(_lin(hidden, p, pre + ".self.query"), n_head)
     k = _heads(_lin(src, p, pre + ".self.key"), n_head)
     v = _heads(_lin(src, p, pre + ".self.value"), n_head)
     scores = q @ k.transpose(-1, -2) / math.sqrt(q.size(-1)) + add_mask
-    ctx = (torch.softmax(scores, dim=-1) @ v).permute(0, 2, 1, 3).flatten(start_dim=2)
-    return _ln(_lin(ctx, p, pre + ".output.dense") + hidden, p, pre + ".output.LayerNorm", 1e-12)
+    probs = torch.softmax(scores, dim=-1)
+    if dropout is not None:
+        probs = dropout(probs, "attn")
+    ctx = (probs @ v).permute(0, 2, 1, 3).flatten(start_dim=2)
+    out = _lin(ctx, p, pre + ".output.dense")
+    if dropout is not None:
+        out = dropout(out, "hidden")
+    return _ln(out + hidden, p, pre + ".output.LayerNorm", 1e-12)
 
 
-def _bert_ffn(p: P, pre: str, suffix: str, x: Tensor) -> Tensor:
-    """Qformer.py:329-355,459-467: dense -> gelu -> dense -> LN(x + .)"""
+def _bert_ffn(p: P, pre: str, suffix: str, x: Tensor, dropout=None) -> Tensor:
+    """Qformer.py:329-355,459-467: dense -> gelu -> dense -> dropout (:353) -> LN(x + .)"""
     h = F.gelu(_lin(x, p, f"{pre}.intermediate{suffix}.dense"))
-    return _ln(_lin(h, p, f"{pre}.output{suffix}.dense") + x, p, f"{pre}.output{suffix}.LayerNorm", 1e-12)
+    y = _lin(h, p, f"{pre}.output{suffix}.dense")
+    if dropout is not None:
+        y = dropout(y, "hidden")
+    return _ln(y + x, p, f"{pre}.output{suffix}.LayerNorm", 1e-12)
 
 
 def qformer_adapter(p: P, pre: str, cfg: TSConfig, x: Tensor, x_lens: Tensor, enroll: Tensor, enroll_lens: Tensor,
-                    cross_mask_value: Optional[float] = None) -> Tuple[Tensor, Tensor]:
+                    cross_mask_value: Optional[float] = None, dropout=None) -> Tuple[Tensor, Tensor]:
     """qformer_adapter.py:58-94 + Qformer.py:69-87 (embeddings), :382-467 (layer), :698-787/:886-911 (masks).
 
     tokens = [q learned queries ; Linear(enroll)+sinusoid]; self-attention over all tokens with key-padding
@@ -182,6 +192,8 @@ def qformer_adapter(p: P, pre: str, cfg: TSConfig, x: Tensor, x_lens: Tensor, en
     emb = _lin(enroll, p, bert + ".embeddings.word_embeddings")
     emb = emb + p[bert + ".embeddings.position_embeddings"][: emb.size(1)].to(emb.dtype)
     h = _ln(torch.cat([query, emb], dim=1), p, bert + ".embeddings.LayerNorm", 1e-12)
+    if dropout is not None:   # training mode (BertConfig dropout 0.1): Qformer.py:86; the call order below is the reference's
+        h = dropout(h, "hidden")
 
     enr_keep = ~upstream.make_pad_mask(enroll_lens)
     keep = torch.cat([torch.ones(B, q, dtype=torch.bool), enr_keep], dim=1)
@@ -193,15 +205,16 @@ def qformer_adapter(p: P, pre: str, cfg: TSConfig, x: Tensor, x_lens: Tensor, en
 
     for l in range(cfg.qformer_layers):
         lp = f"{bert}.encoder.layer.{l}"
-        a = _bert_attention(p, lp + ".attention", h, self_mask, nh)
-        qa = _bert_attention(p, lp + ".crossattention", a[:, :q], cross_mask, nh, kv=x)
-        h = torch.cat([_bert_ffn(p, lp, "_query", qa), _bert_ffn(p, lp, "", a[:, q:])], dim=1)
+        a = _bert_attention(p, lp + ".attention", h, self_mask, nh, dropout=dropout)
+        qa = _bert_attention(p, lp + ".crossattention", a[:, :q], cross_mask, nh, kv=x, dropout=dropout)
+        out_q = _bert_ffn(p, lp, "_query", qa, dropout)
+        h = torch.cat([out_q, _bert_ffn(p, lp, "", a[:, q:], dropout)], dim=1)
     return h[:, :q].contiguous(), h[:, q:].contiguous()
 
 
 # ----------------------------------------------------------------------------- a2+a8+a9 encoder
 def encoder_forward(p: P, cfg: TSConfig, speech: Tensor, ilens: Tensor, enroll: Tensor, enroll_lens: Tensor,
-                    pre: str = "encoder", collect: Optional[dict] = None):
+                    pre: str = "encoder", collect: Optional[dict] = None, dropout=None):
     """whisper_encoder.py:506-530 -> :437-504.  Returns (xs (B,q+S,d), olens, spk_prompt (B,q,d), enroll_emb (B,Se,d))."""
     d, n_head, n_layer = cfg.dims
     enc = pre + ".encoders"
@@ -217,7 +230,7 @@ def encoder_forward(p: P, cfg: TSConfig, speech: Tensor, ilens: Tensor, enroll: 
     e = conv_stem(p, enc, efeats)
     assert e.size(1) <= pos.size(0)
     e_lens = conv_out_lens(efeats_lens, pos.size(0))
-    prompt, enroll_emb = qformer_adapter(p, pre + ".qformer", cfg, x, x_lens, e, e_lens)
+    prompt, enroll_emb = qformer_adapter(p, pre + ".qformer", cfg, x, x_lens, e, e_lens, dropout=dropout)
     if collect is not None:
         collect.update(mel=feats, enroll_mel=efeats, conv_mix=x, conv_enroll=e, qf_prompt=prompt, qf_enroll=enroll_emb)
     if (pre + ".prompt_proj.weight") in p:
@@ -361,11 +374,12 @@ def att_loss(p: P, cfg: TSConfig, enc_out: Tensor, ys_pad: Tensor, spk_prompt: T
 
 # ----------------------------------------------------------------------------- a14 model forward
 def model_forward(p: P, cfg: TSConfig, batch: dict, epoch: int = 0, collect: Optional[dict] = None,
-                  neg_idx: Optional[Tensor] = None):
+                  neg_idx: Optional[Tensor] = None, dropout=None, labels: Optional[Tensor] = None):
     """ts_qformer_espnet_model.py:516-657 with ctc_weight == 0.  Returns (loss (1,), stats, weight (1,)).
 
     ``neg_idx``: pass pre-sampled negatives (B,K) to bypass the CPU RNG; otherwise they are drawn
     exactly as the reference does (:693-697) from the global torch CPU generator.
+    ``dropout``: the SQ-Former's training-mode dropout as a callable (see ``_bert_attention``); None = ``qformer.eval()``.
     """
     speech, speech_lengths = batch["speech"], batch["speech_lengths"]
     text, text_lengths = batch["text"], batch["text_lengths"]
@@ -380,8 +394,10 @@ def model_forward(p: P, cfg: TSConfig, batch: dict, epoch: int = 0, collect: Opt
 
     speech = speech[:, : speech_lengths.max()]
     enroll = enroll[:, : enroll_lengths.max()]
-    enc_out, enc_lens, prompt, enroll_emb = encoder_forward(p, cfg, speech, speech_lengths, enroll, enroll_lengths, collect=collect)
-    labels = speaker_labels(utt_id, cfg.is_wsj2mix, cfg.is_ami)
+    enc_out, enc_lens, prompt, enroll_emb = encoder_forward(p, cfg, speech, speech_lengths, enroll, enroll_lengths, collect=collect,
+                                                            dropout=dropout)
+    if labels is None:
+        labels = speaker_labels(utt_id, cfg.is_wsj2mix, cfg.is_ami)
 
     gamma = current_asp_gamma(cfg, epoch)
     stats: Dict[str, object] = {}

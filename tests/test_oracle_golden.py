@@ -116,3 +116,34 @@ def test_tiny_model_matches_reference_fixture(golden_dir):
     with torch.no_grad():
         ids = port.greedy_decode(sd, cfg, col["enc_out"], col["spk_prompt"], 6)
     assert np.array_equal(ids.numpy(), gold["greedy_ids"])
+
+
+def test_tiny_model_train_mode_matches_reference_fixture(golden_dir):
+    """SQ-Former in train() (dropout 0.1 at Qformer.py:86,237,266,353): the fixture was produced by the real reference
+    with its nn.Dropout masks drawn from oracle/philox.py; the port's ``dropout=`` hook at the same masks must agree —
+    this pins the port's dropout sites and their call order."""
+    from oracle import philox
+    gold = _load(golden_dir, "tiny_model_train.npz")
+    c = make_golden.TINY_CASE
+    cfg = port.TSConfig(whisper_model=c["whisper_model"], num_negatives=c["num_negatives"])
+    batch = synth.make_batch(c["batch"], c["mix_s"], c["enr_s"], text_len=c["text_len"], seed=c["seed"])
+    sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in port.init_state_dict(cfg, c["weight_seed"]).items()}
+    drop = philox.PhiloxDropout(0.1, 0.1, make_golden.TRAIN_DROPOUT_SEED)
+    torch.manual_seed(c["rng_seed"])
+    col = {}
+    loss, stats, _ = port.model_forward(sd, cfg, batch, epoch=c["epoch"], collect=col, dropout=drop)
+    assert drop.calls == int(gold["dropout_calls"]) == 1 + 2 * 6          # embeddings + 6 sites per SQ-Former layer
+    assert loss.item() == pytest.approx(gold["loss"].item(), rel=2e-5)
+    eval_gold = _load(golden_dir, "tiny_model.npz")
+    assert abs(gold["loss"].item() - eval_gold["loss"].item()) > 1e-4 * abs(eval_gold["loss"].item())   # dropout really acted
+    for k in ("loss_con", "loss_aam", "loss_att", "acc", "acc_con", "acc_aam"):
+        assert float(stats[k]) == pytest.approx(gold["stat_" + k].item(), rel=2e-5, abs=1e-7), k
+    for k in ("enc_out", "spk_prompt", "enroll_emb"):
+        got = col[k][make_golden.SLICES[k]].detach().numpy()
+        ref = gold["act_" + k]
+        assert np.abs(got - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max()), k
+    loss.backward()
+    for k in make_golden.GRAD_KEYS:
+        got = make_golden.GRAD_SLICE(sd[k].grad).numpy()
+        ref = gold["grad_" + k]
+        assert np.abs(got - ref).max() <= 1e-3 * max(np.abs(ref).max(), 1e-6) + 1e-7, k
