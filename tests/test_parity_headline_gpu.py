@@ -58,16 +58,25 @@ def test_headline_shapes_bf16_vs_port(name, mix_s, enr_s):
     assert torch.equal(olens.cpu(), col["enc_lens"])
     S = 16 + int(mix_s * 50)
     assert xs.shape == (B, S, cfg.dims[0]) and prompt.shape == (B, 16, cfg.dims[0]) and enr.shape == (B, int(enr_s * 50), cfg.dims[0])
+    # worst single element: 2e-2 of the tensor's max; 3e-2 after medium's 24 layers (measured 2.4e-2 on enc_out: the
+    # residual stream is rounded to bf16 after each of the 48 residual adds, as it is in the reference under autocast)
+    tol_max = 3e-2 if name == "medium" else 2e-2
     for got, key in ((xs, "enc_out"), (prompt, "spk_prompt"), (enr, "enroll_emb")):
         ref = col[key].detach()
-        err = (got.float().cpu() - ref).abs().max().item()
-        assert err <= 2e-2 * ref.abs().max().item(), (key, err, ref.abs().max().item())
+        diff = got.float().cpu() - ref
+        err = diff.abs().max().item()
+        assert err <= tol_max * ref.abs().max().item(), (key, err, ref.abs().max().item())
+        rel_l2 = (diff.double().norm() / ref.double().norm()).item()
+        assert rel_l2 <= 1e-2, (key, rel_l2)   # north-star budget: activations within 1e-2 relative
         # element-wise too: bf16 activations after LayerNorm span a wide dynamic range
         close = torch.isclose(got.float().cpu(), ref, rtol=5e-2, atol=2e-2 * ref.abs().max().item() * 0.25)
         assert close.float().mean().item() > 0.999, key
     params = dict(m.named_parameters())
     worst = ("", 0.0)
     for k in _grad_keys(n_layer):
+        if k not in params:      # encoder.prompt_proj exists only when d != 768 (whisper_encoder.py:430-433): not for small
+            assert name == "small" and "prompt_proj" in k, k
+            continue
         g, r = params[k].grad, sd[k].grad
         assert g is not None and torch.isfinite(g).all(), k
         e = abs(g.float().norm().item() / r.norm().item() - 1.0)
