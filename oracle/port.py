@@ -80,12 +80,12 @@ def log_mel_spectrogram(audio: Tensor, ilens: Optional[Tensor] = None) -> Tuple[
     1e-10 floor -> per-utterance (max - 8) floor -> (x + 4) / 4.
     """
     n_fft, hop = upstream.N_FFT, upstream.HOP_LENGTH
-    window = torch.hann_window(n_fft, dtype=audio.dtype)
+    window = torch.hann_window(n_fft, dtype=audio.dtype, device=audio.device)
     padded = F.pad(audio[:, None, :], (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
     frames = padded.unfold(-1, n_fft, hop)  # (B, 1+N//hop, 400)
     spec = torch.fft.rfft(frames * window, dim=-1)  # (B, F, 201)
     power = (spec.real ** 2 + spec.imag ** 2)[:, :-1].transpose(1, 2)  # (B,201,T)
-    filters = torch.from_numpy(upstream.mel_filterbank()).to(audio.dtype)
+    filters = torch.from_numpy(upstream.mel_filterbank()).to(audio.device, audio.dtype)
     mel = filters @ power
     log_spec = torch.clamp(mel, min=1e-10).log10()
     floor = log_spec.reshape(audio.size(0), -1).max(dim=-1)[0][:, None, None] - 8.0
@@ -195,10 +195,10 @@ def qformer_adapter(p: P, pre: str, cfg: TSConfig, x: Tensor, x_lens: Tensor, en
     if dropout is not None:   # training mode (BertConfig dropout 0.1): Qformer.py:86; the call order below is the reference's
         h = dropout(h, "hidden")
 
-    enr_keep = ~upstream.make_pad_mask(enroll_lens)
-    keep = torch.cat([torch.ones(B, q, dtype=torch.bool), enr_keep], dim=1)
+    enr_keep = (~upstream.make_pad_mask(enroll_lens)).to(h.device)
+    keep = torch.cat([torch.ones(B, q, dtype=torch.bool, device=enr_keep.device), enr_keep], dim=1)
     self_mask = ((1.0 - keep.to(h.dtype)) * -10000.0)[:, None, None, :]
-    mix_keep = (~upstream.make_pad_mask(x_lens)).to(h.dtype)
+    mix_keep = (~upstream.make_pad_mask(x_lens)).to(h.device, h.dtype)
     if cross_mask_value is None:
         cross_mask_value = torch.finfo(h.dtype).min
     cross_mask = ((1.0 - mix_keep) * cross_mask_value)[:, None, None, :]
@@ -273,7 +273,8 @@ def aam_softmax_loss(pooled: Tensor, class_weight: Tensor, labels: Tensor, margi
     """ts_qformer_espnet_model.py:370-405.  Returns (loss, acc, logits)."""
     f = F.normalize(pooled.float(), dim=-1)
     w = F.normalize(class_weight, dim=-1)
-    one_hot = torch.zeros(f.size(0), w.size(0), dtype=f.dtype).scatter_(1, labels.view(-1, 1), 1.0)
+    labels = labels.to(f.device)
+    one_hot = torch.zeros(f.size(0), w.size(0), dtype=f.dtype, device=f.device).scatter_(1, labels.to(f.device).view(-1, 1), 1.0)
     logits = _margin_logits(F.linear(f, w), one_hot, margin, temp).type_as(pooled)
     loss = F.cross_entropy(logits, labels)
     acc = float((logits.argmax(-1) == labels).sum()) / float(labels.numel())
@@ -321,7 +322,7 @@ def arc_infonce_loss(spk_prompt: Tensor, pooled_enroll: Tensor, neg_idx: Tensor,
     mask = torch.zeros_like(cos)
     mask[:, 0] = 1.0
     logits = _margin_logits(cos, mask, margin, temp).type_as(anchor)
-    target = torch.zeros(logits.size(0), dtype=torch.long)
+    target = torch.zeros(logits.size(0), dtype=torch.long, device=logits.device)
     loss = F.cross_entropy(logits, target)
     acc = float((logits.argmax(-1) == target).sum()) / float(target.numel())
     return loss, acc, logits
@@ -333,11 +334,11 @@ def decoder_forward(p: P, cfg: TSConfig, hs: Tensor, ys_in: Tensor, spk_prompt: 
     _, n_head, n_layer = cfg.dims
     dec = pre + ".decoders"
     E = p[dec + ".token_embedding.weight"]
-    sop = E[torch.full((ys_in.size(0), 1), cfg.startofprev_token, dtype=torch.long)]
+    sop = E[torch.full((ys_in.size(0), 1), cfg.startofprev_token, dtype=torch.long, device=E.device)]
     tgt = torch.cat([sop, spk_prompt.to(E.dtype), E[ys_in]], dim=1)
     x = (tgt + p[dec + ".positional_embedding"][: tgt.size(1)]).to(hs.dtype)
     n_ctx = p[dec + ".positional_embedding"].size(0)
-    mask = torch.full((n_ctx, n_ctx), float("-inf")).triu_(1)
+    mask = torch.full((n_ctx, n_ctx), float("-inf"), device=hs.device).triu_(1)
     for l in range(n_layer):
         x = whisper_block(p, f"{dec}.blocks.{l}", x, n_head, xa=hs, mask=mask)
     x = _ln(x, p, dec + ".ln")
@@ -355,7 +356,7 @@ def forward_one_step(p: P, cfg: TSConfig, ys: Tensor, memory: Tensor, spk_prompt
 
 def greedy_decode(p: P, cfg: TSConfig, memory: Tensor, spk_prompt: Tensor, max_len: int, sos: Optional[int] = None) -> Tensor:
     """Beam-1 search through batch_score (whisper_decoder.py:354-380): argmax token ids, (B, max_len)."""
-    ys = torch.full((memory.size(0), 1), cfg.sos if sos is None else sos, dtype=torch.long)
+    ys = torch.full((memory.size(0), 1), cfg.sos if sos is None else sos, dtype=torch.long, device=memory.device)
     for _ in range(max_len):
         nxt = forward_one_step(p, cfg, ys, memory, spk_prompt).argmax(-1, keepdim=True)
         ys = torch.cat([ys, nxt], dim=1)
