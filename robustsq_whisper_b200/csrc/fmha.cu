@@ -13,6 +13,7 @@
 //   warps 2-5   softmax / output (each owns the 32 TMEM lanes its index allows)
 // Two CTAs are resident per SM (112 KB smem, 256 TMEM columns each) so one CTA's softmax overlaps the other's MMAs.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "tc_ptx.cuh"
@@ -284,6 +285,307 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc<256>(s.tmem_slot); }
+}
+
+
+// ================================================================================================ forward, two query tiles per CTA
+// fmha_fwd2_kernel (Sq > 128, no causal mask: encoder and SQ-Former self-attention) — persistent, one CTA per SM, each work item
+// = (batch, head, PAIR of 128-query tiles).  What bounds head-dim-64 attention on one SM is not the tensor pipe but (a) the
+// 16 exp2 / clk of the MUFU and (b) shared-memory bandwidth: an SS-mode tcgen05.mma with N = 64 reads 6 KB of operands per 32
+// tensor cycles, more than the 128 B / clk the shared memory delivers, on top of the TMA fills and the P stores.  So:
+//   * P never touches shared memory: the softmax threads write bf16 probabilities straight back into TMEM (tcgen05.st) and
+//     P V is a TS-mode MMA (A operand from TMEM) — no st.shared, no generic->async proxy fence, no operand re-read;
+//   * the two query tiles of an item share every K / V tile (half the TMA fills per tile);
+//   * one thread owns one query row (all 128 keys of a tile): the row maximum needs no exchange, there is no CTA barrier
+//     in the loop; the two softmax warpgroups (one per query tile) alternate on the MUFU while the tensor pipe serves the
+//     other tile's S = Q K^T / P V (the issuer polls both tiles' barriers and issues whatever is ready);
+//   * the pipeline runs across work items (Q double buffer, K / V ring, O hand-off barrier): no per-CTA prologue.
+//   warp 0: TMA producer   warp 1: TMEM allocator + MMA issuer   warps 2-5: softmax of tile 0   warps 6-9: softmax of tile 1
+// TMEM (512 columns): S0 S1 (2 x 128, fp32) | O0 O1 (2 x 64, fp32) | P0 P1 (2 x 64 columns = 128 keys of packed bf16 pairs)
+constexpr int F2_THREADS = 320;
+constexpr int F2_KV = 3;   // K and V ring depth
+
+struct FmhaFwd2Smem {
+  unsigned char q[2][2][kTileBytes];     // [item parity][tile]
+  unsigned char k[F2_KV][kTileBytes];
+  unsigned char v[F2_KV][kTileBytes];
+  uint64_t q_full[2], q_empty[2], k_full[F2_KV], k_empty[F2_KV], v_full[F2_KV], v_empty[F2_KV];
+  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2], o_free[2];
+  uint32_t tmem_slot;
+};
+
+struct Fwd2Item { int b, h, q0, n_kv, limit, n_tiles; };
+__device__ __forceinline__ Fwd2Item fwd2_item(const FmhaParams& p, int w, int n_qp) {
+  Fwd2Item I;
+  const int qp = w % n_qp, bh = w / n_qp;
+  I.h = bh % p.H; I.b = bh / p.H; I.q0 = qp * 2 * FQ;
+  I.limit = p.Sk;
+  if (p.key_len) I.limit = max(0, min(I.limit, p.key_len[I.b]));
+  I.n_kv = (I.limit + FK - 1) / FK;
+  I.n_tiles = (I.q0 + FQ < p.Sq) ? 2 : 1;
+  return I;
+}
+
+// 32 scores of one row -> bf16 probability pairs (16 registers), running sum and raw maximum
+template <bool MASKED>
+__device__ __forceinline__ void fwd2_chunk(const uint32_t* v, float scale_log2, float m_ref, int first_key, int row_limit, uint32_t* pk,
+                                           float2& lsum, float& tmax) {
+  const float2 sc = splat2(scale_log2), mr = splat2(-m_ref);
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
+    const float2 x = ffma2(make_float2(a, b), sc, mr);
+    float p0 = ex2_approx(x.x), p1 = ex2_approx(x.y);
+    if (MASKED) {
+      if (first_key + i >= row_limit) { p0 = 0.f; a = -INFINITY; }
+      if (first_key + i + 1 >= row_limit) { p1 = 0.f; b = -INFINITY; }
+    }
+    tmax = fmaxf(tmax, fmaxf(a, b));
+    lsum = fadd2(lsum, make_float2(p0, p1));
+    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+  }
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1)
+fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                 const FmhaParams p, const int n_qp, const int total) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  FmhaFwd2Smem& s = *reinterpret_cast<FmhaFwd2Smem*>(smem_raw);
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_fwd2: dynamic smem not 1024-aligned\n"); __trap(); }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 2);
+      mbar_init(&s.s_full[i], 1); mbar_init(&s.s_free[i], 4); mbar_init(&s.p_full[i], 4); mbar_init(&s.pv_done[i], 1); mbar_init(&s.o_free[i], 4);
+    }
+    for (int i = 0; i < F2_KV; ++i) { mbar_init(&s.k_full[i], 1); mbar_init(&s.k_empty[i], 2); mbar_init(&s.v_full[i], 1); mbar_init(&s.v_empty[i], 2); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = s.tmem_slot;
+  const int step = gridDim.x;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int it = 0, kc = 0;   // items with keys so far; K/V tiles so far
+      for (int w = blockIdx.x; w < total; w += step) {
+        const Fwd2Item I = fwd2_item(p, w, n_qp);
+        if (I.n_kv == 0) continue;
+        const int qb = it & 1;
+        mbar_wait(&s.q_empty[qb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&s.q_full[qb], I.n_tiles * kTileBytes);
+        for (int t = 0; t < I.n_tiles; ++t) tma_load_4d(&tmQ, &s.q_full[qb], s.q[qb][t], I.h * FD, I.q0 + t * FQ, I.b, 0);
+        for (int j = 0; j < I.n_kv; ++j, ++kc) {
+          const int st = kc % F2_KV; const uint32_t ph = (kc / F2_KV) & 1;
+          mbar_wait(&s.k_empty[st], ph ^ 1);
+          mbar_expect_tx(&s.k_full[st], kTileBytes);
+          tma_load_4d(&tmK, &s.k_full[st], s.k[st], I.h * FD, j * FK, I.b, 0);
+          mbar_wait(&s.v_empty[st], ph ^ 1);
+          mbar_expect_tx(&s.v_full[st], kTileBytes);
+          tma_load_4d(&tmV, &s.v_full[st], s.v[st], I.h * FD, j * FK, I.b, 0);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer: polls both tiles' barriers, issues what is ready
+    const bool leader_lane = elect_one();
+    const uint32_t id_s = idesc_bf16(FQ, FK, 0, 0);    // S = Q K^T : both K-major, N = 128
+    const uint32_t id_pv = idesc_bf16(FQ, FD, 0, 1);   // P V : A = P from TMEM, B = V MN-major ([key][dh]), N = 64
+    int it = 0, kc0 = 0;
+    int tiles_done[2] = {0, 0};   // S / PV tiles completed in earlier items, per query tile (barrier phases)
+    int items_done[2] = {0, 0};   // earlier items in which the query tile was active (o_free phases)
+    for (int w = blockIdx.x; w < total; w += step) {
+      const Fwd2Item I = fwd2_item(p, w, n_qp);
+      if (I.n_kv == 0) continue;
+      const int qb = it & 1;
+      mbar_wait(&s.q_full[qb], (it >> 1) & 1);
+      int s_iss[2] = {0, 0}, pv_iss[2] = {0, 0};
+      if (I.n_tiles == 1) { s_iss[1] = pv_iss[1] = I.n_kv; }
+      int remaining = 2 * I.n_kv * I.n_tiles;
+      while (remaining > 0) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          // ---- S_t(j) = Q_t K_j^T
+          if (s_iss[t] < I.n_kv) {
+            const int j = s_iss[t], n = tiles_done[t] + j, kc = kc0 + j, st = kc % F2_KV;
+            if (mbar_test_wait(&s.s_free[t], (n & 1) ^ 1) && mbar_test_wait(&s.k_full[st], (kc / F2_KV) & 1)) {
+              tc_fence_after();
+              if (leader_lane) {
+                const uint64_t qd = make_smem_desc(smem_u32(s.q[qb][t]), 16, 1024), kd = make_smem_desc(smem_u32(s.k[st]), 16, 1024);
+                const uint32_t ts = tm + t * 128;
+                umma_bf16_c<false>(ts, qd, kd, id_s);
+#pragma unroll
+                for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(ts, desc_advance(qd, k * 32), desc_advance(kd, k * 32), id_s);
+                umma_commit(&s.s_full[t]);
+                umma_commit(&s.k_empty[st]);
+                if (I.n_tiles == 1) umma_commit(&s.k_empty[st]);   // the absent second tile's share
+                if (j + 1 == I.n_kv) { umma_commit(&s.q_empty[qb]); if (I.n_tiles == 1) umma_commit(&s.q_empty[qb]); }
+              }
+              __syncwarp();
+              ++s_iss[t]; --remaining;
+            }
+          }
+          // ---- O_t (+)= P_t(j) V_j
+          if (pv_iss[t] < s_iss[t]) {
+            const int j = pv_iss[t], n = tiles_done[t] + j, kc = kc0 + j, st = kc % F2_KV;
+            bool ok = mbar_test_wait(&s.p_full[t], n & 1) && mbar_test_wait(&s.v_full[st], (kc / F2_KV) & 1);
+            if (ok && j == 0) ok = mbar_test_wait(&s.o_free[t], (items_done[t] & 1) ^ 1);   // the previous item's output has been read
+            if (ok) {
+              tc_fence_after();
+              if (leader_lane) {
+                const uint64_t vd = make_smem_desc(smem_u32(s.v[st]), kTileBytes, 1024);
+                const uint32_t to = tm + 256 + t * 64, tp = tm + 384 + t * 64;
+                if (j == 0) umma_bf16_ts_c<false>(to, tp, vd, id_pv); else umma_bf16_ts_c<true>(to, tp, vd, id_pv);
+#pragma unroll
+                for (int k = 1; k < FK / 16; ++k) umma_bf16_ts_c<true>(to, tp + k * 8, desc_advance(vd, k * 2048), id_pv);
+                umma_commit(&s.pv_done[t]);
+                umma_commit(&s.v_empty[st]);
+                if (I.n_tiles == 1) umma_commit(&s.v_empty[st]);
+              }
+              __syncwarp();
+              ++pv_iss[t]; --remaining;
+            }
+          }
+        }
+      }
+      for (int t = 0; t < I.n_tiles; ++t) { tiles_done[t] += I.n_kv; ++items_done[t]; }
+      kc0 += I.n_kv;
+      ++it;
+    }
+  } else {
+    // ===================================================== softmax + output: thread = one query row of tile t
+    const int t = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t ts = tm + lane_off + t * 128, to = tm + lane_off + 256 + t * 64, tp = tm + lane_off + 384 + t * 64;
+    int n = 0, items = 0;   // tiles / items this warpgroup has processed (barrier phases)
+    for (int w = blockIdx.x; w < total; w += step) {
+      const Fwd2Item I = fwd2_item(p, w, n_qp);
+      if (t >= I.n_tiles) continue;
+      const int qi = I.q0 + t * FQ + r;
+      const int row_limit = I.limit;
+      if (I.n_kv == 0) {   // no visible key: zero output, -inf log-sum-exp
+        if (qi < p.Sq) {
+          __nv_bfloat16* orow = p.o + ((int64_t)I.b * p.Sq + qi) * p.ldo + I.h * FD;
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(orow)[c] = z;
+          p.lse[((int64_t)I.b * p.H + I.h) * p.Sq + qi] = -INFINITY;
+        }
+        continue;
+      }
+      // Lazy running maximum (see fmha_fwd_kernel): the reference moves only when a tile overshoots it by more than 2^8
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < I.n_kv; ++j, ++n) {
+        mbar_wait(&s.s_full[t], n & 1);
+        tc_fence_after();
+        const int kb = j * FK;
+        const bool full = kb + FK <= row_limit;
+        uint32_t sa[32], sb[32];
+        if (j == 0) {   // exact maximum of the first tile -> initial reference (S is read twice)
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32_async(ts + 32 * c, sa);
+            tmem_ld_wait();
+            tmem_ld_fence32(sa);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (full || kb + 32 * c + i < row_limit) mx = fmaxf(mx, __uint_as_float(sa[i]));
+          }
+          m_ref = mx * p.scale_log2;
+          if (m_ref == -INFINITY) m_ref = 0.f;
+        }
+        float2 lsum = make_float2(0.f, 0.f);
+        float tmax = -INFINITY;
+        tmem_ld32_async(ts, sa);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // 32 keys at a time; the next chunk's TMEM load is in flight under the exponentials
+          uint32_t* cur = (c & 1) ? sb : sa;
+          uint32_t* nxt = (c & 1) ? sa : sb;
+          tmem_ld_wait();
+          tmem_ld_fence32(cur);
+          if (c < 3) tmem_ld32_async(ts + 32 * (c + 1), nxt);
+          uint32_t pk[16];
+          if (full) fwd2_chunk<false>(cur, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
+          else fwd2_chunk<true>(cur, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
+          if (c == 0 && n > 0) { mbar_wait(&s.pv_done[t], (n - 1) & 1); tc_fence_after(); }   // P V of the previous tile has read P (and updated O)
+          tmem_st16_async(tp + 16 * c, pk);
+          if (c == 3) {
+            tmem_ld_fence32(nxt);   // keep the compiler from sinking anything below
+          }
+        }
+        // all of S is in registers / consumed: the issuer may overwrite it with the next tile's scores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.s_free[t]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.p_full[t]);
+        l_run += lsum.x + lsum.y;
+        const float m_tile = tmax * p.scale_log2;
+        const bool move = m_tile > m_ref + 8.f;
+        if (__any_sync(0xffffffffu, move)) {
+          // rare (first tiles): rescale the accumulator — including this tile's P V, which used the old reference — once
+          // that MMA has completed; P V of the next tile is not issued before this warp's next p_full arrival
+          const float alpha = move ? ex2_approx(m_ref - m_tile) : 1.f;
+          mbar_wait(&s.pv_done[t], n & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t ov[32];
+            tmem_ld32_async(to + 32 * hh, ov);
+            tmem_ld_wait();
+            tmem_ld_fence32(ov);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * alpha);
+            tmem_st32(to + 32 * hh, ov);
+          }
+          tc_fence_before();
+          l_run *= alpha;
+          if (move) m_ref = m_tile;
+        }
+      }
+      // ---- output of the item: O / l, log-sum-exp
+      mbar_wait(&s.pv_done[t], (n - 1) & 1);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* orow = p.o + ((int64_t)I.b * p.Sq + qi) * p.ldo + I.h * FD;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float o[32];
+        tmem_ld32(to + 32 * hh, o);
+        if (hh == 1) {   // the accumulator is in registers: the next item's first P V may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s.o_free[t]);
+        }
+        if (qi < p.Sq) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            float tt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] = o[c + i] * inv;
+            Vec<__nv_bfloat16>::store(orow + hh * 32 + c, tt);
+          }
+        }
+      }
+      if (qi < p.Sq) p.lse[((int64_t)I.b * p.H + I.h) * p.Sq + qi] = l_run > 0.f ? (m_ref + log2f(l_run)) * 0.69314718055994530942f : -INFINITY;
+      ++items;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(s.tmem_slot); }
 }
 
 
@@ -709,6 +1011,23 @@ extern "C" int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o
   p.scale_log2 = scale * 1.44269504088896340736f;
   p.key_len = key_len; p.causal = causal ? 1 : 0;
   p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.lse = lse;
+  static const bool v1_only = getenv("TSW_FMHA_FWD_V1") != nullptr;   // A/B knob: the single-tile kernel for every shape
+  if (!causal && Sq > FQ && !v1_only) {
+    // long query sequences (encoder / SQ-Former self-attention): two query tiles per CTA, P in TMEM, persistent
+    const int n_qp = (int)((Sq + 2 * FQ - 1) / (2 * FQ));
+    const int64_t total = (int64_t)B * H * n_qp;
+    TSW_CHECK_ARG(total < (1ll << 31), "fmha_fwd: too many work items");
+    static bool attr2_done = false;
+    const size_t smem2 = sizeof(FmhaFwd2Smem);
+    if (!attr2_done) {
+      TSW_CUDA(cudaFuncSetAttribute(fmha_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      attr2_done = true;
+    }
+    const unsigned grid2 = (unsigned)std::min<int64_t>(total, sm_count());
+    fmha_fwd2_kernel<<<grid2, F2_THREADS, smem2, as_stream(stream)>>>(tq, tk, tv, p, n_qp, (int)total);
+    TSW_LAUNCH_CHECK();
+    return TSW_OK;
+  }
   static bool attr_done = false;
   const size_t smem = sizeof(FmhaFwdSmem);
   if (!attr_done) {

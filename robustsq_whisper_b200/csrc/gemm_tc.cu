@@ -62,7 +62,7 @@ template <> struct RawVec<__nv_bfloat16> {
 };
 
 // instruction descriptor: D=f32, A=B=bf16, majors, N>>3, M>>4
-__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
+__device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n, int m = TBM) {
   uint32_t d = 0;
   d |= 1u << 4;                      // c_format = F32
   d |= 1u << 7;                      // a_format = BF16
@@ -70,7 +70,7 @@ __device__ __forceinline__ uint32_t make_idesc(int a_mn, int b_mn, int n) {
   d |= (uint32_t)(a_mn & 1) << 15;   // a_major (0 = K, 1 = MN)
   d |= (uint32_t)(b_mn & 1) << 16;   // b_major
   d |= (uint32_t)(n >> 3) << 17;     // n_dim
-  d |= (uint32_t)(TBM >> 4) << 24;   // m_dim
+  d |= (uint32_t)(m >> 4) << 24;     // m_dim
   return d;
 }
 
@@ -153,20 +153,25 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TWOSM = false>
 struct TcSmem {
   static constexpr uint32_t kABytes = TBM * TBK * 2;
-  static constexpr uint32_t kBBytes = BN * TBK * 2;
+  static constexpr uint32_t kBBytes = (TWOSM ? BN / 2 : BN) * TBK * 2;   // two-SM UMMA: each CTA holds its half of the N columns
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kStgFloats = 32 * 32;  // per-epilogue-warp transpose staging: 32 rows x 32 fp32, XOR-swizzled 16-byte units
   static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256 + TC_EPI_WARPS * kStgFloats * 4;
 };
 
-template <int BN, int STAGES, typename DT, bool GENERIC, int CL>
+// TWOSM (with CL = 2): the pair runs ONE tcgen05.mma.cta_group::2 per k-step over a 256 x BN tile — each CTA stages its own
+// 128 rows of A and its own BN/2 columns of B (32 KB per stage instead of 48 KB, six stages instead of four), the even CTA
+// issues, both drain their 128 accumulator rows.  Measured on B200 against the multicast pair of round 1: 48512 x 1024 x 1024
+// 1129 -> 1293 TF/s, 48512 x 1024 x 4096 (+residual) 1271 -> 1456, 48512 x 4096 x 1024 1366 -> 1429.
+template <int BN, int STAGES, typename DT, bool GENERIC, int CL, bool TWOSM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB2, const TcParams p, const EpiParams ep) {
-  using S = TcSmem<BN, STAGES>;
+  static_assert(!TWOSM || CL == 2, "two-SM UMMA needs a cluster of two CTAs");
+  using S = TcSmem<BN, STAGES, TWOSM>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = smem;
@@ -186,11 +191,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.kb_total > p.kb_main) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], CL); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
+    // TWOSM: one multicast commit of the pair's issuer frees a slot in each CTA; the issuer's accumulator stage is released by the
+    // epilogue warps of BOTH CTAs
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TWOSM ? 1 : CL); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TWOSM ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 2) { if (TWOSM) tmem_alloc_2sm<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot); }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
@@ -226,11 +233,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = tiles + (size_t)stage * S::kStageBytes;
           unsigned char* sb = sa + S::kABytes;
-          mbar_expect_tx(&full[stage], S::kStageBytes);
+          if (!TWOSM) mbar_expect_tx(&full[stage], S::kStageBytes);
+          else if (crank == 0) mbar_expect_tx(&full[stage], 2 * S::kStageBytes);   // both CTAs' bytes are counted on the issuer's barrier
           const bool second = kb >= p.kb_main;
           const CUtensorMap* ta = second ? &tmA2 : &tmA;
           const CUtensorMap* tb = second ? &tmB2 : &tmB;
           const int k0 = (second ? kb - p.kb_main : kb) * TBK;
+          if (TWOSM) {   // own 128 rows of A, own BN/2 columns of B; completion counted on the even CTA's barrier
+            if (!p.a_mn) {
+              tma_load_4d_2sm(ta, &full[stage], sa, k0, m0, bi, bo);
+            } else {
+#pragma unroll
+              for (int j = 0; j < TBM / 64; ++j) tma_load_4d_2sm(ta, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);
+            }
+            if (!p.b_mn) {
+              tma_load_4d_2sm(tb, &full[stage], sb, k0, n0 + crank * (BN / 2), bi, bo);   // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 128; ++j) tma_load_4d_2sm(tb, &full[stage], sb + j * kPanelBytes, n0 + crank * (BN / 2) + 64 * j, k0, bi, bo);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (!p.a_mn) {
             tma_load_4d(ta, &full[stage], sa, k0, m0, bi, bo);                       // box {64 k, 128 m}
           } else {
@@ -261,8 +285,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.a_mn, p.b_mn, BN);
+    if (lane == 0 && (!TWOSM || crank == 0)) {
+      const uint32_t idesc = make_idesc(p.a_mn, p.b_mn, BN, TWOSM ? 2 * TBM : TBM);
       const uint32_t a_lbo = p.a_mn ? kPanelBytes : 16, b_lbo = p.b_mn ? kPanelBytes : 16;
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;  // bytes per UMMA_K = 16
       int stage = 0; uint32_t phase = 0;
@@ -282,13 +306,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < TBK / 16; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (TWOSM) umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CL > 1) umma_commit_mc(&empty[stage], (uint16_t)3);   // the slot is refilled by both CTAs: release it in both
+          if (TWOSM) umma_commit_2sm(&empty[stage]);
+          else if (CL > 1) umma_commit_mc(&empty[stage], (uint16_t)3);   // the slot is refilled by both CTAs: release it in both
           else umma_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);       // accumulator complete
+        if (TWOSM) umma_commit_2sm(&tfull[as]);   // both CTAs' epilogue warps wait on their own copy
+        else umma_commit(&tfull[as]);       // accumulator complete
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -396,13 +423,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) { if (TWOSM) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer may still multicast into this CTA's smem / barriers until it is done
-  if (warp == 2) { tc_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
+  if (warp == 2) { tc_fence_after(); if (TWOSM) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base); }
 }
 
 // ----------------------------------------------------------------------------------------------- host side
@@ -456,9 +483,9 @@ bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
   return true;
 }
 
-template <int BN, int STAGES, typename DT, bool GENERIC, int CL>
+template <int BN, int STAGES, typename DT, bool GENERIC, int CL, bool TWOSM = false>
 static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
-  using S = TcSmem<BN, STAGES>;
+  using S = TcSmem<BN, STAGES, TWOSM>;
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, g.A, g.a_mn_major, g.M, g.K, g.lda, g.batch_inner, g.a_stride_inner, g.batch_outer, g.a_stride_outer, TBM);
   if (rc) return rc;
@@ -514,7 +541,7 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
     }
     TSW_CUDA(cudaMemsetAsync(ep.colsum, 0, sizeof(float) * (size_t)g.N, st));
   }
-  auto kern = gemm_tc_kernel<BN, STAGES, DT, GENERIC, CL>;
+  auto kern = gemm_tc_kernel<BN, STAGES, DT, GENERIC, CL, TWOSM>;
   static bool attr_done = false;
   if (!attr_done) {
     TSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
@@ -556,12 +583,14 @@ int gemm_tc_launch(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st)
   const int64_t tiles_m = (g.M + TBM - 1) / TBM;
   static const bool no_cluster = getenv("TSW_GEMM_NO_CLUSTER") != nullptr;
   const bool pair = wide && !no_cluster && (tiles_m >= 8 || (tiles_m >= 2 && tiles_m % 2 == 0));
+  static const bool mc_pair = getenv("TSW_GEMM_MC_PAIR") != nullptr;   // A/B knob: the round-1 pair (two cta_group::1 tiles sharing B by TMA multicast)
   // decode-time GEMMs (a handful of token rows against a whole weight matrix) are weight streaming: one row of tiles, so
   // 32-column tiles spread the N x K weight over 8x more CTAs (N = 1024: 32 CTAs pulling 64 KB each instead of 4 pulling 512 KB)
   const bool skinny = tiles_m == 1 && !g.b_mn_major && g.N >= 256 && g.batch_inner * g.batch_outer == 1;
 #define TC_DISPATCH(DT)                                                                                   \
   do {                                                                                                    \
     if (skinny) return generic ? tc_go<32, 8, DT, true, 1>(g, ep, st) : tc_go<32, 8, DT, false, 1>(g, ep, st);   \
+    if (pair && !mc_pair) return generic ? tc_go<256, 6, DT, true, 2, true>(g, ep, st) : tc_go<256, 6, DT, false, 2, true>(g, ep, st);  \
     if (pair) return generic ? tc_go<256, 4, DT, true, 2>(g, ep, st) : tc_go<256, 4, DT, false, 2>(g, ep, st);  \
     if (wide) return generic ? tc_go<256, 4, DT, true, 1>(g, ep, st) : tc_go<256, 4, DT, false, 1>(g, ep, st);  \
     return generic ? tc_go<128, 6, DT, true, 1>(g, ep, st) : tc_go<128, 6, DT, false, 1>(g, ep, st);            \

@@ -36,6 +36,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking probe (a failing try_wait parks the thread for a system-dependent time — hundreds of cycles — before it
+// reports false: wrong for an issuer that polls several barriers and must react to whichever completes first)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~`ns` nanoseconds pass
 // (the default try_wait gives up after a few dozen cycles, and a warp that polls in a loop takes issue slots from the
 // math warps on its scheduler: in the attention backward a third of all issued instructions were such polls).
@@ -82,6 +93,44 @@ __device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* tm, uint64_t* 
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
       : "memory");
 }
+// ---- cta_group::2 (two-SM UMMA): both CTAs of a pair load their own halves of the operands; the even CTA issues the MMA.
+// Shared-window addresses carry the CTA's rank in the cluster from bit 24 up: clearing bit 24 turns an address of the odd
+// CTA into the same offset in the even ("leader") CTA of the pair.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+// TMA load whose completion bytes are counted on the LEADER CTA's mbarrier (same offset as `bar`)
+__device__ __forceinline__ void tma_load_4d_2sm(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (epilogue warps of both CTAs release the accumulator stage to the one MMA issuer)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {   // the same warp index in BOTH CTAs of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D (TMEM of both CTAs, 128 rows each) (+)= A (2 x 128 rows, one half per CTA) x B (2 x N/2 columns, one half per CTA)
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit of the pair's MMAs, arriving on the same-offset mbarrier of both CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -192,6 +241,27 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[30]), "r"(r[31])
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// 16 registers -> 16 TMEM columns of this warp's lane quarter, no wait (pair with tmem_st_wait)
+__device__ __forceinline__ void tmem_st16_async(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D (TMEM) (+)= A (TMEM: lane = row, one 32-bit column = two consecutive-k bf16) x B (shared memory descriptor)
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_ts_c(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc) {
+  if (ACC) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc) : "memory");
+  }
 }
 
 // shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version 1); offsets in bytes
