@@ -370,7 +370,9 @@ def run_b200(args):
             for mod in model.modules():
                 if getattr(mod, "lora_B", None) is not None:
                     mod.lora_B.normal_(0.0, 0.01)
-    reducer = GradientAllReducer(model.parameters(), overlap=os.environ.get("TSW_DDP_OVERLAP", "1") != "0")
+    reducer = GradientAllReducer(model.parameters(), overlap=os.environ.get("TSW_DDP_OVERLAP", "1") != "0",
+                                 compress=os.environ.get("TSW_DDP_BF16", "0") == "1",
+                                 bucket_bytes=int(os.environ.get("TSW_DDP_BUCKET_MB", "64")) << 20)
 
     B = args.batch
     batch = synth.make_batch(B, args.mix_s, args.enr_s, seed=1234 + rank, utt_offset=rank * B)

@@ -326,8 +326,27 @@ __device__ __forceinline__ Fwd2Item fwd2_item(const FmhaParams& p, int w, int n_
   return I;
 }
 
-// 32 scores of one row -> bf16 probability pairs (16 registers), running sum and raw maximum
-template <bool MASKED>
+// 2^x for a pair on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f with n = round(x) taken from the low mantissa
+// bits of x + 1.5 * 2^23, a degree-3 minimax polynomial for 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the
+// 3.9e-3 resolution of the bf16 probabilities it feeds), and n added into the exponent field.  The MUFU delivers 16 exp2 per
+// clock and SM, which is what bounds head-dim-64 attention; a quarter of the exponentials are moved here.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f); x.y = fmaxf(x.y, -126.f);
+  const float2 t = fadd2(x, splat2(12582912.f));
+  const float2 n = fadd2(t, splat2(-12582912.f));
+  const float2 f = ffma2(n, splat2(-1.f), x);
+  float2 q = ffma2(splat2(0.055171459913253784f), f, splat2(0.2426108568906784f));
+  q = ffma2(q, f, splat2(0.6932609677314758f));
+  q = ffma2(q, f, splat2(0.9999281167984009f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// 32 scores of one row -> bf16 probability pairs (16 registers), running sum and raw maximum; the first NPOLY pairs take the
+// polynomial exp2, the others the MUFU
+template <bool MASKED, int NPOLY>
 __device__ __forceinline__ void fwd2_chunk(const uint32_t* v, float scale_log2, float m_ref, int first_key, int row_limit, uint32_t* pk,
                                            float2& lsum, float& tmax) {
   const float2 sc = splat2(scale_log2), mr = splat2(-m_ref);
@@ -335,18 +354,21 @@ __device__ __forceinline__ void fwd2_chunk(const uint32_t* v, float scale_log2, 
   for (int i = 0; i < 32; i += 2) {
     float a = __uint_as_float(v[i]), b = __uint_as_float(v[i + 1]);
     const float2 x = ffma2(make_float2(a, b), sc, mr);
-    float p0 = ex2_approx(x.x), p1 = ex2_approx(x.y);
+    float2 pr;
+    if ((i >> 1) < NPOLY) pr = exp2_poly2(x);
+    else { pr.x = ex2_approx(x.x); pr.y = ex2_approx(x.y); }
     if (MASKED) {
-      if (first_key + i >= row_limit) { p0 = 0.f; a = -INFINITY; }
-      if (first_key + i + 1 >= row_limit) { p1 = 0.f; b = -INFINITY; }
+      if (first_key + i >= row_limit) { pr.x = 0.f; a = -INFINITY; }
+      if (first_key + i + 1 >= row_limit) { pr.y = 0.f; b = -INFINITY; }
     }
     tmax = fmaxf(tmax, fmaxf(a, b));
-    lsum = fadd2(lsum, make_float2(p0, p1));
-    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+    lsum = fadd2(lsum, pr);
+    const __nv_bfloat162 pb = __floats2bfloat162_rn(pr.x, pr.y);
     pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
   }
 }
 
+template <int NPOLY>
 __global__ void __launch_bounds__(F2_THREADS, 1)
 fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                  const FmhaParams p, const int n_qp, const int total) {
@@ -490,43 +512,42 @@ fmha_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_after();
         const int kb = j * FK;
         const bool full = kb + FK <= row_limit;
-        uint32_t sa[32], sb[32];
-        if (j == 0) {   // exact maximum of the first tile -> initial reference (S is read twice)
+        // the row of scores is pulled out of TMEM in two halves of 64 keys: the second half is in flight under the
+        // exponentials of the first, and S is released to the issuer (next tile's Q K^T) as soon as it has landed — half a
+        // tile of exponentials before this thread is done with the tile
+        uint32_t sv[128];
+        tmem_ld32_async(ts, sv);
+        tmem_ld32_async(ts + 32, sv + 32);
+        tmem_ld_wait();
+        tmem_ld_fence32(sv); tmem_ld_fence32(sv + 32);
+        tmem_ld32_async(ts + 64, sv + 64);
+        tmem_ld32_async(ts + 96, sv + 96);
+        if (j == 0) {   // exact maximum of the first tile -> initial reference (needs the whole row: wait for the second half now)
+          tmem_ld_wait();
+          tmem_ld_fence32(sv + 64); tmem_ld_fence32(sv + 96);
           float mx = -INFINITY;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            tmem_ld32_async(ts + 32 * c, sa);
-            tmem_ld_wait();
-            tmem_ld_fence32(sa);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) if (full || kb + 32 * c + i < row_limit) mx = fmaxf(mx, __uint_as_float(sa[i]));
-          }
+          for (int i = 0; i < 128; ++i) if (full || kb + i < row_limit) mx = fmaxf(mx, __uint_as_float(sv[i]));
           m_ref = mx * p.scale_log2;
           if (m_ref == -INFINITY) m_ref = 0.f;
         }
         float2 lsum = make_float2(0.f, 0.f);
         float tmax = -INFINITY;
-        tmem_ld32_async(ts, sa);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {   // 32 keys at a time; the next chunk's TMEM load is in flight under the exponentials
-          uint32_t* cur = (c & 1) ? sb : sa;
-          uint32_t* nxt = (c & 1) ? sa : sb;
-          tmem_ld_wait();
-          tmem_ld_fence32(cur);
-          if (c < 3) tmem_ld32_async(ts + 32 * (c + 1), nxt);
+        for (int c = 0; c < 4; ++c) {   // 32 keys at a time: exponentials -> bf16 pairs -> the P operand in TMEM
+          if (c == 2) {
+            tmem_ld_wait();
+            tmem_ld_fence32(sv + 64); tmem_ld_fence32(sv + 96);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.s_free[t]);
+          }
           uint32_t pk[16];
-          if (full) fwd2_chunk<false>(cur, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
-          else fwd2_chunk<true>(cur, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
+          if (full) fwd2_chunk<false, NPOLY>(sv + 32 * c, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
+          else fwd2_chunk<true, NPOLY>(sv + 32 * c, p.scale_log2, m_ref, kb + 32 * c, row_limit, pk, lsum, tmax);
           if (c == 0 && n > 0) { mbar_wait(&s.pv_done[t], (n - 1) & 1); tc_fence_after(); }   // P V of the previous tile has read P (and updated O)
           tmem_st16_async(tp + 16 * c, pk);
-          if (c == 3) {
-            tmem_ld_fence32(nxt);   // keep the compiler from sinking anything below
-          }
         }
-        // all of S is in registers / consumed: the issuer may overwrite it with the next tile's scores
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s.s_free[t]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -945,20 +966,29 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(s.tmem_slot); }
 }
 
-// delta[b,h,i] = sum_c dO[b,i,h*64+c] * O[b,i,h*64+c]; one warp per (row, head)
+// delta[b,h,i] = sum_c dO[b,i,h*64+c] * O[b,i,h*64+c]; 8 lanes per (row, head), 16 bytes of each tensor per lane: a warp reads
+// four whole 128-byte head rows of O and of dO per instruction
 __global__ void __launch_bounds__(256)
 fmha_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO, int64_t ldo, int64_t lddo, int B, int H, int Sq,
                   float* __restrict__ delta) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // (b, i, h)
-  if (w >= (int64_t)B * Sq * H) return;
-  const int h = (int)(w % H);
-  const int64_t bi = w / H;
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + bi * ldo + h * FD + lane * 2);
-  const __nv_bfloat162 g = *reinterpret_cast<const __nv_bfloat162*>(dO + bi * lddo + h * FD + lane * 2);
-  const float2 af = __bfloat1622float2(a), gf = __bfloat1622float2(g);
-  const float sum = warp_sum(af.x * gf.x + af.y * gf.y);
-  if (lane == 0) { const int64_t b = bi / Sq, i = bi - b * Sq; delta[(b * H + h) * Sq + i] = sum; }
+  const int sub = threadIdx.x & 7;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;  // (b, i, h)
+  const bool live = w < (int64_t)B * Sq * H;
+  float sum = 0.f;
+  int h = 0; int64_t bi = 0;
+  if (live) {
+    h = (int)(w % H);
+    bi = w / H;
+    float a[8], g[8];
+    Vec<__nv_bfloat16>::load(o + bi * ldo + h * FD + sub * 8, a);
+    Vec<__nv_bfloat16>::load(dO + bi * lddo + h * FD + sub * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum = fmaf(a[j], g[j], sum);
+  }
+  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+  sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+  if (live && sub == 0) { const int64_t b = bi / Sq, i = bi - b * Sq; delta[(b * H + h) * Sq + i] = sum; }
 }
 
 // fp32 dQ accumulator (rows, 8 * cols8) contiguous -> bf16 rows with stride ld (dq may be a column slice of a packed q|k|v gradient)
@@ -1012,19 +1042,26 @@ extern "C" int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o
   p.key_len = key_len; p.causal = causal ? 1 : 0;
   p.o = (__nv_bfloat16*)o; p.ldo = ldo; p.lse = lse;
   static const bool v1_only = getenv("TSW_FMHA_FWD_V1") != nullptr;   // A/B knob: the single-tile kernel for every shape
-  if (!causal && Sq > FQ && !v1_only) {
-    // long query sequences (encoder / SQ-Former self-attention): two query tiles per CTA, P in TMEM, persistent
+  if (!causal && Sq >= 8 * FQ && !v1_only) {
+    // long query sequences (encoder self-attention, S = 1516): two query tiles per CTA, P in TMEM, persistent; shorter ones
+    // (SQ-Former, decoder) have too few tile pairs per (batch, head) to fill the persistent grid evenly
     const int n_qp = (int)((Sq + 2 * FQ - 1) / (2 * FQ));
     const int64_t total = (int64_t)B * H * n_qp;
     TSW_CHECK_ARG(total < (1ll << 31), "fmha_fwd: too many work items");
     static bool attr2_done = false;
     const size_t smem2 = sizeof(FmhaFwd2Smem);
+    // pairs (of 16 per 32-key chunk) whose exp2 runs as a polynomial on the FMA pipe instead of the MUFU; TSW_FMHA_POLY = 0 | 4 | 6
+    static const int npoly = getenv("TSW_FMHA_POLY") ? atoi(getenv("TSW_FMHA_POLY")) : 4;
     if (!attr2_done) {
-      TSW_CUDA(cudaFuncSetAttribute(fmha_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      TSW_CUDA(cudaFuncSetAttribute(fmha_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      TSW_CUDA(cudaFuncSetAttribute(fmha_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      TSW_CUDA(cudaFuncSetAttribute(fmha_fwd2_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
       attr2_done = true;
     }
     const unsigned grid2 = (unsigned)std::min<int64_t>(total, sm_count());
-    fmha_fwd2_kernel<<<grid2, F2_THREADS, smem2, as_stream(stream)>>>(tq, tk, tv, p, n_qp, (int)total);
+    if (npoly == 0) fmha_fwd2_kernel<0><<<grid2, F2_THREADS, smem2, as_stream(stream)>>>(tq, tk, tv, p, n_qp, (int)total);
+    else if (npoly == 6) fmha_fwd2_kernel<6><<<grid2, F2_THREADS, smem2, as_stream(stream)>>>(tq, tk, tv, p, n_qp, (int)total);
+    else fmha_fwd2_kernel<4><<<grid2, F2_THREADS, smem2, as_stream(stream)>>>(tq, tk, tv, p, n_qp, (int)total);
     TSW_LAUNCH_CHECK();
     return TSW_OK;
   }
@@ -1060,8 +1097,8 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   float* delta = (float*)((char*)workspace + (size_t)(B * Sq * dcols) * 4);
   TSW_CUDA(cudaMemsetAsync(dq32, 0, (size_t)(B * Sq * dcols) * 4, st));
   {
-    const int64_t warps = B * Sq * H;
-    fmha_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, ldo, lddo, (int)B, (int)H, (int)Sq, delta);
+    const int64_t groups = B * Sq * H;   // 8 lanes each
+    fmha_delta_kernel<<<(unsigned)((groups + 31) / 32), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, ldo, lddo, (int)B, (int)H, (int)Sq, delta);
     TSW_LAUNCH_CHECK();
   }
   CUtensorMap tq, tk, tv, tdo, tdq;

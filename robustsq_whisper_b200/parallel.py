@@ -43,13 +43,14 @@ def all_gather_with_grad(x: Tensor) -> Tensor:
 
 
 class _Bucket:
-    __slots__ = ("params", "offsets", "numel", "flat", "ready", "work")
+    __slots__ = ("params", "offsets", "numel", "flat", "flat16", "ready", "work")
 
     def __init__(self):
         self.params: List[torch.nn.Parameter] = []
         self.offsets: List[int] = []
         self.numel = 0
         self.flat: Optional[Tensor] = None
+        self.flat16: Optional[Tensor] = None   # bf16 wire copy (compress=True)
         self.ready = 0
         self.work = None
 
@@ -66,10 +67,14 @@ class GradientAllReducer:
     SURVEY.md §2.2) are skipped, so no ``find_unused_parameters`` machinery is needed: which parameters take part is
     learnt from the first step, which runs un-overlapped.  At world size 1 everything is a no-op."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, overlap: bool = True):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, overlap: bool = True, compress: bool = False):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.bucket_bytes = bucket_bytes
         self.overlap = overlap
+        # compress: the buckets travel as bf16 (cast on this rank, averaged over NVLink, cast back into the fp32 bucket) — half
+        # the bytes on the wire and half the time NCCL's CTAs share the SMs with backward; the gradients were produced from
+        # bf16 operands, the averaged values are rounded to bf16 once (what DDP's bf16_compress_hook does).  NCCL only.
+        self.compress = compress
         self._buckets: Optional[List[_Bucket]] = None   # built from the parameters that had a gradient in the first step
         self._where = {}                                 # id(param) -> (bucket, index)
         self._hooks = []
@@ -101,6 +106,13 @@ class GradientAllReducer:
 
     def _launch(self, b: _Bucket) -> None:
         avg = dist.get_backend() == "nccl"
+        if self.compress and avg and b.flat.is_cuda:
+            from . import kernels as K
+            if b.flat16 is None:
+                b.flat16 = torch.empty(b.numel, dtype=torch.bfloat16, device=b.flat.device)
+            K.cast(b.flat, torch.bfloat16, out=b.flat16)
+            b.work = dist.all_reduce(b.flat16, op=dist.ReduceOp.AVG, async_op=True)
+            return
         b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, async_op=True)
 
     def _stage(self, b: _Bucket, i: int) -> None:
@@ -140,6 +152,9 @@ class GradientAllReducer:
                 self._launch(b)
         for b in self._buckets:
             b.work.wait()
+            if self.compress and b.flat16 is not None:
+                from . import kernels as K
+                K.cast(b.flat16, torch.float32, out=b.flat)
             if dist.get_backend() != "nccl":
                 b.flat.div_(world)
             for i, p in enumerate(b.params):
