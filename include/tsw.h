@@ -28,7 +28,7 @@ extern "C" {
 
 typedef struct CUstream_st* tsw_stream_t; /* == cudaStream_t */
 
-#define TSW_ABI_VERSION 2
+#define TSW_ABI_VERSION 3
 
 enum { TSW_F32 = 0, TSW_BF16 = 1 };
 
@@ -130,9 +130,10 @@ int tsw_layernorm_fwd(const void* x, const void* res, const float* gamma, const 
 size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d);
 /* dx = LN'(dy) (+ dres, the gradient arriving on the residual branch that bypasses the LN, or NULL); dgamma/dbeta (d) fp32
  * are OVERWRITTEN (both NULL: frozen affine parameters, the parameter-gradient pass is skipped). x is the LN input
- * (x + res when fused). */
+ * (x + res when fused).  dx_colsum (d) fp32 or NULL: column sums of dx — the bias gradient of the Linear whose output fed
+ * the residual stream this LayerNorm reads (its incoming gradient IS dx), produced in the same sweep. */
 int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
-                      void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
+                      void* dx, float* dgamma, float* dbeta, float* dx_colsum, int64_t rows, int64_t d, int dtype, void* workspace,
                       size_t workspace_bytes, tsw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ elementwise / reductions */
@@ -194,12 +195,15 @@ int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o, float* ls
 
 /* Backward of tsw_fmha_fwd: recomputes the probabilities from lse; dq / dk / dv are laid out like q / k / v (row strides
  * ldq / ldk / ldv: they may be column slices of one packed q|k|v gradient buffer).
- * workspace holds the fp32 dQ accumulator (filled by bulk tensor reduce-adds) and delta = rowsum(dO * O). */
+ * workspace holds the fp32 dQ accumulator (filled by bulk tensor reduce-adds) and delta = rowsum(dO * O).
+ * dq_colsum / dv_colsum (H * 64) fp32 or NULL: column sums over all (batch, position) rows of dq / dv as stored — the bias
+ * gradients of the query / value projections (Whisper's key projection has no bias) — produced on the way: dv in the key-tile
+ * epilogue, dq in the fp32 -> bf16 cast pass (atomic accumulation: summation order varies run to run). */
 size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq);
 int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
                  void* dv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                 int64_t lddo, float scale, const int32_t* key_len, int causal, void* workspace, size_t workspace_bytes,
-                 tsw_stream_t stream);
+                 int64_t lddo, float scale, const int32_t* key_len, int causal, float* dq_colsum, float* dv_colsum, void* workspace,
+                 size_t workspace_bytes, tsw_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ cached decode
  * One new query token per (hypothesis, head) against L cached keys/values: o[b, h*64:(h+1)*64] = softmax_j(scale <q, K_j>) V_j.

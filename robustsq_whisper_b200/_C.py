@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtsw_sm100.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 EPI_NONE, EPI_GELU, EPI_MUL_DGELU, EPI_GELU_SAVE_GRAD, EPI_MUL_AUX = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
 
@@ -60,7 +60,7 @@ SIGNATURES = {
     "tsw_gemm": (c_int, [POINTER(GemmDesc), _P, _SZ, _P]),
     "tsw_layernorm_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _F, _I, _P]),
     "tsw_layernorm_bwd_workspace_bytes": (_SZ, [_I64, _I64]),
-    "tsw_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _P, _SZ, _P]),
+    "tsw_layernorm_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I, _P, _SZ, _P]),
     "tsw_cast": (c_int, [_P, _I, _P, _I, _I64, _P]),
     "tsw_colsum_workspace_bytes": (_SZ, [_I64, _I64]),
     "tsw_colsum": (c_int, [_P, _I, _I64, _I64, _I64, _P, _P, _SZ, _P]),
@@ -74,7 +74,7 @@ SIGNATURES = {
     "tsw_softmax_bwd": (c_int, [_P, _P, _P, _I, _I64, _I64, _I64, _F, _P]),
     "tsw_fmha_fwd": (c_int, [_P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _F, _P, _I, _P]),
     "tsw_fmha_bwd_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
-    "tsw_fmha_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _F, _P, _I, _P, _SZ, _P]),
+    "tsw_fmha_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _I64, _F, _P, _I, _P, _P, _P, _SZ, _P]),
     "tsw_decode_attention": (c_int, [_P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I64, _P, _F, _P, _I64, _I, _P, _P, _I64, _P]),
     "tsw_decoder_embed": (c_int, [_P, _P, _P, _I, _P, _I64, _I64, _I64, _I64, _I64, _P, _I, _P]),
     "tsw_decoder_embed_bwd": (c_int, [_P, _I, _P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _I, _P]),

@@ -640,6 +640,7 @@ struct FmhaBwdParams {
   const float* lse;    // (B, H, Sq)
   const float* delta;  // (B, H, Sq) rowsum(dO * O)
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
+  float* dv_colsum;    // (H * 64) fp32 or null: column sums of dV (bias gradient of the value projection), atomically accumulated
 };
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -919,6 +920,14 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
       }
+      if (p.dv_colsum != nullptr) {   // bias gradient of the value projection: sum over this tile's key rows, as stored (bf16-rounded)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float t = key < p.Sk ? __bfloat162float(__float2bfloat16_rn(gv[c])) : 0.f;
+          t = warp_sum(t);
+          if (lane == c) atomicAdd(p.dv_colsum + I.h * FD + part * 16 + c, t);
+        }
+      }
       ++j;
     }
   } else {
@@ -1004,6 +1013,41 @@ fmha_dq_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d
   Vec<__nv_bfloat16>::store(dst + row * ld + c8 * 8, v);
 }
 
+// the same cast, plus the column sums of the bf16 result (bias gradient of the query projection) in the same pass: CTA = 32 column
+// vectors x 8 row lanes over a chunk of rows, row lanes folded through shared memory, one atomic add per column and CTA
+__global__ void __launch_bounds__(256)
+fmha_dq_cast_colsum_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int cols8, int64_t ld,
+                           int64_t rows_per_chunk, float* __restrict__ colsum) {
+  __shared__ float sm[8][32 * 8 + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c8 = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (c8 < cols8) {
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      float v[8];
+      Vec<float>::load(src + (r * cols8 + c8) * 8, v);
+      Vec<float>::load(src + (r * cols8 + c8) * 8 + 4, v + 4);
+      Vec<__nv_bfloat16>::store(dst + r * ld + c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(__float2bfloat16_rn(v[j]));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;   // 256 columns of this CTA
+  const int col = blockIdx.x * 256 + c;
+  if (col < cols8 * 8) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][c];
+    atomicAdd(colsum + col, t);
+  }
+}
+
 // (B, S, d) bf16 tensor -> 4-D map {d, S, B, 1}, box {64, 128, 1, 1}, SWIZZLE_128B
 static int make_bsd_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t d_cols, int64_t ld, bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
@@ -1083,8 +1127,8 @@ extern "C" size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq)
 
 extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
                             void* dv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
-                            int64_t lddo, float scale, const int32_t* key_len, int causal, void* workspace, size_t workspace_bytes,
-                            tsw_stream_t stream) {
+                            int64_t lddo, float scale, const int32_t* key_len, int causal, float* dq_colsum, float* dv_colsum, void* workspace,
+                            size_t workspace_bytes, tsw_stream_t stream) {
   TSW_CHECK_ARG(q && k && v && o && dO && lse && dq && dk && dv, "fmha_bwd: null argument");
   TSW_CHECK_ARG(B > 0 && H > 0 && Sq > 0 && Sk > 0 && B <= 65535 && H <= 65535, "fmha_bwd: bad sizes");
   TSW_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && lddo % 8 == 0, "fmha_bwd: leading dimensions must be multiples of 8");
@@ -1117,6 +1161,9 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   p.key_len = key_len; p.causal = causal ? 1 : 0;
   p.lse = lse; p.delta = delta;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddk = ldk; p.lddv = ldv;
+  p.dv_colsum = dv_colsum;
+  if (dv_colsum) TSW_CUDA(cudaMemsetAsync(dv_colsum, 0, sizeof(float) * (size_t)dcols, st));
+  if (dq_colsum) TSW_CUDA(cudaMemsetAsync(dq_colsum, 0, sizeof(float) * (size_t)dcols, st));
   static bool attr_done = false;
   const size_t smem = sizeof(FmhaBwdSmem);
   if (!attr_done) {
@@ -1127,7 +1174,16 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   TSW_LAUNCH_CHECK();
   // dq (B * Sq rows, row stride ldq) bf16 <- contiguous fp32 accumulator
-  {
+  if (dq_colsum) {
+    const int64_t rows = B * Sq;
+    const int cols8 = (int)(dcols / 8);
+    const unsigned gx = (unsigned)((cols8 + 31) / 32);
+    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * 8 / gx, (rows + 63) / 64));
+    chunks = std::min<int64_t>(chunks, 65535);
+    const int64_t rpc = (rows + chunks - 1) / chunks;
+    fmha_dq_cast_colsum_kernel<<<dim3(gx, (unsigned)chunks), 256, 0, st>>>(dq32, (__nv_bfloat16*)dq, rows, cols8, ldq, rpc, dq_colsum);
+    TSW_LAUNCH_CHECK();
+  } else {
     const int64_t n8 = B * Sq * (dcols / 8);
     fmha_dq_cast_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(dq32, (__nv_bfloat16*)dq, n8, (int)(dcols / 8), ldq);
     TSW_LAUNCH_CHECK();

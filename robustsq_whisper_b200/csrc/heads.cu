@@ -18,11 +18,6 @@ namespace cg = cooperative_groups;
 
 namespace tsw {
 
-// one bulk asynchronous copy (TMA, non-tensor form) of a contiguous slab into shared memory, completion on an mbarrier
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 constexpr int kAspThreads = 256;
 constexpr int kMaxCPT = 2;  // vector chunks per thread along d (d <= 256 * kMaxCPT * VN)

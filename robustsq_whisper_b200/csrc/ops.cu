@@ -5,6 +5,7 @@
 #include <cstdlib>
 
 #include "gemm_common.cuh"   // common.cuh + the 4-element load4 / store4 helpers
+#include "tc_ptx.cuh"        // mbarrier + bulk-copy wrappers (TMA-staged LayerNorm backward)
 
 namespace tsw {
 
@@ -179,118 +180,173 @@ ln_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float*
   }
 }
 
-// Single-pass variant for d <= 32 lanes * 4 vectors (every Whisper / SQ-Former width in bf16): the same warp-per-row sweep also
-// accumulates the lane's 4 x VN columns of dgamma = sum dy * xhat and dbeta = sum dy in registers, so dy and x are read ONCE
-// (the two-pass form re-reads both for the parameter gradients: 6 instead of 4 tensor passes).  One CTA per SM at ~170
-// registers; the next row's x / dy and this row's dres are in flight during the two warp reductions.  The 8 warps fold
-// their column sums through shared memory in warp order, each CTA writes one partial row, and ln_bwd_fold_kernel adds the
-// partial rows in CTA order (deterministic).
-template <typename T, int NC>
-__global__ void __launch_bounds__(256, 1)
-ln_bwd_fused_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
-                    const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx, int64_t rows, int d,
-                    float* __restrict__ partial) {
-  constexpr int VN = Vec<T>::N;
-  extern __shared__ float sm_acc[];   // [2][d]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 5);
-  int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  const int nvec = d / VN;
-  float ag[NC][VN], ab[NC][VN];
-#pragma unroll
-  for (int c = 0; c < NC; ++c)
-#pragma unroll
-    for (int j = 0; j < VN; ++j) ag[c][j] = ab[c][j] = 0.f;
-  uint4 cx[NC], cd[NC], nx[NC], nd[NC];
-  auto load_row = [&](int64_t r, uint4* xd, uint4* dd) {
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int i = lane + 32 * c;
-      if (i < nvec) { xd[c] = ldg16(x + r * d + (int64_t)i * VN); dd[c] = ldg16(dy + r * d + (int64_t)i * VN); }
-    }
-  };
-  if (row < rows) load_row(row, cx, cd);
-  for (; row < rows; row += stride) {
-    const bool more = row + stride < rows;
-    if (more) load_row(row + stride, nx, nd);
-    const float mu = mean[row], rs = rstd[row];
-    uint4 rr[NC];
-    if (dres != nullptr) {
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int i = lane + 32 * c;
-        if (i < nvec) rr[c] = ldg16(dres + row * d + (int64_t)i * VN);
+// TMA-staged LayerNorm backward (large activations, parameter gradients wanted).  The kernel is pure streaming — dy, x and the
+// residual-branch gradient in, dx out, 4 tensor passes — and was latency-bound as long as the rows in flight lived in
+// registers (one warp per row, 204 registers, 0.53 of the HBM roofline).  Here a producer warp streams tiles of R whole rows
+// (R x d x sizeof(T) contiguous bytes per tensor: ONE bulk asynchronous copy each, plus the R means / reciprocal deviations)
+// into a ring of shared-memory stages, so ~100 KB per SM are in flight at all times at no register cost, and 16 consumer warps
+// work out of shared memory.  A row is spread over TPR = d / VN threads (one 16-byte vector each, TPR rounded up to whole
+// warps), 512 / TPR rows per pass, two passes per stage; the row statistics cross the row's warps through a double-buffered
+// shared array: one named barrier per stage.  Per-thread column sums are 3 x VN registers: dgamma = sum dy * xhat, dbeta =
+// sum dy and, optionally, the column sums of the OUTPUT dx — the bias gradient of the Linear that fed the normalised residual
+// stream (the dY it sees is exactly this dx), so its separate 100 MB reduction pass disappears.  Each CTA writes one partial
+// row per sum; ln_bwd_fold_kernel adds them in CTA order (deterministic).
+constexpr int LNB_U = 2;
+
+template <typename T, int LNB_CONSUMERS>
+__global__ void __launch_bounds__(LNB_CONSUMERS + 32, 512 / LNB_CONSUMERS)
+ln_bwd_tma_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ mean,
+                  const float* __restrict__ rstd, const T* __restrict__ dres, T* __restrict__ dx, int64_t rows, int d, int tpr, int rpp,
+                  int nsum, int stages, float* __restrict__ partial) {
+  constexpr int VN = Vec<T>::N, U = LNB_U;
+  extern __shared__ __align__(128) unsigned char lnb_smem[];
+  // rpp: rows per pass (<= 512 / tpr, chosen by the host so that a stage holds a multiple of 4 rows)
+  const int R = rpp * U;                         // rows per stage
+  const int ntens = dres != nullptr ? 3 : 2;
+  const uint32_t row_bytes = (uint32_t)d * sizeof(T);
+  const uint32_t tens_bytes = (uint32_t)R * row_bytes;
+  const uint32_t stat_bytes = ((uint32_t)R * 4 + 15) & ~15u;
+  const uint32_t stage_bytes = ntens * tens_bytes + 2 * stat_bytes;
+  unsigned char* ring = lnb_smem;
+  float* sm_acc = reinterpret_cast<float*>(lnb_smem + (size_t)stages * stage_bytes);                 // [3][d]
+  float* red = sm_acc + 3 * d;                                                                       // [2][U][<= 16 warps][2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * U * 16 * 2);
+  uint64_t* empty = full + stages;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], LNB_CONSUMERS / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int64_t n_tiles = (rows + R - 1) / R;
+  if (warp == LNB_CONSUMERS / 32) {
+    // ===================================================== producer: one lane streams this CTA's tiles through the ring
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t r0 = t * R;
+        const uint32_t nr = (uint32_t)min((int64_t)R, rows - r0);
+        unsigned char* sp = ring + (size_t)st * stage_bytes;
+        mbar_wait(&empty[st], ph ^ 1);
+        const uint32_t sb = nr * 4;   // rows and R are multiples of 4: a whole number of 16-byte units, 16-byte aligned
+        mbar_expect_tx(&full[st], ntens * nr * row_bytes + 2 * sb);
+        bulk_load(sp, x + r0 * d, nr * row_bytes, &full[st]);
+        bulk_load(sp + tens_bytes, dy + r0 * d, nr * row_bytes, &full[st]);
+        if (ntens == 3) bulk_load(sp + 2 * tens_bytes, dres + r0 * d, nr * row_bytes, &full[st]);
+        bulk_load(sp + ntens * tens_bytes, mean + r0, sb, &full[st]);
+        bulk_load(sp + ntens * tens_bytes + stat_bytes, rstd + r0, sb, &full[st]);
+        if (++st == stages) { st = 0; ph ^= 1; }
       }
     }
-    float s1 = 0.f, s2 = 0.f;
+    return;
+  }
+  // ===================================================== consumers
+  const int rl = tid / tpr, v = tid - rl * tpr;    // row slot, vector index inside the row
+  const int nvec = d / VN;
+  const bool col_ok = rl < rpp && v < nvec;
+  const int wpr = tpr >> 5, w0 = rl * wpr;         // warps per row; first warp of this thread's row slot
+  const float inv_d = 1.f / (float)d;
+  float gv[VN], ag[VN], ab[VN], ac[VN];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int i = lane + 32 * c;
-      if (i < nvec) {
-        float xv[VN], dv[VN], gv[VN];
-        unpack16<T>(cx[c], xv); unpack16<T>(cd[c], dv);
+  for (int j = 0; j < VN; ++j) { gv[j] = 0.f; ag[j] = ab[j] = ac[j] = 0.f; }
+  if (col_ok) {
 #pragma unroll
-        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+    for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + v * VN + j, gv + j);
+  }
+  int st = 0, par = 0; uint32_t ph = 0;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, par ^= 1) {
+    const int64_t r0 = t * R;
+    const unsigned char* sp = ring + (size_t)st * stage_bytes;
+    const float* s_mean = reinterpret_cast<const float*>(sp + ntens * tens_bytes);
+    const float* s_rstd = reinterpret_cast<const float*>(sp + ntens * tens_bytes + stat_bytes);
+    mbar_wait(&full[st], ph);
+    uint4 cx[U], cd[U], cr[U];
+    float mu[U], rs[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int lr = u * rpp + rl;                 // row inside the tile
+      ok[u] = col_ok && r0 + lr < rows;
+      if (ok[u]) {
+        const uint32_t off = (uint32_t)lr * row_bytes + (uint32_t)v * 16;
+        cx[u] = *reinterpret_cast<const uint4*>(sp + off);
+        cd[u] = *reinterpret_cast<const uint4*>(sp + tens_bytes + off);
+        if (ntens == 3) cr[u] = *reinterpret_cast<const uint4*>(sp + 2 * tens_bytes + off);
+        mu[u] = s_mean[lr]; rs[u] = s_rstd[lr];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[st]);        // the stage is in registers: the producer may refill it
+    if (++st == stages) { st = 0; ph ^= 1; }
+    // ---- row statistics: s1 = mean(dy * gamma), s2 = mean(dy * gamma * xhat) over the row's TPR threads
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s1 = 0.f, s2 = 0.f;
+      if (ok[u]) {
+        float xv[VN], dv[VN];
+        unpack16<T>(cx[u], xv); unpack16<T>(cd[u], dv);
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
-          const float xh = (xv[j] - mu) * rs, g = dv[j] * gv[j];
+          const float xh = (xv[j] - mu[u]) * rs[u], g = dv[j] * gv[j];
           s1 += g; s2 = fmaf(g, xh, s2);
-          ag[c][j] = fmaf(dv[j], xh, ag[c][j]); ab[c][j] += dv[j];
         }
       }
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) { red[((par * U + u) * 16 + warp) * 2] = s1; red[((par * U + u) * 16 + warp) * 2 + 1] = s2; }
     }
-    s1 = warp_sum(s1) / d;
-    s2 = warp_sum(s2) / d;
+    asm volatile("bar.sync 1, %0;" ::"n"(LNB_CONSUMERS) : "memory");
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int i = lane + 32 * c;
-      if (i < nvec) {
-        float xv[VN], dv[VN], gv[VN], o[VN];
-        unpack16<T>(cx[c], xv); unpack16<T>(cd[c], dv);
+    for (int u = 0; u < U; ++u) {
+      if (!ok[u]) continue;
+      float s1 = 0.f, s2 = 0.f;
+      for (int w = 0; w < wpr; ++w) { s1 += red[((par * U + u) * 16 + w0 + w) * 2]; s2 += red[((par * U + u) * 16 + w0 + w) * 2 + 1]; }
+      s1 *= inv_d; s2 *= inv_d;
+      float xv[VN], dv[VN], o[VN];
+      unpack16<T>(cx[u], xv); unpack16<T>(cd[u], dv);
 #pragma unroll
-        for (int j = 0; j < VN; j += 4) Vec<float>::load(gamma + i * VN + j, gv + j);
+      for (int j = 0; j < VN; ++j) {
+        const float xh = (xv[j] - mu[u]) * rs[u];
+        o[j] = rs[u] * (dv[j] * gv[j] - s1 - xh * s2);
+        ag[j] = fmaf(dv[j], xh, ag[j]); ab[j] += dv[j];
+      }
+      if (ntens == 3) {
+        float r[VN];
+        unpack16<T>(cr[u], r);
 #pragma unroll
-        for (int j = 0; j < VN; ++j) o[j] = rs * (dv[j] * gv[j] - s1 - (xv[j] - mu) * rs * s2);
-        if (dres != nullptr) {
-          float r[VN];
-          unpack16<T>(rr[c], r);
+        for (int j = 0; j < VN; ++j) o[j] += r[j];
+      }
+      Vec<T>::store(dx + (r0 + u * rpp + rl) * d + (int64_t)v * VN, o);
+      if (nsum == 3) {
 #pragma unroll
-          for (int j = 0; j < VN; ++j) o[j] += r[j];
-        }
-        Vec<T>::store(dx + row * d + (int64_t)i * VN, o);
+        for (int j = 0; j < VN; ++j) ac[j] += to_f32(from_f32<T>(o[j]));   // column sums of dx as stored (rounded), as a separate pass would see it
       }
     }
-#pragma unroll
-    for (int c = 0; c < NC; ++c) { cx[c] = nx[c]; cd[c] = nd[c]; }
   }
-  // fold the 8 warps' column sums in warp order, then one partial row per CTA
-  for (int w = 0; w < 8; ++w) {
-    if (warp == w) {
+  // fold the row slots of the CTA in slot order, then one partial row per sum
+  asm volatile("bar.sync 1, %0;" ::"n"(LNB_CONSUMERS) : "memory");
+  for (int sidx = 0; sidx < rpp; ++sidx) {
+    if (rl == sidx && col_ok) {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        const int i = lane + 32 * c;
-        if (i < nvec) {
-#pragma unroll
-          for (int j = 0; j < VN; ++j) {
-            const int col = i * VN + j;
-            sm_acc[col] = (w == 0 ? 0.f : sm_acc[col]) + ag[c][j];
-            sm_acc[d + col] = (w == 0 ? 0.f : sm_acc[d + col]) + ab[c][j];
-          }
-        }
+      for (int j = 0; j < VN; ++j) {
+        const int col = v * VN + j;
+        sm_acc[col] = (sidx == 0 ? 0.f : sm_acc[col]) + ag[j];
+        sm_acc[d + col] = (sidx == 0 ? 0.f : sm_acc[d + col]) + ab[j];
+        if (nsum == 3) sm_acc[2 * d + col] = (sidx == 0 ? 0.f : sm_acc[2 * d + col]) + ac[j];
       }
     }
-    __syncthreads();
+    asm volatile("bar.sync 1, %0;" ::"n"(LNB_CONSUMERS) : "memory");
   }
-  for (int c = threadIdx.x; c < 2 * d; c += 256) partial[(int64_t)blockIdx.x * 2 * d + c] = sm_acc[c];
+  for (int c = tid; c < nsum * d; c += LNB_CONSUMERS) partial[(int64_t)blockIdx.x * nsum * d + c] = sm_acc[c];
 }
 
 __global__ void __launch_bounds__(256)
-ln_bwd_fold_kernel(const float* __restrict__ partial, int n_parts, int d, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+ln_bwd_fold_kernel(const float* __restrict__ partial, int n_parts, int d, int nsum, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dxsum) {
   const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= 2 * d) return;
+  if (c >= nsum * d) return;
   float t = 0.f;
-  for (int p = 0; p < n_parts; ++p) t += partial[(int64_t)p * 2 * d + c];
-  if (c < d) dgamma[c] = t; else dbeta[c - d] = t;
+  for (int p = 0; p < n_parts; ++p) t += partial[(int64_t)p * nsum * d + c];
+  if (c < d) dgamma[c] = t; else if (c < 2 * d) dbeta[c - d] = t; else dxsum[c - 2 * d] = t;
 }
 
 template <typename T>
@@ -775,12 +831,12 @@ static unsigned int* colsum_counters();
 static int64_t colsum_chunks(int64_t rows, int64_t n, int vn);
 
 extern "C" size_t tsw_layernorm_bwd_workspace_bytes(int64_t rows, int64_t d) {
-  const size_t parts = (size_t)std::max<int64_t>(std::max(colsum_chunks(rows, d, 4), colsum_chunks(rows, d, 8)), sm_count());
-  return sizeof(float) * 2 * (size_t)d * parts;
+  const size_t parts = (size_t)std::max<int64_t>(std::max(colsum_chunks(rows, d, 4), colsum_chunks(rows, d, 8)), 2 * (int64_t)sm_count());
+  return sizeof(float) * 3 * (size_t)d * parts;
 }
 
 extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dres,
-                                 void* dx, float* dgamma, float* dbeta, int64_t rows, int64_t d, int dtype, void* workspace,
+                                 void* dx, float* dgamma, float* dbeta, float* dx_colsum, int64_t rows, int64_t d, int dtype, void* workspace,
                                  size_t workspace_bytes, tsw_stream_t stream) {
   TSW_CHECK_ARG(dy && x && gamma && mean && rstd && dx && rows > 0, "layernorm_bwd: null/empty argument");
   TSW_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta go together");
@@ -791,23 +847,58 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   cudaStream_t st = as_stream(stream);
   const int nc = (int)((d / vn + 31) / 32);
   static const bool two_pass = getenv("TSW_LN_BWD_TWO_PASS") != nullptr;
-  if (dgamma && nc <= 4 && rows >= 4096 && !two_pass) {
-    // single pass: dx and the parameter gradients from one sweep (large activations; small ones stay on the two-pass form,
-    // whose parameter pass spreads over more CTAs than there are 8-row groups)
-    const unsigned g1 = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count());
-    float* partial = (float*)workspace;
-    const size_t smem = sizeof(float) * 2 * (size_t)d;
-#define LN_FUSED(NCV) DISPATCH_T(dtype, (ln_bwd_fused_kernel<T, NCV><<<g1, 256, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d, partial)))
-    if (nc <= 1) { LN_FUSED(1); } else if (nc <= 2) { LN_FUSED(2); } else if (nc <= 3) { LN_FUSED(3); } else { LN_FUSED(4); }
-#undef LN_FUSED
-    TSW_LAUNCH_CHECK();
-    ln_bwd_fold_kernel<<<(unsigned)((2 * d + 255) / 256), 256, 0, st>>>(partial, (int)g1, (int)d, dgamma, dbeta);
-    TSW_LAUNCH_CHECK();
-    return TSW_OK;
+  const int tpr = (int)(((d / vn) + 31) / 32 * 32);   // threads per row of the staged kernel, whole warps
+  const int es = dtype == TSW_F32 ? 4 : 2;
+  static const int ln_cons = getenv("TSW_LN_CONS") ? atoi(getenv("TSW_LN_CONS")) : 512;   // consumer threads per CTA: 512 (one CTA / SM) | 256 (two)
+  const int ncons = (ln_cons == 256 && tpr <= 256) ? 256 : 512;
+  if (dgamma && tpr <= ncons && rows >= 4096 && rows % 4 == 0 && !two_pass) {
+    // single pass: dx, the parameter gradients and (optionally) the column sums of dx from one sweep (large activations; small
+    // ones stay on the two-pass form, whose parameter pass spreads over more CTAs than there are row groups).  rows % 4 and a
+    // stage of a multiple of 4 rows: the per-tile slices of the fp32 statistics are then whole, aligned 16-byte units.
+    int rpp = ncons / tpr;
+    if ((rpp * LNB_U) % 4 != 0 && rpp > 1) rpp -= rpp % 2;   // d = 768: 5 -> 4 rows per pass
+    const int R = rpp * LNB_U, nsum = dx_colsum ? 3 : 2, ntens = dres ? 3 : 2;
+    if ((R * 4) % 16 == 0) {
+      const size_t stage_bytes = (size_t)ntens * R * d * es + 2 * (((size_t)R * 4 + 15) & ~(size_t)15);
+      const size_t fixed = sizeof(float) * (3 * (size_t)d + 2 * LNB_U * 16 * 2) + 16 * sizeof(uint64_t);
+      const size_t budget = (ncons == 512 ? 200 : 100) * 1024;
+      int stages = (int)std::min<size_t>(8, (budget - fixed) / stage_bytes);
+      static const int stages_env = getenv("TSW_LN_STAGES") ? atoi(getenv("TSW_LN_STAGES")) : 0;
+      if (stages_env > 0) stages = std::min(stages, stages_env);
+      if (stages >= 2) {
+        const int64_t n_tiles = (rows + R - 1) / R;
+        const unsigned g1 = (unsigned)std::min<int64_t>(n_tiles, (int64_t)sm_count() * (512 / ncons));
+        float* partial = (float*)workspace;
+        const size_t smem = (size_t)stages * stage_bytes + fixed;
+        static bool attr_done = false;
+        if (!attr_done) {
+          TSW_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<float, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+          TSW_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<__nv_bfloat16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+          TSW_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<float, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+          TSW_CUDA(cudaFuncSetAttribute(ln_bwd_tma_kernel<__nv_bfloat16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+          attr_done = true;
+        }
+        if (ncons == 512) {
+          DISPATCH_T(dtype, (ln_bwd_tma_kernel<T, 512><<<g1, 544, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows,
+                                                                               (int)d, tpr, rpp, nsum, stages, partial)));
+        } else {
+          DISPATCH_T(dtype, (ln_bwd_tma_kernel<T, 256><<<g1, 288, smem, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows,
+                                                                               (int)d, tpr, rpp, nsum, stages, partial)));
+        }
+        TSW_LAUNCH_CHECK();
+        ln_bwd_fold_kernel<<<(unsigned)((nsum * d + 255) / 256), 256, 0, st>>>(partial, (int)g1, (int)d, nsum, dgamma, dbeta, dx_colsum);
+        TSW_LAUNCH_CHECK();
+        return TSW_OK;
+      }
+    }
   }
   const unsigned grid = (unsigned)std::min<int64_t>((rows + 7) / 8, (int64_t)sm_count() * 2);
   DISPATCH_T(dtype, LN_DISPATCH_NC(nc, (ln_bwd_dx_kernel<T, NC><<<grid, 256, 0, st>>>((const T*)dy, (const T*)x, gamma, mean, rstd, (const T*)dres, (T*)dx, rows, (int)d))));
   TSW_LAUNCH_CHECK();
+  if (dx_colsum) {   // small activations / frozen affine parameters: the column sums of dx take their own (stream-ordered) pass
+    const int rc = tsw_colsum(dx, dtype, rows, d, d, dx_colsum, workspace, workspace_bytes, stream);
+    if (rc != TSW_OK) return rc;
+  }
   if (!dgamma) return TSW_OK;   // frozen affine parameters: no parameter-gradient pass
   const int64_t chunks = colsum_chunks(rows, d, vn);
   const int64_t rpc = (rows + chunks - 1) / chunks;

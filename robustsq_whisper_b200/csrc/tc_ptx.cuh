@@ -59,13 +59,13 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
   return ok != 0;
 }
-// Bounded wait: each probe sleeps up to ~16 us in hardware; the SM clock is read every 64 probes and after ~2 s of
+// Bounded wait: each probe sleeps up to ~2 us in hardware; the SM clock is read every 64 probes and after ~2 s of
 // waiting the kernel traps, which surfaces as a CUDA error instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = 0;
   uint32_t probes = 0;
-  while (!mbar_try_wait_hint(bar, parity, 16384u)) {
+  while (!mbar_try_wait_hint(bar, parity, 2048u)) {
     if ((++probes & 63u) == 0) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
@@ -79,6 +79,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// one bulk asynchronous copy (TMA, non-tensor form) of a contiguous slab into shared memory, completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
   asm volatile(

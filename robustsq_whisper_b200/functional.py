@@ -102,6 +102,30 @@ def grad_out(w: Tensor) -> Optional[Tensor]:
     return slot.view_as(slot)
 
 
+# Bias gradients that ride in the producer of their dY: the LayerNorm-backward kernel also emits the column sums of the
+# residual-stream gradient dx it writes, which is exactly the dY the preceding Linear (attention out-projection, MLP fc2)
+# receives next.  One entry: the most recent LayerNorm-backward output, matched by object identity and storage.
+_DX_COLSUM = {}
+
+
+def _remember_colsum(t: Tensor, cs: Tensor) -> None:
+    _DX_COLSUM.clear()
+    _DX_COLSUM["last"] = (weakref.ref(t), t.data_ptr(), t._version, cs)
+
+
+def _take_colsum(dy: Tensor, n: int) -> Optional[Tensor]:
+    ent = _DX_COLSUM.pop("last", None)
+    if ent is None or ent[0]() is not dy or ent[1] != dy.data_ptr() or ent[2] != dy._version or ent[3].numel() != n or dy.shape[-1] != n:
+        return None
+    return ent[3]
+
+
+def bias_grad(dy: Tensor, dy2: Tensor, rows: int, n: int) -> Tensor:
+    """Column sums of dY: taken from the producer when it computed them on the way (``_take_colsum``), else one reduction pass."""
+    cs = _take_colsum(dy, n)
+    return cs if cs is not None else K.colsum(dy2, rows, n)
+
+
 def _impl_for(dtype: torch.dtype) -> int:
     return _C.GEMM_AUTO if dtype == torch.bfloat16 else _C.GEMM_SIMT
 
@@ -142,7 +166,7 @@ class _Linear(Function):
         if ctx.needs_input_grad[1]:
             dw = K.gemm(dy2, x2, M=N, N=Kd, K=rows, a_mn=True, b_mn=True, lda=N, ldb=Kd, out_dtype=torch.float32, impl=impl, out=grad_out(w))
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = K.colsum(dy2, rows, N)
+            db = bias_grad(dy, dy2, rows, N)
         dres = dy if ctx.has_res else None
         return dx, dw, db, dres
 
@@ -232,7 +256,7 @@ class _MLP(Function):
         if need[3]:
             dw2 = K.gemm(dy2, g, M=N, N=H, K=rows, a_mn=True, b_mn=True, lda=N, ldb=H, out_dtype=torch.float32, impl=impl, out=grad_out(w2))
         if need[4]:
-            db2 = K.colsum(dy2, rows, N)
+            db2 = bias_grad(dy, dy2, rows, N)
         if not (need[0] or need[1] or need[2]):
             return None, None, None, dw2, db2, (dy if ctx.has_res else None)
         # fc1's bias gradient = column sums of dh: in the bf16 regime they ride in the epilogue of the GEMM that produces dh
@@ -267,7 +291,9 @@ class _LayerNorm(Function):
     @staticmethod
     def backward(ctx, dy: Tensor):
         xin, gamma, mean, rstd = ctx.saved_tensors
-        dx, dg, db = K.layernorm_bwd(dy, xin, gamma.detach(), mean, rstd, param_grads=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dx, dg, db, cs = K.layernorm_bwd(dy, xin, gamma.detach(), mean, rstd, param_grads=ctx.needs_input_grad[1] or ctx.needs_input_grad[2],
+                                         want_dx_colsum=True)
+        _remember_colsum(dx, cs)
         return dx, dg, db, None, (dx if ctx.has_res else None)
 
 
@@ -288,7 +314,9 @@ class _LayerNormTap(Function):
         x, gamma, mean, rstd = ctx.saved_tensors
         if gy is None:
             return g_skip, None, None, None
-        dx, dg, db = K.layernorm_bwd(gy, x, gamma.detach(), mean, rstd, dres=g_skip, param_grads=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        dx, dg, db, cs = K.layernorm_bwd(gy, x, gamma.detach(), mean, rstd, dres=g_skip, param_grads=ctx.needs_input_grad[1] or ctx.needs_input_grad[2],
+                                         want_dx_colsum=True)
+        _remember_colsum(dx, cs)
         return dx, dg, db, None
 
 
@@ -483,7 +511,9 @@ class _PackedSelfAttention(Function):
         rows = B * S
         q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
         dqkv = torch.empty_like(qkv)
-        K.fmha_bwd(q, k, v, o, do, lse, n_head, scale, causal=causal, out=(dqkv[..., :d], dqkv[..., d:2 * d], dqkv[..., 2 * d:]))
+        need_b = ctx.needs_input_grad[2] or ctx.needs_input_grad[5]
+        res = K.fmha_bwd(q, k, v, o, do, lse, n_head, scale, causal=causal, out=(dqkv[..., :d], dqkv[..., d:2 * d], dqkv[..., 2 * d:]),
+                         bias_grads=need_b)   # the bias gradients of q and v ride in the attention backward (no column-sum passes over dqkv)
         dy2 = dqkv.view(rows, d3)
         w = shadow_cat((wq, wk, wv), x2.dtype)
         dx = K.gemm(dy2, w, M=rows, N=d, K=d3, b_mn=True, ldb=d, out_dtype=x2.dtype).view(B, S, d) if ctx.needs_input_grad[0] else None
@@ -492,19 +522,33 @@ class _PackedSelfAttention(Function):
         if need[1] or need[3] or need[4]:
             dw = K.gemm(dy2, x2, M=d3, N=d, K=rows, a_mn=True, b_mn=True, lda=d3, ldb=d, out_dtype=torch.float32)
             dwq, dwk, dwv = dw[:d], dw[d:2 * d], dw[2 * d:]
-        # bias gradients of q and v only (Whisper's key projection has none): two d-wide column sums over slices of dqkv
+        # bias gradients of q and v only (Whisper's key projection has none)
         if need[2]:
-            dbq = K.colsum(dy2[:, :d], rows, d, ld=d3)
+            dbq = res[3]
         if need[5]:
-            dbv = K.colsum(dy2[:, 2 * d:], rows, d, ld=d3)
+            dbv = res[4]
         return dx, dwq, dbq, dwk, dwv, dbv, None, None, None
+
+
+class MemoryGradSink:
+    """The encoder memory feeds the cross-attention of every decoder layer, so its gradient is the sum of L gradients of
+    48512 x 1024 bf16 each — which the autograd engine forms with L - 1 separate 3-pass adds.  With a sink (one per decoder
+    forward), each layer's k|v input-gradient GEMM accumulates into one buffer in its epilogue (residual = the buffer, in
+    place) and only the layer whose backward runs last hands the buffer to autograd; the others return no gradient."""
+
+    def __init__(self):
+        self.uses = 0
+        self.buf: Optional[Tensor] = None
 
 
 class _PackedCrossAttention(Function):
     """Cross-attention with the k | v projections of the memory packed into one (2d, d) GEMM; q comes in projected."""
 
     @staticmethod
-    def forward(ctx, q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float):
+    def forward(ctx, q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float, sink: Optional[MemoryGradSink] = None):
+        ctx.sink = sink
+        if sink is not None:
+            sink.uses += 1
         B, Sk, d = xa.shape
         xa2 = xa.reshape(B * Sk, d)
         if not xa2.is_contiguous():
@@ -527,18 +571,31 @@ class _PackedCrossAttention(Function):
         rows = B * Sk
         dq = torch.empty_like(q)
         dkv = torch.empty_like(kv)
-        K.fmha_bwd(q, kv[..., :d], kv[..., d:], o, do, lse, n_head, scale, out=(dq, dkv[..., :d], dkv[..., d:]))
+        res = K.fmha_bwd(q, kv[..., :d], kv[..., d:], o, do, lse, n_head, scale, out=(dq, dkv[..., :d], dkv[..., d:]), bias_grads=True)
+        _remember_colsum(dq, res[3])   # dq goes to the query projection's Linear next: its bias gradient is already here
         dy2 = dkv.view(rows, d2)
         w = shadow_cat((wk, wv), xa2.dtype)
-        dxa = K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, out_dtype=xa2.dtype).view(B, Sk, d) if ctx.needs_input_grad[1] else None
+        dxa = None
+        sink = ctx.sink
+        if ctx.needs_input_grad[1]:
+            if sink is None:
+                dxa = K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, out_dtype=xa2.dtype).view(B, Sk, d)
+            else:
+                sink.uses -= 1
+                if sink.buf is None:
+                    sink.buf = K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, out_dtype=xa2.dtype)
+                else:   # buf += dy2 W in the GEMM epilogue (residual read and output written at the same element by the same thread)
+                    K.gemm(dy2, w, M=rows, N=d, K=d2, b_mn=True, ldb=d, residual=sink.buf, out=sink.buf)
+                if sink.uses == 0:   # the last backward of the L layers: autograd gets the whole sum, once
+                    dxa, sink.buf = sink.buf.view(B, Sk, d), None
         need = ctx.needs_input_grad
         dwk = dwv = dbv = None
         if need[2] or need[3]:
             dw = K.gemm(dy2, xa2, M=d2, N=d, K=rows, a_mn=True, b_mn=True, lda=d2, ldb=d, out_dtype=torch.float32)
             dwk, dwv = dw[:d], dw[d:]
         if need[4]:
-            dbv = K.colsum(dy2[:, d:], rows, d, ld=d2)   # the value half only: the key projection has no bias
-        return dq, dxa, dwk, dwv, dbv, None, None
+            dbv = res[4]   # the value half only: the key projection has no bias
+        return dq, dxa, dwk, dwv, dbv, None, None, None
 
 
 def packed_attention_ok(x: Tensor, n_head: int) -> bool:
@@ -550,8 +607,9 @@ def self_attention_packed(x: Tensor, wq: Tensor, bq: Tensor, wk: Tensor, wv: Ten
     return _PackedSelfAttention.apply(x, wq, bq, wk, wv, bv, n_head, scale, causal)
 
 
-def cross_attention_packed(q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float) -> Tensor:
-    return _PackedCrossAttention.apply(q, xa, wk, wv, bv, n_head, scale)
+def cross_attention_packed(q: Tensor, xa: Tensor, wk: Tensor, wv: Tensor, bv: Tensor, n_head: int, scale: float,
+                           sink: Optional[MemoryGradSink] = None) -> Tensor:
+    return _PackedCrossAttention.apply(q, xa, wk, wv, bv, n_head, scale, sink)
 
 
 def attention(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len: Optional[Tensor] = None, causal: bool = False,

@@ -199,7 +199,10 @@ def layernorm_fwd(x: Tensor, gamma: Tensor, beta: Tensor, eps: float, res: Optio
     return y, sum_out, mean, rstd
 
 
-def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dres: Optional[Tensor] = None, param_grads: bool = True):
+def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dres: Optional[Tensor] = None, param_grads: bool = True,
+                  want_dx_colsum: bool = False):
+    """-> dx, dgamma, dbeta[, column sums of dx (fp32, d) when ``want_dx_colsum``: the bias gradient of the Linear that fed the
+    normalised stream, produced in the same sweep]."""
     lib = _C.load()
     d = x.shape[-1]
     rows = x.numel() // d
@@ -209,10 +212,13 @@ def layernorm_bwd(dy: Tensor, x: Tensor, gamma: Tensor, mean: Tensor, rstd: Tens
     dx = torch.empty_like(x)
     dgamma = torch.empty(d, dtype=torch.float32, device=x.device) if param_grads else None
     dbeta = torch.empty(d, dtype=torch.float32, device=x.device) if param_grads else None
+    dxsum = torch.empty(d, dtype=torch.float32, device=x.device) if want_dx_colsum else None
     ws = _ws(lib.tsw_layernorm_bwd_workspace_bytes(rows, d), x.device)
-    check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d,
-                                dtype_code(x.dtype), ptr(ws), ws.numel(), stream()), "tsw_layernorm_bwd")
+    check(lib.tsw_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dres), ptr(dx), ptr(dgamma), ptr(dbeta), ptr(dxsum),
+                                rows, d, dtype_code(x.dtype), ptr(ws), ws.numel(), stream()), "tsw_layernorm_bwd")
     _count(2 if param_grads else 1)
+    if want_dx_colsum:
+        return dx, dgamma, dbeta, dxsum
     return dx, dgamma, dbeta
 
 
@@ -348,8 +354,10 @@ def fmha_fwd(q: Tensor, k: Tensor, v: Tensor, n_head: int, scale: float, key_len
 
 
 def fmha_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, do: Tensor, lse: Tensor, n_head: int, scale: float,
-             key_len: Optional[Tensor] = None, causal: bool = False, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None):
-    """-> dq, dk, dv (bf16, shapes and row strides of q, k, v; ``out`` supplies them, e.g. as slices of a packed buffer)."""
+             key_len: Optional[Tensor] = None, causal: bool = False, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None,
+             bias_grads: bool = False):
+    """-> dq, dk, dv (bf16, shapes and row strides of q, k, v; ``out`` supplies them, e.g. as slices of a packed buffer)
+    [, column sums of dq and of dv (fp32, d) when ``bias_grads``: the bias gradients of the query / value projections]."""
     lib = _C.load()
     B, Sq, d = q.shape
     Sk = k.shape[1]
@@ -362,10 +370,14 @@ def fmha_bwd(q: Tensor, k: Tensor, v: Tensor, o: Tensor, do: Tensor, lse: Tensor
         if (dq.stride(1), dk.stride(1), dv.stride(1)) != (q.stride(1), k.stride(1), v.stride(1)):
             raise _C.TswError("fmha_bwd: dq / dk / dv must have the row strides of q / k / v")
     ws = _ws(lib.tsw_fmha_bwd_workspace_bytes(B, n_head, Sq), q.device)
+    dqs = torch.empty(d, dtype=torch.float32, device=q.device) if bias_grads else None
+    dvs = torch.empty(d, dtype=torch.float32, device=q.device) if bias_grads else None
     check(lib.tsw_fmha_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dq), ptr(dk), ptr(dv), B, n_head, Sq, Sk, q.stride(1),
-                           k.stride(1), v.stride(1), o.stride(1), do.stride(1), scale, ptr(key_len), int(causal), ptr(ws), ws.numel(),
-                           stream()), "tsw_fmha_bwd")
+                           k.stride(1), v.stride(1), o.stride(1), do.stride(1), scale, ptr(key_len), int(causal), ptr(dqs), ptr(dvs), ptr(ws),
+                           ws.numel(), stream()), "tsw_fmha_bwd")
     _count(4)
+    if bias_grads:
+        return dq, dk, dv, dqs, dvs
     return dq, dk, dv
 
 

@@ -58,8 +58,10 @@ class QFormerTgtSpkWhisperDecoder_V2(AbsDecoder, BatchScorerInterface):
         dec = self.decoders
         dt = memory.dtype
         x = F.decoder_embed(dec.token_embedding.weight, dec.positional_embedding, spk_prompt, ys_in, self.startofprev_token, dt)
+        # one gradient sink for the memory: the L cross-attention layers sum their memory gradients inside their GEMM epilogues
+        sink = F.MemoryGradSink() if (torch.is_grad_enabled() and memory.requires_grad) else None
         for block in dec.blocks:
-            x = W.residual_block(block, x, xa=memory, causal=True)
+            x = W.residual_block(block, x, xa=memory, causal=True, sink=sink)
         return F.layernorm(x, dec.ln.weight, dec.ln.bias, dec.ln.eps)
 
     def hidden_for_loss(self, hs_pad: Tensor, ys_in_pad: Tensor, spk_prompt: Tensor) -> Tensor:

@@ -111,7 +111,8 @@ def build_text_decoder(name: str, download_root=None) -> TextDecoderParams:
 
 
 # ----------------------------------------------------------------------------------------------- compute
-def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False, residual: Optional[Tensor] = None) -> Tensor:
+def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False, residual: Optional[Tensor] = None,
+        sink: Optional["F.MemoryGradSink"] = None) -> Tensor:
     """openai-whisper MultiHeadAttention: q,k scaled by dh**-0.25 each (folded into the softmax scale), fp32 softmax,
     no key-padding mask (the reference passes none, whisper_encoder.py:497-500)."""
     if F.packed_attention_ok(x, p.n_head):   # training regime: packed projections around the fused attention kernel
@@ -126,7 +127,7 @@ def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool
             if lora.has_lora(p.key, p.value):
                 a = lora.cross_attention_packed(p, q, xa, p.n_head, scale)
             else:
-                a = F.cross_attention_packed(q, xa, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale)
+                a = F.cross_attention_packed(q, xa, p.key.weight, p.value.weight, p.value.bias, p.n_head, scale, sink)
         return lora.linear(p.out, a, residual=residual)
     src = x if xa is None else xa
     q = lora.linear(p.query, x)
@@ -137,12 +138,12 @@ def mha(p: AttentionParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool
     return lora.linear(p.out, a, residual=residual)
 
 
-def residual_block(p: BlockParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False) -> Tensor:
+def residual_block(p: BlockParams, x: Tensor, xa: Optional[Tensor] = None, causal: bool = False, sink: Optional["F.MemoryGradSink"] = None) -> Tensor:
     """openai-whisper ResidualAttentionBlock: x += attn(ln(x)); [x += cross_attn(ln(x), xa)]; x += mlp(ln(x))."""
     x, h = F.layernorm_tap(x, p.attn_ln.weight, p.attn_ln.bias, p.attn_ln.eps)
     x = mha(p.attn, h, causal=causal, residual=x)
     if xa is not None:
         x, h = F.layernorm_tap(x, p.cross_attn_ln.weight, p.cross_attn_ln.bias, p.cross_attn_ln.eps)
-        x = mha(p.cross_attn, h, xa=xa, residual=x)
+        x = mha(p.cross_attn, h, xa=xa, residual=x, sink=sink)
     x, h = F.layernorm_tap(x, p.mlp_ln.weight, p.mlp_ln.bias, p.mlp_ln.eps)
     return F.mlp(h, p.mlp[0].weight, p.mlp[0].bias, p.mlp[2].weight, p.mlp[2].bias, residual=x)
