@@ -17,19 +17,34 @@ from torch.autograd import Function
 from . import functional as _F
 
 
+def _through_host(t: Tensor) -> bool:
+    """gloo (CPU tests, and emulated ranks sharing one GPU) moves device tensors through host memory."""
+    return t.is_cuda and dist.get_backend() == "gloo"
+
+
 class _AllGatherWithGrad(Function):
     @staticmethod
     def forward(ctx, x: Tensor):
         world = dist.get_world_size()
         x = x.contiguous()
+        ctx.rows = x.shape[0]
+        if _through_host(x):
+            xc = x.cpu()
+            oc = torch.empty((world * xc.shape[0],) + tuple(xc.shape[1:]), dtype=xc.dtype)
+            dist.all_gather_into_tensor(oc, xc)
+            return oc.to(x.device)
         out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
         dist.all_gather_into_tensor(out, x)
-        ctx.rows = x.shape[0]
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
         g = g.contiguous()
+        if _through_host(g):
+            gc = g.cpu()
+            oc = torch.empty((ctx.rows,) + tuple(gc.shape[1:]), dtype=gc.dtype)
+            dist.reduce_scatter_tensor(oc, gc, op=dist.ReduceOp.SUM)
+            return oc.to(g.device)
         out = torch.empty((ctx.rows,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
         dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
         return out
@@ -40,6 +55,11 @@ def all_gather_with_grad(x: Tensor) -> Tensor:
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return x
     return _AllGatherWithGrad.apply(x)
+
+
+class _Done:
+    def wait(self):
+        return True
 
 
 class _Bucket:
@@ -112,6 +132,12 @@ class GradientAllReducer:
                 b.flat16 = torch.empty(b.numel, dtype=torch.bfloat16, device=b.flat.device)
             K.cast(b.flat, torch.bfloat16, out=b.flat16)
             b.work = dist.all_reduce(b.flat16, op=dist.ReduceOp.AVG, async_op=True)
+            return
+        if _through_host(b.flat):   # emulated ranks on one GPU: blocking, through the host
+            fc = b.flat.cpu()
+            dist.all_reduce(fc, op=dist.ReduceOp.SUM)
+            b.flat.copy_(fc)
+            b.work = _Done()
             return
         b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, async_op=True)
 

@@ -1,7 +1,8 @@
 """Data-parallel self-check: W ranks x B utterances must equal ONE process on the concatenated W*B batch.
 
-Run inside an initialised ``torch.distributed`` job (bench.py --selfcheck under torchrun, or the 2-rank GPU test).  Every
-rank
+Run inside an initialised ``torch.distributed`` job (bench.py --selfcheck under torchrun over NCCL, or the 2-rank GPU test —
+which, on a box with a single GPU, runs both ranks on that GPU with gloo carrying the collectives through host memory: the
+kernels, the reducer and the gathered-negative logic are the same, only the wire differs).  Every rank
   1. takes its shard of a deterministic global batch and runs the public training step: ``model(**shard, utt_id=...)`` with
      ``gather_negatives=True`` (speaker exchange on the host, Arc-InfoNCE negatives and AAM labels over the global batch,
      all-gathered pool with reduce-scatter backward), ``loss.backward()``, ``GradientAllReducer.reduce()``  — twice, so the
@@ -29,7 +30,8 @@ def _clone(batch):
 
 
 def _to(batch, dev):
-    return {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    """The tensor arguments of ``model.forward`` on the device (``utt_id`` is passed separately)."""
+    return {k: v.to(dev) for k, v in batch.items() if torch.is_tensor(v)}
 
 
 def data_parallel_selfcheck(whisper_model: str = "tiny", batch_per_rank: int = 4, mix_s: float = 6.0, enr_s: float = 3.0,
@@ -64,12 +66,12 @@ def data_parallel_selfcheck(whisper_model: str = "tiny", batch_per_rank: int = 4
     ddp_grads = {n: p.grad.detach().float().clone() for n, p in model.named_parameters() if p.grad is not None}
     torch.manual_seed(rng_seed)
     _, my_neg, my_labels = model._global_negatives(shard["utt_id"])   # the same draw the step made (same generator state)
-    all_neg = [torch.empty_like(my_neg) for _ in range(world)]
-    neg_dev = [t.to(dev) for t in all_neg]
-    dist.all_gather(neg_dev, my_neg.to(dev))
-    global_neg = torch.cat([t.cpu() for t in neg_dev], dim=0)
+    host = dist.get_backend() == "gloo"   # emulated ranks on one GPU: collectives on host tensors
+    all_neg = [torch.empty_like(my_neg) if host else torch.empty_like(my_neg).to(dev) for _ in range(world)]
+    dist.all_gather(all_neg, my_neg if host else my_neg.to(dev))
+    global_neg = torch.cat([t.cpu() for t in all_neg], dim=0)
     for k in losses:
-        t = losses[k].to(dev)
+        t = losses[k].cpu() if host else losses[k].to(dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         losses[k] = (t / world).item()
 
