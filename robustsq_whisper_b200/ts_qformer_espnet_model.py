@@ -393,14 +393,16 @@ class TgtSpkQformerESPnetASRModel_V4(TgtSpkQformerESPnetASRModel_V2):
         neg_idx = kwargs.get("neg_idx")
         speaker_labels = kwargs.get("speaker_labels")   # precomputed on the host by graph.GraphedTrainStep
         neg_weight = None
-        if self.contrastive_weight > 0.0 and neg_idx is None:
-            if self._gathering():   # negatives and speaker labels over the global batch
-                neg_weight, neg_idx, labels_global = self._global_negatives(utt_id)
-                if speaker_labels is None:
-                    speaker_labels = labels_global
-            else:
-                neg_weight, neg_idx = self._negatives(utt_id)
+        gathering = self.contrastive_weight > 0.0 and neg_idx is None and self._gathering()
+        if self.contrastive_weight > 0.0 and neg_idx is None and not gathering:
+            neg_weight, neg_idx = self._negatives(utt_id)   # before the encoder, like the reference (:563-570): same CPU RNG order
         encoder_out, encoder_out_lens, spk_prompt, enroll_embedding = self.encode(speech, speech_lengths, enroll, enroll_lengths)
+        if gathering:
+            # negatives and speaker labels over the global batch: the host-side exchange of speaker strings runs while the
+            # GPU works through the encoder kernels queued above
+            neg_weight, neg_idx, labels_global = self._global_negatives(utt_id)
+            if speaker_labels is None:
+                speaker_labels = labels_global
         if speaker_labels is None:
             speaker_labels = get_speaker_labels(utt_id, self.is_wsj2mix, self.is_ami)
         speaker_labels = speaker_labels.to(enroll_embedding.device, non_blocking=True)
