@@ -640,7 +640,7 @@ struct FmhaBwdParams {
   const float* lse;    // (B, H, Sq)
   const float* delta;  // (B, H, Sq) rowsum(dO * O)
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
-  float* dv_colsum;    // (H * 64) fp32 or null: column sums of dV (bias gradient of the value projection), atomically accumulated
+  float* dv_partial;   // (total work items, 4 lane quarters, 64) fp32 or null: per-item column sums of dV, folded by fmha_dv_colsum_fold_kernel
 };
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -864,6 +864,7 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           reinterpret_cast<uint4*>(dvrow)[0] = z; reinterpret_cast<uint4*>(dvrow)[1] = z;
           reinterpret_cast<uint4*>(dkrow)[0] = z; reinterpret_cast<uint4*>(dkrow)[1] = z;
         }
+        if (p.dv_partial != nullptr && lane < 16) p.dv_partial[((int64_t)w * 4 + quarter) * FD + part * 16 + lane] = 0.f;
         continue;
       }
       const int64_t stat_base = ((int64_t)I.b * p.H + I.h) * p.Sq;
@@ -920,13 +921,15 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
       }
-      if (p.dv_colsum != nullptr) {   // bias gradient of the value projection: sum over this tile's key rows, as stored (bf16-rounded)
+      if (p.dv_partial != nullptr) {   // bias gradient of the value projection: this warp's 32 key rows x 16 columns, as stored (bf16-rounded)
+        float mine = 0.f;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           float t = key < p.Sk ? __bfloat162float(__float2bfloat16_rn(gv[c])) : 0.f;
           t = warp_sum(t);
-          if (lane == c) atomicAdd(p.dv_colsum + I.h * FD + part * 16 + c, t);
+          if (lane == c) mine = t;
         }
+        if (lane < 16) p.dv_partial[((int64_t)w * 4 + quarter) * FD + part * 16 + lane] = mine;   // no atomics: one slot per (item, quarter)
       }
       ++j;
     }
@@ -1048,6 +1051,21 @@ fmha_dq_cast_colsum_kernel(const float* __restrict__ src, __nv_bfloat16* __restr
   }
 }
 
+// dv_colsum[h * 64 + c] = sum over (batch, key tile, lane quarter) of the per-item partial sums, in a fixed order (deterministic):
+// CTA per head, 64 columns x 4 row lanes
+__global__ void __launch_bounds__(256)
+fmha_dv_colsum_fold_kernel(const float* __restrict__ partial, int B, int H, int n_kt, float* __restrict__ out) {
+  __shared__ float sm[4][FD];
+  const int h = blockIdx.x, c = threadIdx.x & 63, l = threadIdx.x >> 6;
+  float t = 0.f;
+  for (int b = 0; b < B; ++b)
+    for (int r = l; r < n_kt * 4; r += 4)   // rows of (key tile, quarter) for this (b, h): items are numbered (b * H + h) * n_kt + kt
+      t += partial[(((int64_t)(b * H + h) * n_kt) * 4 + r) * FD + c];
+  sm[l][c] = t;
+  __syncthreads();
+  if (l == 0) out[h * FD + c] = (sm[0][c] + sm[1][c]) + (sm[2][c] + sm[3][c]);
+}
+
 // (B, S, d) bf16 tensor -> 4-D map {d, S, B, 1}, box {64, 128, 1, 1}, SWIZZLE_128B
 static int make_bsd_map(CUtensorMap* tm, const void* base, int64_t B, int64_t S, int64_t d_cols, int64_t ld, bool f32 = false) {
   EncodeTiledFn enc = get_encode_fn();
@@ -1121,8 +1139,10 @@ extern "C" int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o
   return TSW_OK;
 }
 
+// fp32 dQ accumulator | delta | per-item dV column sums (the latter sized for the longest key sequence the model uses: Sk <= 4 * Sq + 4096)
+static size_t fmha_bwd_dvpart_bytes(int64_t B, int64_t H, int64_t Sk) { return (size_t)(B * H * ((Sk + FK - 1) / FK)) * 4 * FD * 4; }
 extern "C" size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq) {
-  return (size_t)(B * Sq * H * FD) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256);
+  return (size_t)(B * Sq * H * FD) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256) + fmha_bwd_dvpart_bytes(B, H, 4 * Sq + 4096);
 }
 
 extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
@@ -1161,8 +1181,13 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   p.key_len = key_len; p.causal = causal ? 1 : 0;
   p.lse = lse; p.delta = delta;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddk = ldk; p.lddv = ldv;
-  p.dv_colsum = dv_colsum;
-  if (dv_colsum) TSW_CUDA(cudaMemsetAsync(dv_colsum, 0, sizeof(float) * (size_t)dcols, st));
+  float* dv_partial = nullptr;
+  if (dv_colsum) {
+    const size_t head = (size_t)(B * Sq * dcols) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256);
+    if (workspace_bytes < head + fmha_bwd_dvpart_bytes(B, H, Sk)) { set_error("fmha_bwd: workspace too small for the dV column sums (Sk > 4 Sq + 4096)"); return TSW_E_WORKSPACE; }
+    dv_partial = (float*)((char*)workspace + head);
+  }
+  p.dv_partial = dv_partial;
   if (dq_colsum) TSW_CUDA(cudaMemsetAsync(dq_colsum, 0, sizeof(float) * (size_t)dcols, st));
   static bool attr_done = false;
   const size_t smem = sizeof(FmhaBwdSmem);
@@ -1173,6 +1198,10 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
   fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   TSW_LAUNCH_CHECK();
+  if (dv_colsum) {
+    fmha_dv_colsum_fold_kernel<<<(unsigned)H, 256, 0, st>>>(dv_partial, (int)B, (int)H, p.n_kt, dv_colsum);
+    TSW_LAUNCH_CHECK();
+  }
   // dq (B * Sq rows, row stride ldq) bf16 <- contiguous fp32 accumulator
   if (dq_colsum) {
     const int64_t rows = B * Sq;

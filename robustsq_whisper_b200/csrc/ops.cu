@@ -339,14 +339,26 @@ ln_bwd_tma_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float
   for (int c = tid; c < nsum * d; c += LNB_CONSUMERS) partial[(int64_t)blockIdx.x * nsum * d + c] = sm_acc[c];
 }
 
+// fold of the per-CTA partial rows: CTA = 32 columns x 8 partial lanes (lane l adds partials l, l + 8, ... in order; the 8 lane
+// sums are then added in lane order: a fixed summation tree, so the result is bit-reproducible) — 96 CTAs with 19 loads per
+// thread in flight instead of one thread walking all 148 partials of a column
 __global__ void __launch_bounds__(256)
 ln_bwd_fold_kernel(const float* __restrict__ partial, int n_parts, int d, int nsum, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ dxsum) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= nsum * d) return;
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float t = 0.f;
-  for (int p = 0; p < n_parts; ++p) t += partial[(int64_t)p * nsum * d + c];
-  if (c < d) dgamma[c] = t; else if (c < 2 * d) dbeta[c - d] = t; else dxsum[c - 2 * d] = t;
+  if (c < nsum * d)
+    for (int p = ty; p < n_parts; p += 8) t += partial[(int64_t)p * nsum * d + c];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < nsum * d) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += sm[k][tx];
+    if (c < d) dgamma[c] = r; else if (c < 2 * d) dbeta[c - d] = r; else dxsum[c - 2 * d] = r;
+  }
 }
 
 template <typename T>
@@ -886,7 +898,7 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
                                                                                (int)d, tpr, rpp, nsum, stages, partial)));
         }
         TSW_LAUNCH_CHECK();
-        ln_bwd_fold_kernel<<<(unsigned)((nsum * d + 255) / 256), 256, 0, st>>>(partial, (int)g1, (int)d, nsum, dgamma, dbeta, dx_colsum);
+        ln_bwd_fold_kernel<<<(unsigned)((nsum * d + 31) / 32), 256, 0, st>>>(partial, (int)g1, (int)d, nsum, dgamma, dbeta, dx_colsum);
         TSW_LAUNCH_CHECK();
         return TSW_OK;
       }

@@ -17,5 +17,6 @@ def timeit(fn, n=5):
 o, lse = K.fmha_fwd(q, k, v, H, 0.125)
 tf = timeit(lambda: K.fmha_fwd(q, k, v, H, 0.125))
 tb = timeit(lambda: K.fmha_bwd(q, k, v, o, do, lse, H, 0.125))
+tb2 = timeit(lambda: K.fmha_bwd(q, k, v, o, do, lse, H, 0.125, bias_grads=True))
 fl = 4.0 * B * H * S * S * 64
-print(f"B={B} H={H} S={S}: fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TF/s)  bwd {tb:.3f} ms ({2.5 * fl / tb / 1e9:.0f} TF/s)")
+print(f"B={B} H={H} S={S}: fwd {tf:.3f} ms ({fl / tf / 1e9:.0f} TF/s)  bwd {tb:.3f} ms ({2.5 * fl / tb / 1e9:.0f} TF/s)  bwd + q/v bias grads {tb2:.3f} ms")
