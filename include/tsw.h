@@ -197,8 +197,9 @@ int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o, float* ls
  * ldq / ldk / ldv: they may be column slices of one packed q|k|v gradient buffer).
  * workspace holds the fp32 dQ accumulator (filled by bulk tensor reduce-adds) and delta = rowsum(dO * O).
  * dq_colsum / dv_colsum (H * 64) fp32 or NULL: column sums over all (batch, position) rows of dq / dv as stored — the bias
- * gradients of the query / value projections (Whisper's key projection has no bias) — produced on the way: dv in the key-tile
- * epilogue, dq in the fp32 -> bf16 cast pass (atomic accumulation: summation order varies run to run). */
+ * gradients of the query / value projections (Whisper's key projection has no bias) — both NULL or both given; produced by the
+ * launch that casts the fp32 dQ accumulator to bf16 (dq in the same pass, dv by the other half of the grid; atomic accumulation
+ * of per-CTA partial sums: the summation order varies run to run). */
 size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq);
 int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
                  void* dv, int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,

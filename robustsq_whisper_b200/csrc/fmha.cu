@@ -640,7 +640,6 @@ struct FmhaBwdParams {
   const float* lse;    // (B, H, Sq)
   const float* delta;  // (B, H, Sq) rowsum(dO * O)
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
-  float* dv_partial;   // (total work items, 4 lane quarters, 64) fp32 or null: per-item column sums of dV, folded by fmha_dv_colsum_fold_kernel
 };
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -864,7 +863,6 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           reinterpret_cast<uint4*>(dvrow)[0] = z; reinterpret_cast<uint4*>(dvrow)[1] = z;
           reinterpret_cast<uint4*>(dkrow)[0] = z; reinterpret_cast<uint4*>(dkrow)[1] = z;
         }
-        if (p.dv_partial != nullptr && lane < 16) p.dv_partial[((int64_t)w * 4 + quarter) * FD + part * 16 + lane] = 0.f;
         continue;
       }
       const int64_t stat_base = ((int64_t)I.b * p.H + I.h) * p.Sq;
@@ -920,16 +918,6 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (key < p.Sk) {
 #pragma unroll
         for (int c = 0; c < 16; c += 8) { Vec<__nv_bfloat16>::store(dvrow + c, gv + c); Vec<__nv_bfloat16>::store(dkrow + c, gk + c); }
-      }
-      if (p.dv_partial != nullptr) {   // bias gradient of the value projection: this warp's 32 key rows x 16 columns, as stored (bf16-rounded)
-        float mine = 0.f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float t = key < p.Sk ? __bfloat162float(__float2bfloat16_rn(gv[c])) : 0.f;
-          t = warp_sum(t);
-          if (lane == c) mine = t;
-        }
-        if (lane < 16) p.dv_partial[((int64_t)w * 4 + quarter) * FD + part * 16 + lane] = mine;   // no atomics: one slot per (item, quarter)
       }
       ++j;
     }
@@ -1016,20 +1004,61 @@ fmha_dq_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d
   Vec<__nv_bfloat16>::store(dst + row * ld + c8 * 8, v);
 }
 
-// the same cast, plus the column sums of the bf16 result (bias gradient of the query projection) in the same pass: CTA = 32 column
-// vectors x 8 row lanes over a chunk of rows, row lanes folded through shared memory, one atomic add per column and CTA
+// the same cast, plus the column sums of the bf16 result (bias gradient of the query projection) in the same pass, and — as the
+// blockIdx.z = 1 half of the SAME launch — the column sums of dV (bias gradient of the value projection; reducing them inside the
+// attention kernel's key-tile epilogue was measured slower: +38 us on its critical path).  CTA = 32 column vectors x 8 row
+// lanes over a chunk of rows, four rows in flight per thread, row lanes folded through shared memory, one atomic add per
+// column and CTA.
 __global__ void __launch_bounds__(256)
 fmha_dq_cast_colsum_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int cols8, int64_t ld,
-                           int64_t rows_per_chunk, float* __restrict__ colsum) {
+                           int64_t rows_per_chunk, float* __restrict__ colsum, const __nv_bfloat16* __restrict__ dv, int64_t rows_v,
+                           int64_t lddv, int64_t rows_per_chunk_v, float* __restrict__ colsum_v) {
   __shared__ float sm[8][32 * 8 + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c8 = blockIdx.x * 32 + tx;
-  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  const bool second = blockIdx.z == 1;
+  const int64_t rpc = second ? rows_per_chunk_v : rows_per_chunk, nrows = second ? rows_v : rows;
+  const int64_t r0 = (int64_t)blockIdx.y * rpc, r1 = min(nrows, r0 + rpc);
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  if (c8 < cols8) {
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
+  if (c8 < cols8 && second) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      uint4 a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const uint4*>(dv + (r + 8 * u) * lddv + c8 * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t wds[4] = {a[u].x, a[u].y, a[u].z, a[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { acc[2 * i] += __uint_as_float(wds[i] << 16); acc[2 * i + 1] += __uint_as_float(wds[i] & 0xffff0000u); }
+      }
+    }
+    for (; r < r1; r += 8) {
+      float v[8];
+      Vec<__nv_bfloat16>::load(dv + r * lddv + c8 * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  } else if (c8 < cols8) {
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {   // four rows (eight 16-byte loads) in flight per thread
+      float4 a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* sp = src + ((r + 8 * u) * cols8 + c8) * 8;
+        a[u] = *reinterpret_cast<const float4*>(sp); b[u] = *reinterpret_cast<const float4*>(sp + 4);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float v[8] = {a[u].x, a[u].y, a[u].z, a[u].w, b[u].x, b[u].y, b[u].z, b[u].w};
+        Vec<__nv_bfloat16>::store(dst + (r + 8 * u) * ld + c8 * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(__float2bfloat16_rn(v[j]));
+      }
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       Vec<float>::load(src + (r * cols8 + c8) * 8, v);
       Vec<float>::load(src + (r * cols8 + c8) * 8 + 4, v + 4);
@@ -1043,27 +1072,12 @@ fmha_dq_cast_colsum_kernel(const float* __restrict__ src, __nv_bfloat16* __restr
   __syncthreads();
   const int c = threadIdx.x;   // 256 columns of this CTA
   const int col = blockIdx.x * 256 + c;
-  if (col < cols8 * 8) {
+  if (col < cols8 * 8 && r0 < r1) {
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += sm[k][c];
-    atomicAdd(colsum + col, t);
+    atomicAdd((second ? colsum_v : colsum) + col, t);
   }
-}
-
-// dv_colsum[h * 64 + c] = sum over (batch, key tile, lane quarter) of the per-item partial sums, in a fixed order (deterministic):
-// CTA per head, 64 columns x 4 row lanes
-__global__ void __launch_bounds__(256)
-fmha_dv_colsum_fold_kernel(const float* __restrict__ partial, int B, int H, int n_kt, float* __restrict__ out) {
-  __shared__ float sm[4][FD];
-  const int h = blockIdx.x, c = threadIdx.x & 63, l = threadIdx.x >> 6;
-  float t = 0.f;
-  for (int b = 0; b < B; ++b)
-    for (int r = l; r < n_kt * 4; r += 4)   // rows of (key tile, quarter) for this (b, h): items are numbered (b * H + h) * n_kt + kt
-      t += partial[(((int64_t)(b * H + h) * n_kt) * 4 + r) * FD + c];
-  sm[l][c] = t;
-  __syncthreads();
-  if (l == 0) out[h * FD + c] = (sm[0][c] + sm[1][c]) + (sm[2][c] + sm[3][c]);
 }
 
 // (B, S, d) bf16 tensor -> 4-D map {d, S, B, 1}, box {64, 128, 1, 1}, SWIZZLE_128B
@@ -1139,10 +1153,8 @@ extern "C" int tsw_fmha_fwd(const void* q, const void* k, const void* v, void* o
   return TSW_OK;
 }
 
-// fp32 dQ accumulator | delta | per-item dV column sums (the latter sized for the longest key sequence the model uses: Sk <= 4 * Sq + 4096)
-static size_t fmha_bwd_dvpart_bytes(int64_t B, int64_t H, int64_t Sk) { return (size_t)(B * H * ((Sk + FK - 1) / FK)) * 4 * FD * 4; }
 extern "C" size_t tsw_fmha_bwd_workspace_bytes(int64_t B, int64_t H, int64_t Sq) {
-  return (size_t)(B * Sq * H * FD) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256) + fmha_bwd_dvpart_bytes(B, H, 4 * Sq + 4096);
+  return (size_t)(B * Sq * H * FD) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256);
 }
 
 extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const void* o, const void* dO, const float* lse, void* dq, void* dk,
@@ -1181,14 +1193,11 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   p.key_len = key_len; p.causal = causal ? 1 : 0;
   p.lse = lse; p.delta = delta;
   p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv; p.lddk = ldk; p.lddv = ldv;
-  float* dv_partial = nullptr;
-  if (dv_colsum) {
-    const size_t head = (size_t)(B * Sq * dcols) * 4 + (size_t)((B * H * Sq * 4 + 255) / 256 * 256);
-    if (workspace_bytes < head + fmha_bwd_dvpart_bytes(B, H, Sk)) { set_error("fmha_bwd: workspace too small for the dV column sums (Sk > 4 Sq + 4096)"); return TSW_E_WORKSPACE; }
-    dv_partial = (float*)((char*)workspace + head);
+  TSW_CHECK_ARG((dq_colsum == nullptr) == (dv_colsum == nullptr), "fmha_bwd: dq_colsum and dv_colsum go together");
+  if (dq_colsum) {
+    TSW_CUDA(cudaMemsetAsync(dq_colsum, 0, sizeof(float) * (size_t)dcols, st));
+    TSW_CUDA(cudaMemsetAsync(dv_colsum, 0, sizeof(float) * (size_t)dcols, st));
   }
-  p.dv_partial = dv_partial;
-  if (dq_colsum) TSW_CUDA(cudaMemsetAsync(dq_colsum, 0, sizeof(float) * (size_t)dcols, st));
   static bool attr_done = false;
   const size_t smem = sizeof(FmhaBwdSmem);
   if (!attr_done) {
@@ -1198,10 +1207,6 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
   fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
   TSW_LAUNCH_CHECK();
-  if (dv_colsum) {
-    fmha_dv_colsum_fold_kernel<<<(unsigned)H, 256, 0, st>>>(dv_partial, (int)B, (int)H, p.n_kt, dv_colsum);
-    TSW_LAUNCH_CHECK();
-  }
   // dq (B * Sq rows, row stride ldq) bf16 <- contiguous fp32 accumulator
   if (dq_colsum) {
     const int64_t rows = B * Sq;
@@ -1210,7 +1215,9 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
     int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * 8 / gx, (rows + 63) / 64));
     chunks = std::min<int64_t>(chunks, 65535);
     const int64_t rpc = (rows + chunks - 1) / chunks;
-    fmha_dq_cast_colsum_kernel<<<dim3(gx, (unsigned)chunks), 256, 0, st>>>(dq32, (__nv_bfloat16*)dq, rows, cols8, ldq, rpc, dq_colsum);
+    const int64_t rows_v = B * Sk, rpc_v = (rows_v + chunks - 1) / chunks;
+    fmha_dq_cast_colsum_kernel<<<dim3(gx, (unsigned)chunks, 2), 256, 0, st>>>(dq32, (__nv_bfloat16*)dq, rows, cols8, ldq, rpc, dq_colsum,
+                                                                            (const __nv_bfloat16*)dv, rows_v, ldv, rpc_v, dv_colsum);
     TSW_LAUNCH_CHECK();
   } else {
     const int64_t n8 = B * Sq * (dcols / 8);

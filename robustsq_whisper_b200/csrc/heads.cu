@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -706,6 +707,154 @@ extern "C" int tsw_asp_pool_bwd(const void* x, int dtype, int64_t B, int64_t T, 
 #undef ASP_BWD
 }
 
+// ---- the whole of K8 in ONE cooperative launch (the training step's call: B <= 32 rows per rank, B * d * 4 bytes of shared memory).
+// The algorithm is a chain of five small reductions (normalise f, logits, row softmax, class / feature gradients, normalise-
+// backward) over 4 MB of class weights: as eight stream operations it was launch-latency-bound (240 us for 8 MB of traffic).
+// Here every CTA keeps the normalised features in shared memory, a warp owns a class (w_j in registers), the phases are
+// separated by grid-wide barriers, and the loss / counters are zeroed by the kernel itself.
+__global__ void __launch_bounds__(256, 1)
+aam_fused_kernel(const float* __restrict__ f, const float* __restrict__ w, const int64_t* __restrict__ labels, int B, int C, int d, float cm,
+                 float sm_, float inv_temp, float* __restrict__ loss, int32_t* __restrict__ ncorrect, float* __restrict__ gf,
+                 float* __restrict__ gw, float* __restrict__ logits, float* __restrict__ gcos, float* __restrict__ gfhat,
+                 float* __restrict__ winv, float* __restrict__ lse_ws) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ float aam_sm[];
+  float* fhat = aam_sm;                 // [B][d]
+  float* fnorm = fhat + (size_t)B * d;  // [B]
+  float* red = fnorm + B;               // [8][kGfRows][33] scratch of the feature-gradient phase
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * nw + warp, gwarps = gridDim.x * nw;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { *loss = 0.f; *ncorrect = 0; }
+  // ---- phase 0: normalised features (every CTA, all rows: 128 KB out of L2)
+  for (int b = warp; b < B; b += nw) {
+    float sq = 0.f;
+    for (int c = lane; c < d; c += 32) { const float v = f[(int64_t)b * d + c]; sq += v * v; }
+    const float nrm = sqrtf(warp_sum(sq));
+    const float inv = 1.f / fmaxf(nrm, 1e-12f);
+    if (lane == 0) fnorm[b] = nrm;
+    for (int c = lane; c < d; c += 32) fhat[(size_t)b * d + c] = f[(int64_t)b * d + c] * inv;
+  }
+  __syncthreads();
+  // ---- phase 1: margin logits, one warp per class
+  for (int j = gwarp; j < C; j += gwarps) {
+    float wv[32];
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const int c = lane + 32 * i; wv[i] = c < d ? w[(int64_t)j * d + c] : 0.f; sq += wv[i] * wv[i]; }
+    const float inv = 1.f / fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
+    if (lane == 0) winv[j] = inv;
+    for (int b = 0; b < B; ++b) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) { const int c = lane + 32 * i; if (c < d) sdot = fmaf(wv[i], fhat[(size_t)b * d + c], sdot); }
+      sdot = warp_sum(sdot) * inv;
+      if (lane == 0) {
+        float dl;
+        logits[(int64_t)b * C + j] = margin_logit(sdot, labels[b] == j, cm, sm_, inv_temp, &dl);
+        gcos[(int64_t)b * C + j] = dl;
+      }
+    }
+  }
+  grid.sync();
+  // ---- phase 2: row statistics (log-sum-exp, first-index argmax, loss), one warp per row
+  for (int b = gwarp; b < B; b += gwarps) {
+    const float* l = logits + (int64_t)b * C;
+    const int y = (int)labels[b];
+    float m = -INFINITY;
+    for (int j = lane; j < C; j += 32) m = fmaxf(m, l[j]);
+    m = warp_max(m);
+    float z = 0.f;
+    int first = 0x7fffffff;
+    for (int j = lane; j < C; j += 32) { z += expf(l[j] - m); if (l[j] == m) first = min(first, j); }
+    z = warp_sum(z);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    const float lse = m + logf(z);
+    if (lane == 0) {
+      lse_ws[b] = lse;
+      atomicAdd(loss, (lse - l[y]) / (float)B);
+      if (first == y) atomicAdd(ncorrect, 1);
+    }
+  }
+  grid.sync();
+  // ---- phase 3: dL/dcos for the warp's class (kept for the feature gradient) and the class-weight gradient
+  const float inv_rows = 1.f / (float)B;
+  for (int j = gwarp; j < C; j += gwarps) {
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+      const int b = b0 + lane;
+      float g = 0.f;
+      if (b < B) {
+        const float p = expf(logits[(int64_t)b * C + j] - lse_ws[b]);
+        g = gcos[(int64_t)b * C + j] * (p - ((int)labels[b] == j ? 1.f : 0.f)) * inv_rows;
+        gcos[(int64_t)b * C + j] = g;
+      }
+      const int nb = min(32, B - b0);
+      for (int bb = 0; bb < nb; ++bb) {
+        const float gb = __shfl_sync(0xffffffffu, g, bb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const int c = lane + 32 * i; if (c < d) acc[i] = fmaf(gb, fhat[(size_t)(b0 + bb) * d + c], acc[i]); }
+      }
+    }
+    const float inv = winv[j];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const int c = lane + 32 * i; if (c < d) dot = fmaf(acc[i], w[(int64_t)j * d + c] * inv, dot); }
+    dot = warp_sum(dot);
+    const bool tiny = inv >= 1e12f;  // ||w|| <= eps: F.normalize divides by eps, no projection term
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) gw[(int64_t)j * d + c] = tiny ? acc[i] * inv : (acc[i] - w[(int64_t)j * d + c] * inv * dot) * inv;
+    }
+  }
+  grid.sync();
+  // ---- phase 4: g_fhat[b] = sum_j gcos[b][j] * what_j; work item = (kGfRows rows, 32 columns), 8 class lanes per item
+  {
+    const int tx = lane, ty = warp;
+    const int n_rg = (B + kGfRows - 1) / kGfRows, n_cb = (d + 31) / 32;
+    for (int item = blockIdx.x; item < n_rg * n_cb; item += gridDim.x) {
+      const int b0 = (item / n_cb) * kGfRows, col = (item % n_cb) * 32 + tx;
+      float a[kGfRows];
+#pragma unroll
+      for (int r = 0; r < kGfRows; ++r) a[r] = 0.f;
+      if (col < d) {
+        for (int j = ty; j < C; j += 8) {
+          const float wh = w[(int64_t)j * d + col] * winv[j];
+#pragma unroll
+          for (int r = 0; r < kGfRows; ++r) if (b0 + r < B) a[r] = fmaf(gcos[(int64_t)(b0 + r) * C + j], wh, a[r]);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < kGfRows; ++r) red[(ty * kGfRows + r) * 33 + tx] = a[r];
+      __syncthreads();
+      if (ty < kGfRows && col < d && b0 + ty < B) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[(k * kGfRows + ty) * 33 + tx];
+        gfhat[(int64_t)(b0 + ty) * d + col] = t;
+      }
+    }
+  }
+  grid.sync();
+  // ---- phase 5: through F.normalize of the features
+  for (int b = gwarp; b < B; b += gwarps) {
+    const float nrm = fnorm[b];
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) dot += fhat[(size_t)b * d + c] * gfhat[(int64_t)b * d + c];
+    dot = warp_sum(dot);
+    if (nrm > 1e-12f) {
+      const float inv = 1.f / nrm;
+      for (int c = lane; c < d; c += 32) gf[(int64_t)b * d + c] = (gfhat[(int64_t)b * d + c] - fhat[(size_t)b * d + c] * dot) * inv;
+    } else {
+      for (int c = lane; c < d; c += 32) gf[(int64_t)b * d + c] = gfhat[(int64_t)b * d + c] * 1e12f;
+    }
+  }
+}
+
 // workspace: fhat (B,d) | fnorm (B) | winv (C) | logits (B,C) | gcos (B,C) | gfhat (B,d)
 static size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
 extern "C" size_t tsw_aam_workspace_bytes(int64_t B, int64_t C, int64_t d) {
@@ -728,6 +877,26 @@ extern "C" int tsw_aam_softmax_fwd_bwd(const float* f, const float* w, const int
   float* logits = (float*)p; p += pad256(4 * B * C);
   float* gcos = (float*)p;
   cudaStream_t st = as_stream(stream);
+  {
+    // one cooperative launch when the normalised features fit in shared memory (every training configuration: B <= 48 at d = 1024)
+    const size_t smem = sizeof(float) * ((size_t)B * d + B + 8 * kGfRows * 33);
+    static const bool multi = getenv("TSW_AAM_MULTI_LAUNCH") != nullptr;   // A/B knob: the eight-operation form below
+    if (!multi && smem <= 200 * 1024) {
+      static bool attr_done = false;
+      if (!attr_done) {
+        TSW_CUDA(cudaFuncSetAttribute(aam_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_done = true;
+      }
+      int Bi = (int)B, Ci = (int)C, di = (int)d;
+      float cm = cosf(margin), sm_ = sinf(margin), it = 1.f / temp;
+      float* lse_ws = fnorm;   // (B) scratch
+      const int grid = (int)std::min<int64_t>((C + 7) / 8, (int64_t)sm_count());
+      void* args[] = {(void*)&f, (void*)&w, (void*)&labels, &Bi, &Ci, &di, &cm, &sm_, &it, (void*)&loss, (void*)&ncorrect, (void*)&gf, (void*)&gw,
+                      (void*)&logits, (void*)&gcos, (void*)&gfhat, (void*)&winv, (void*)&lse_ws};
+      TSW_CUDA(cudaLaunchCooperativeKernel((const void*)aam_fused_kernel, dim3((unsigned)grid), dim3(256), args, smem, st));
+      return TSW_OK;
+    }
+  }
   TSW_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
   TSW_CUDA(cudaMemsetAsync(ncorrect, 0, sizeof(int32_t), st));
   int rc = tsw_l2norm_fwd(f, fhat, fnorm, B, d, 1e-12f, stream);

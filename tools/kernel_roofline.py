@@ -52,7 +52,7 @@ hbm("K7 ASP bwd", 2 * 2 * B * 500 * d, lambda: K.asp_pool_bwd(xe, 6.0, ms, pt, v
 # K8 / K9
 f = torch.nn.functional.normalize(torch.randn(B, d, device="cuda"), dim=-1); w = torch.randn(1000, d, device="cuda") * 0.03
 lab = torch.randint(0, B, (B,), device="cuda")
-hbm("K8 AAM-softmax fwd+bwd (C=1000)", 2 * 4 * 1000 * d + 2 * 4 * B * d, lambda: K.aam_softmax_fwd_bwd(f, w, lab, 0.25, 0.0333), "6 small launches: latency-bound")
+hbm("K8 AAM-softmax fwd+bwd (C=1000)", 2 * 4 * 1000 * d + 2 * 4 * B * d, lambda: K.aam_softmax_fwd_bwd(f, w, lab, 0.25, 0.0333), "one cooperative launch, five grid-wide barriers: latency-bound")
 pr = torch.randn(B, 16, d, device="cuda").to(bf); neg = torch.randint(0, B, (B, 20), device="cuda"); pos = torch.arange(B, device="cuda")
 hbm("K9 Arc-InfoNCE fwd+bwd (K=20)", 2 * 2 * B * 16 * d + 2 * 4 * B * d, lambda: K.arc_infonce_fwd_bwd(pr, f, pos, neg, 0.15, 0.1), "latency-bound")
 # K10 LS-CE
