@@ -17,7 +17,9 @@
 // the tensor core with the MN-major canonical layout (LBO = panel stride, SBO = 8-row group stride).
 // Every mbarrier wait is bounded: a protocol bug traps instead of hanging the GPU.
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 #include "gemm_common.cuh"
 #include "tc_ptx.cuh"
@@ -40,6 +42,7 @@ struct TcParams {
   int splits, kb_per_split;  // split-K: work item = (tile, split); partial sums are atomically added into fp32 D
   int kb_main, kb_total;     // k-blocks of A x B, and including the appended low-rank pair A2 x B2 (LoRA term)
   int epi_limit;             // columns of each tile the epilogue drains (= BN; lowered only by the TSW_GEMM_EPI_LIMIT experiment knob)
+  int tma_kind;              // >= 0: the EK_* kind the TMA-store epilogue runs (bf16 output through swizzled boxes); -1: register -> global epilogue
   int64_t total_work;    // total_tiles * splits
 };
 
@@ -153,13 +156,213 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
   }
 }
 
+// ================================================================================ TMA-store epilogue (bf16 outputs)
+// Lane = accumulator row straight out of tcgen05.ld: the fused arithmetic runs on the lane's 32 columns, the result is packed
+// to bf16 and written as one 64-byte row of a 32 x 32 box (SWIZZLE_64B: 16-byte unit j of row r lives at j ^ ((r >> 1) & 3),
+// which makes the warp's 16-byte stores conflict-free), and one elected lane hands the box to TMA (UTMASTG).  No fp32
+// transpose through shared memory, no per-lane global addresses; rows / columns beyond M / N are clipped by the tensor map.
+// Operands of the same shape as D (residual, aux_in) arrive the same way: a TMA load fills the box one chunk ahead, the lane
+// reads its own row, and the result overwrites it in place.  Each epilogue warp owns two boxes (4 KB): output double buffer,
+// or D + aux_out, or input ping-pong.
+__device__ __forceinline__ float2 bf16x2_as_float2(uint32_t w) { return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t float2_as_bf16x2(float2 v) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int KIND>
+__device__ __forceinline__ void tma_chunk_math(const uint32_t* r, float alpha, const float* bias_n, unsigned char* rowD, unsigned char* rowX, int sw) {
+  constexpr bool kIn = KIND == EK_RES || KIND == EK_MUL_AUX || KIND == EK_MUL_DGELU;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int pj = (j ^ sw) << 4;
+    uint4 in4 = make_uint4(0u, 0u, 0u, 0u);
+    if (kIn) in4 = *reinterpret_cast<const uint4*>(rowD + pj);
+    float4 bA = make_float4(0.f, 0.f, 0.f, 0.f), bB = bA;
+    if (bias_n) { bA = __ldg(reinterpret_cast<const float4*>(bias_n + 8 * j)); bB = __ldg(reinterpret_cast<const float4*>(bias_n + 8 * j + 4)); }
+    const float bb[8] = {bA.x, bA.y, bA.z, bA.w, bB.x, bB.y, bB.z, bB.w};
+    const uint32_t inw[4] = {in4.x, in4.y, in4.z, in4.w};
+    uint32_t outw[4], auxw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int col = 8 * j + 2 * t;
+      float2 o = ffma2(splat2(alpha), make_float2(__uint_as_float(r[col]), __uint_as_float(r[col + 1])), make_float2(bb[2 * t], bb[2 * t + 1]));
+      if (KIND == EK_RES) {
+        o = fadd2(o, bf16x2_as_float2(inw[t]));
+      } else if (KIND == EK_MUL_AUX) {
+        o = fmul2(o, bf16x2_as_float2(inw[t]));
+      } else if (KIND == EK_MUL_DGELU) {
+        const float2 e = bf16x2_as_float2(inw[t]);
+        o = make_float2(o.x * dgelu_fast(e.x), o.y * dgelu_fast(e.y));
+      } else if (KIND == EK_GELU) {
+        auxw[t] = float2_as_bf16x2(o);
+        o = gelu_fast2(o);
+      } else if (KIND == EK_GELU_GRAD) {
+        float2 g, d;
+        gelu_and_grad_fast2(o, g, d);
+        auxw[t] = float2_as_bf16x2(d);
+        o = g;
+      }
+      outw[t] = float2_as_bf16x2(o);
+    }
+    *reinterpret_cast<uint4*>(rowD + pj) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    if ((KIND == EK_GELU || KIND == EK_GELU_GRAD) && rowX != nullptr) *reinterpret_cast<uint4*>(rowX + pj) = make_uint4(auxw[0], auxw[1], auxw[2], auxw[3]);
+  }
+}
+
+// Column sums of a finished 32 x 32 bf16 box (the bias gradient riding in the producer's epilogue): ones(16 x 16) x box on the
+// warp-level tensor-core path — ldmatrix.trans feeds the rows of the box as the k index of mma.m16n8k16, fp32 accumulation,
+// every row of the product holds the sums.  ~25 instructions per box where a shuffle transpose-reduce takes ~120.
+__device__ __forceinline__ void box_colsum(const unsigned char* boxD, int lane, float* colsum_n) {
+  float acc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+  const uint32_t ones = 0x3F803F80u;   // bf16 {1, 1}
+  const int mi = lane >> 3;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+    for (int jp = 0; jp < 2; ++jp) {
+      const int row = 16 * ks + (mi & 1) * 8 + (lane & 7);
+      const int unit = 2 * jp + (mi >> 1);
+      const uint32_t addr = smem_u32(boxD + row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
+      uint32_t b0, b1, b2, b3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+                   : "+f"(acc[2 * jp][0]), "+f"(acc[2 * jp][1]), "+f"(acc[2 * jp][2]), "+f"(acc[2 * jp][3]) : "r"(ones), "r"(b0), "r"(b1));
+      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
+                   : "+f"(acc[2 * jp + 1][0]), "+f"(acc[2 * jp + 1][1]), "+f"(acc[2 * jp + 1][2]), "+f"(acc[2 * jp + 1][3]) : "r"(ones), "r"(b2), "r"(b3));
+    }
+  }
+  // accumulator registers 0, 1 of lane l: product row l / 4 (all rows are equal), columns 2 (l % 4) + {0, 1} of each 8-column block:
+  // lanes 0-15 take block l / 4 each
+  const int j = lane >> 2;
+  const float v0 = j == 0 ? acc[0][0] : j == 1 ? acc[1][0] : j == 2 ? acc[2][0] : acc[3][0];
+  const float v1 = j == 0 ? acc[0][1] : j == 1 ? acc[1][1] : j == 2 ? acc[2][1] : acc[3][1];
+  if (lane < 16) atomicAdd(reinterpret_cast<float2*>(colsum_n + 8 * j + 2 * (lane & 3)), make_float2(v0, v1));
+}
+
+template <int BN, int CL, bool TWOSM>
+__device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, const CUtensorMap* tmAO, const CUtensorMap* tmIn, const TcParams& p,
+                                             const EpiParams& ep, unsigned char* stg_all, uint64_t* ibars_all, uint64_t* tfull, uint64_t* tempty,
+                                             uint32_t tmem_base, int warp, int lane, int crank, int w_first, int w_step, int tiles_per_batch) {
+  constexpr uint32_t kBoxBytes = 32 * 64;
+  const int q = warp & 3;            // TMEM lane quarter this warp may access
+  const int half = (warp - 4) >> 2;  // which of the tile's 32-column chunks (even / odd) this warp drains
+  unsigned char* const box = stg_all + (warp - 4) * (2 * kBoxBytes);
+  uint64_t* const ibar = ibars_all + (warp - 4) * 2;
+  const int kind = p.tma_kind;
+  const bool has_in = kind == EK_RES || kind == EK_MUL_AUX || kind == EK_MUL_DGELU;
+  const bool two_out = kind == EK_GELU_GRAD || (kind == EK_GELU && ep.aux_out != nullptr);
+  const bool do_cs = ep.colsum != nullptr;   // kinds PLAIN / MUL_AUX only (host)
+  const float alpha = ep.alpha_dev ? ep.alpha * __ldg(ep.alpha_dev) : ep.alpha;
+  const int total_work = (int)p.total_work;   // splits == 1 on this path: work item = tile (pair)
+  const int sw = (lane >> 1) & 3;
+  const int row_off = lane * 64;
+
+  auto locate = [&](int w, int& m0, int& n0, int& bi, int& bo) {
+    const int bt = w / tiles_per_batch;
+    const int r = w - bt * tiles_per_batch;
+    const int mt = (r / p.tiles_n) * CL + crank;
+    n0 = (r % p.tiles_n) * BN;
+    bo = bt / p.batch_inner; bi = bt - bo * p.batch_inner;
+    m0 = mt * TBM + q * 32;
+  };
+  auto load_in = [&](int slot, int n, int m, int bi, int bo) {   // lane 0 only
+    tma_store_wait_read<0>();   // the store that last read this box has finished with it
+    mbar_expect_tx(&ibar[slot], kBoxBytes);
+    tma_load_4d(tmIn, &ibar[slot], box + slot * kBoxBytes, n, m, bi, bo);
+  };
+
+  int k = 0;        // boxes this warp has produced (input kinds: slot = k & 1, barrier parity = (k >> 1) & 1)
+  int issued = 0;   // input boxes requested so far
+  int as = 0; uint32_t aphase = 0;
+  int w = w_first, m0 = 0, n0t = 0, bi = 0, bo = 0;
+  if (w < total_work) locate(w, m0, n0t, bi, bo);
+  while (w < total_work) {
+    const bool active = m0 < (int)p.M;   // else: phantom tile of an odd pair / rows beyond M — nothing to load or store
+    const int nchunks = min(BN, (int)p.N - n0t) / 64;   // N % 64 == 0 (host): both halves have the same count
+    const int wn = w + w_step;
+    int m0n = 0, n0tn = 0, bin = 0, bon = 0;
+    if (wn < total_work) locate(wn, m0n, n0tn, bin, bon);
+    if (has_in && active && issued == k) {   // first box of the run (or the tile before was inactive): request it now
+      if (lane == 0) load_in(k & 1, n0t + half * 32, m0, bi, bo);
+      ++issued;
+    }
+    mbar_wait(&tfull[as], aphase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+    for (int i = 0; i < nchunks; ++i) {
+      const int c = half * 32 + 64 * i;
+      uint32_t r[32];
+      tmem_ld32_async(taddr + c, r);
+      if (active) {
+        const int slot = k & 1;
+        __syncwarp();   // every lane is done with the previous chunk's boxes (its own row, the column-sum reads)
+        if (has_in) {
+          // request the next box's operand into the other slot while this chunk is processed
+          const bool more = i + 1 < nchunks;
+          const bool nv = more || (wn < total_work && m0n < (int)p.M);
+          if (nv && issued == k + 1) {
+            if (lane == 0) {
+              if (more) load_in(slot ^ 1, n0t + c + 64, m0, bi, bo);
+              else load_in(slot ^ 1, n0tn + half * 32, m0n, bin, bon);
+            }
+            ++issued;
+          }
+          __syncwarp();
+          mbar_wait(&ibar[slot], (uint32_t)((k >> 1) & 1));
+        } else {
+          if (lane == 0) { if (two_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }
+          __syncwarp();
+        }
+        tmem_ld_wait();
+        tmem_ld_fence32(r);
+        const int n = n0t + c;
+        const float* bias_n = ep.bias ? ep.bias + n : nullptr;
+        unsigned char* rowD = box + (two_out ? 0 : slot * kBoxBytes) + row_off;
+        unsigned char* rowX = two_out ? box + kBoxBytes + row_off : nullptr;
+        switch (kind) {
+          case EK_PLAIN: tma_chunk_math<EK_PLAIN>(r, alpha, bias_n, rowD, rowX, sw); break;
+          case EK_RES: tma_chunk_math<EK_RES>(r, alpha, bias_n, rowD, rowX, sw); break;
+          case EK_GELU: tma_chunk_math<EK_GELU>(r, alpha, bias_n, rowD, rowX, sw); break;
+          case EK_GELU_GRAD: tma_chunk_math<EK_GELU_GRAD>(r, alpha, bias_n, rowD, rowX, sw); break;
+          case EK_MUL_AUX: tma_chunk_math<EK_MUL_AUX>(r, alpha, bias_n, rowD, rowX, sw); break;
+          default: tma_chunk_math<EK_MUL_DGELU>(r, alpha, bias_n, rowD, rowX, sw); break;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(tmD, rowD - row_off, n, m0, bi, bo);
+          if (two_out) tma_store_4d(tmAO, box + kBoxBytes, n, m0, bi, bo);
+          tma_store_commit();
+        }
+        if (do_cs) box_colsum(rowD - row_off, lane, ep.colsum + n);
+        ++k;
+      } else {
+        tmem_ld_wait();
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) { if (TWOSM) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
+    if (++as == 2) { as = 0; aphase ^= 1; }
+    w = wn; m0 = m0n; n0t = n0tn; bi = bin; bo = bon;
+  }
+  if (lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last reads
+}
+
 template <int BN, int STAGES, bool TWOSM = false>
 struct TcSmem {
   static constexpr uint32_t kABytes = TBM * TBK * 2;
   static constexpr uint32_t kBBytes = (TWOSM ? BN / 2 : BN) * TBK * 2;   // two-SM UMMA: each CTA holds its half of the N columns
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr uint32_t kStgFloats = 32 * 32;  // per-epilogue-warp transpose staging: 32 rows x 32 fp32, XOR-swizzled 16-byte units
-  static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + 256 + TC_EPI_WARPS * kStgFloats * 4;
+  // per-epilogue-warp staging, 4 KB: 32 rows x 32 fp32 (XOR-swizzled 16-byte units) for the register -> global epilogue, or two
+  // 32 x 32 bf16 boxes (64-byte rows, SWIZZLE_64B) that TMA stores read / TMA loads of the residual | aux operand fill
+  static constexpr uint32_t kStgFloats = 32 * 32;
+  static constexpr uint32_t kBarBytes = 512;       // ring + accumulator barriers, TMEM slot, 2 input-box barriers per epilogue warp
+  static constexpr size_t kBytes = 1024 /*align slack*/ + (size_t)STAGES * kStageBytes + TC_EPI_WARPS * kStgFloats * 4 + kBarBytes;
 };
 
 // TWOSM (with CL = 2): the pair runs ONE tcgen05.mma.cta_group::2 per k-step over a 256 x BN tile — each CTA stages its own
@@ -169,19 +372,22 @@ struct TcSmem {
 template <int BN, int STAGES, typename DT, bool GENERIC, int CL, bool TWOSM = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
-               const __grid_constant__ CUtensorMap tmB2, const TcParams p, const EpiParams ep) {
+               const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAO,
+               const __grid_constant__ CUtensorMap tmIn, const TcParams p, const EpiParams ep) {
   static_assert(!TWOSM || CL == 2, "two-SM UMMA needs a cluster of two CTAs");
   using S = TcSmem<BN, STAGES, TWOSM>;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
   unsigned char* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * S::kStageBytes);
+  float* stg_base = reinterpret_cast<float*>(smem + (size_t)STAGES * S::kStageBytes);   // 1024-byte aligned: the boxes are swizzled by address bits
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * S::kStageBytes + TC_EPI_WARPS * S::kStgFloats * 4);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* stg_base = reinterpret_cast<float*>(smem + (size_t)STAGES * S::kStageBytes + 256);
+  uint64_t* ibars = tempty + 2;          // [2 * TC_EPI_WARPS] input boxes of the TMA epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ibars + 2 * TC_EPI_WARPS);
+  static_assert((2 * STAGES + 4 + 2 * TC_EPI_WARPS) * 8 + 4 <= S::kBarBytes, "barrier block overflows");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
@@ -189,12 +395,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
     if (p.kb_total > p.kb_main) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    if (p.tma_kind >= 0) { tma_prefetch_desc(&tmD); tma_prefetch_desc(&tmAO); tma_prefetch_desc(&tmIn); }
   }
   if (warp == 1 && lane == 0) {
     // TWOSM: one multicast commit of the pair's issuer frees a slot in each CTA; the issuer's accumulator stage is released by the
     // epilogue warps of BOTH CTAs
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TWOSM ? 1 : CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TWOSM ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&ibars[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) { if (TWOSM) tmem_alloc_2sm<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot); }
@@ -320,7 +528,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== epilogue (TMEM -> registers -> global)
+    // ===================================================== epilogue
+    bool drained = false;
+    if constexpr (sizeof(DT) == 2 && BN % 64 == 0) {
+      if (p.tma_kind >= 0) {   // TMEM -> registers (lane = row) -> swizzled bf16 boxes -> TMA store
+        epilogue_tma<BN, CL, TWOSM>(&tmD, &tmAO, &tmIn, p, ep, reinterpret_cast<unsigned char*>(stg_base), ibars, tfull, tempty, tmem_base, warp,
+                                    lane, crank, w_first, w_step, tiles_per_batch);
+        drained = true;
+      }
+    }
+    if (!drained) {
+    // ----- TMEM -> registers -> shared-memory transpose -> global
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 4) >> 2;  // which half of the tile's 32-column chunks this warp drains
     float* stg = stg_base + (warp - 4) * S::kStgFloats;
@@ -426,6 +644,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) { if (TWOSM) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    }
   }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();   // the peer may still multicast into this CTA's smem / barriers until it is done
@@ -445,11 +664,59 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Tensor maps are pure functions of (base, geometry): encoded once and kept (the caching allocator hands the same activation
+// blocks out step after step, weights never move), so a steady-state launch does no driver call at all.
+namespace {
+struct MapKey {
+  const void* base; uint64_t dims[4]; uint64_t strides[3]; uint32_t box[2]; uint32_t swz;
+  bool operator==(const MapKey& o) const { return memcmp(this, &o, sizeof(MapKey)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(MapKey); ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+}  // namespace
+
+static int encode_map_cached(CUtensorMap* tm, const void* base, const cuuint64_t dims[4], const cuuint64_t strides[3], cuuint32_t box0,
+                             cuuint32_t box1, CUtensorMapSwizzle swz) {
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  for (int i = 0; i < 4; ++i) key.dims[i] = dims[i];
+  for (int i = 0; i < 3; ++i) key.strides[i] = strides[i];
+  key.box[0] = box0; key.box[1] = box1; key.swz = (uint32_t)swz;
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *tm = it->second; return TSW_OK; }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("gemm(tcgen05): cuTensorMapEncodeTiled entry point unavailable"); return TSW_E_CUDA; }
+  cuuint32_t box[4] = {box0, box1, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d (dims %llu x %llu x %llu x %llu, row stride %llu B, box %u x %u)", (int)r,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], (unsigned long long)dims[3],
+              (unsigned long long)strides[0], box0, box1);
+    return TSW_E_CUDA;
+  }
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  if (g_map_cache.size() >= 16384) g_map_cache.clear();   // bounded: a long-running process with ever-changing shapes starts over
+  g_map_cache.emplace(key, *tm);
+  return TSW_OK;
+}
+
 // operand stored [rows][K] (mn_major = 0) or [K][rows] (mn_major = 1); 4-D map {inner, outer, batch_inner, batch_outer}
 static int make_operand_map(CUtensorMap* tm, const void* base, int mn_major, int64_t rows, int64_t K, int64_t ld, int bi_count,
                             int64_t s_inner, int bo_count, int64_t s_outer, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) { set_error("gemm(tcgen05): cuTensorMapEncodeTiled entry point unavailable"); return TSW_E_CUDA; }
   const cuuint64_t inner = mn_major ? (cuuint64_t)rows : (cuuint64_t)K;
   const cuuint64_t outer = mn_major ? (cuuint64_t)K : (cuuint64_t)rows;
   cuuint64_t dims[4] = {inner, outer, (cuuint64_t)bi_count, (cuuint64_t)bo_count};
@@ -457,13 +724,42 @@ static int make_operand_map(CUtensorMap* tm, const void* base, int mn_major, int
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, bi_count > 1 ? (cuuint64_t)s_inner * 2 : fallback,
                            bo_count > 1 ? (cuuint64_t)s_outer * 2 : fallback};
   for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
-  cuuint32_t box[4] = {64u, mn_major ? 64u : (cuuint32_t)box_rows, 1u, 1u};
-  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("gemm(tcgen05): cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%lld ld=%lld mn=%d)", (int)r, (long long)rows, (long long)K, (long long)ld, mn_major); return TSW_E_CUDA; }
-  return TSW_OK;
+  return encode_map_cached(tm, base, dims, strides, 64u, mn_major ? 64u : (cuuint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// (M, N) bf16 matrix the epilogue writes (D, aux_out) or reads (residual, aux_in) through 32 x 32 boxes with 64-byte rows
+static int make_box_map(CUtensorMap* tm, const void* base, int64_t M, int64_t N, int64_t ld, int bi_count, int64_t s_inner, int bo_count, int64_t s_outer) {
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)bi_count, (cuuint64_t)bo_count};
+  const cuuint64_t fallback = (cuuint64_t)ld * 2 * (cuuint64_t)M;
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, bi_count > 1 ? (cuuint64_t)s_inner * 2 : fallback, bo_count > 1 ? (cuuint64_t)s_outer * 2 : fallback};
+  for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
+  return encode_map_cached(tm, base, dims, strides, 32u, 32u, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+// the EK_* kind the TMA-store epilogue can run for this launch, or -1
+static int tma_epilogue_kind(const tsw_gemm_desc& g, const EpiParams& ep) {
+  static const bool off = getenv("TSW_GEMM_NO_TMA_EPI") != nullptr;
+  if (off || g.d_dtype != TSW_BF16 || g.beta != 0.f || g.res_row_mod > 0 || g.N % 64 != 0) return -1;
+  const bool has_res = g.residual != nullptr, has_ao = g.aux_out != nullptr;
+  int kind = -1;
+  switch (g.epilogue) {
+    case TSW_EPI_NONE: kind = (has_res && !has_ao) ? EK_RES : (!has_res && !has_ao) ? EK_PLAIN : -1; break;
+    case TSW_EPI_GELU: kind = !has_res ? EK_GELU : -1; break;
+    case TSW_EPI_GELU_SAVE_GRAD: kind = (!has_res && has_ao) ? EK_GELU_GRAD : -1; break;
+    case TSW_EPI_MUL_AUX: kind = (!has_res && !has_ao) ? EK_MUL_AUX : -1; break;
+    case TSW_EPI_MUL_DGELU: kind = (!has_res && !has_ao) ? EK_MUL_DGELU : -1; break;
+    default: break;
+  }
+  if (kind < 0) return -1;
+  if (ep.colsum && (g.bias || !(kind == EK_PLAIN || kind == EK_MUL_AUX))) return -1;   // rows beyond M must contribute 0 to the sums
+  auto ok = [&](const void* ptr, int64_t ld, int64_t si, int64_t so) {
+    return !ptr || (aligned16(ptr) && ld % 8 == 0 && (g.batch_inner == 1 || si % 8 == 0) && (g.batch_outer == 1 || so % 8 == 0));
+  };
+  if (!ok(g.D, g.ldd, g.d_stride_inner, g.d_stride_outer) || !ok(g.aux_out, g.ldd, g.d_stride_inner, g.d_stride_outer) ||
+      !ok(g.aux_in, g.ldd, g.d_stride_inner, g.d_stride_outer) || !ok(g.residual, g.ldres, g.res_stride_inner, g.res_stride_outer))
+    return -1;
+  if (g.bias && !aligned16(g.bias)) return -1;
+  return kind;
 }
 
 bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
@@ -526,6 +822,20 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
       if (cost < best * 0.98) { best = cost; p.splits = sct; }
     }
   }
+  // TMA-store epilogue (bf16 outputs, no split-K): D / aux_out / residual | aux_in travel as swizzled 32 x 32 boxes
+  p.tma_kind = (sizeof(DT) == 2 && BN % 64 == 0 && p.splits == 1) ? tma_epilogue_kind(g, ep) : -1;
+  CUtensorMap tmD = tmA, tmAO = tmA, tmIn = tmA;
+  if (p.tma_kind >= 0) {
+    rc = make_box_map(&tmD, g.D, g.M, g.N, g.ldd, g.batch_inner, g.d_stride_inner, g.batch_outer, g.d_stride_outer);
+    if (rc) return rc;
+    if (g.aux_out && (p.tma_kind == EK_GELU || p.tma_kind == EK_GELU_GRAD)) {
+      rc = make_box_map(&tmAO, g.aux_out, g.M, g.N, g.ldd, g.batch_inner, g.d_stride_inner, g.batch_outer, g.d_stride_outer);
+      if (rc) return rc;
+    }
+    if (p.tma_kind == EK_RES) rc = make_box_map(&tmIn, g.residual, g.M, g.N, g.ldres, g.batch_inner, g.res_stride_inner, g.batch_outer, g.res_stride_outer);
+    else if (p.tma_kind == EK_MUL_AUX || p.tma_kind == EK_MUL_DGELU) rc = make_box_map(&tmIn, g.aux_in, g.M, g.N, g.ldd, g.batch_inner, g.d_stride_inner, g.batch_outer, g.d_stride_outer);
+    if (rc) return rc;
+  }
   static const int epi_limit_env = getenv("TSW_GEMM_EPI_LIMIT") ? atoi(getenv("TSW_GEMM_EPI_LIMIT")) : 0;   // timing experiments only: wrong results
   p.epi_limit = epi_limit_env > 0 ? epi_limit_env : BN;
   p.kb_per_split = (num_kb + p.splits - 1) / p.splits;
@@ -567,7 +877,7 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
       ++na;
     }
     cfg.attrs = at; cfg.numAttrs = na;
-    TSW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, p, ep));
+    TSW_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmA2, tmB2, tmD, tmAO, tmIn, p, ep));
   }
   TSW_LAUNCH_CHECK();
   return TSW_OK;
