@@ -28,7 +28,7 @@ extern "C" {
 
 typedef struct CUstream_st* tsw_stream_t; /* == cudaStream_t */
 
-#define TSW_ABI_VERSION 3
+#define TSW_ABI_VERSION 4
 
 enum { TSW_F32 = 0, TSW_BF16 = 1 };
 
@@ -116,6 +116,21 @@ typedef struct {
    * of fc2), so no separate pass re-reads D.  tcgen05 kernel, epilogue NONE or MUL_AUX without residual / aux_out / beta,
    * N % 4 == 0, unbatched; zeroed by the call, accumulated with fp32 atomics (summation order not fixed).  NULL when unused. */
   float* colsum_out;
+  /* Optional GROUPED contraction (tcgen05 kernel, bf16 operands, batch_outer == 1, no A2 / B2): the k index runs over
+   * `kgroups` groups of Kg = K / kgroups columns, and inside group g each operand is read through a window on its OUTER
+   * (strided) dimension — the m / n rows of a K-major operand, the k rows of an MN-major one:
+   *     window row r of group g  =  memory row  r * outer_step + outer_off0 + g * outer_off_step   of the matrix at
+   *     base + g * group_stride (elements); window rows that fall outside [0, outer_extent) read as ZERO.
+   * (outer_step 0 is read as 1, outer_extent 0 as the natural row count.)  The tensor maps carry the step as the TMA
+   * traversal stride and the zero padding as out-of-bounds fill, so nothing is materialised.  This is how the conv stem
+   * (whisper_encoder.py:446-447,464-465: Conv1d k = 3, padding 1, stride 2) runs as an implicit GEMM — group = tap,
+   * A window = the input shifted by tap - 1 and subsampled by the stride, B group = that tap's weight matrix — and its
+   * backward too: the weight gradient folds the batch into k (group = utterance, B window = the shifted / subsampled
+   * input), the input gradient is one plain GEMM for the even rows and a two-group one (taps 0 and 2) for the odd rows. */
+  int32_t kgroups;      /* 0: plain contraction (the fields below are ignored); >= 1: grouped */
+  int32_t reserved2;
+  int64_t a_outer_step, a_outer_off0, a_outer_off_step, a_outer_extent, a_group_stride;
+  int64_t b_outer_step, b_outer_off0, b_outer_off_step, b_outer_extent, b_group_stride;
 } tsw_gemm_desc;
 
 size_t tsw_gemm_workspace_bytes(const tsw_gemm_desc* d);

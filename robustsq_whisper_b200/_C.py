@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtsw_sm100.so")
 
 F32, BF16 = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 EPI_NONE, EPI_GELU, EPI_MUL_DGELU, EPI_GELU_SAVE_GRAD, EPI_MUL_AUX = 0, 1, 2, 3, 4
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_SKINNY = 0, 1, 2, 3
 
@@ -40,6 +40,9 @@ class GemmDesc(Structure):
         ("alpha_dev", c_void_p),
         ("A2", c_void_p), ("B2", c_void_p), ("K2", c_int64), ("lda2", c_int64), ("ldb2", c_int64),
         ("colsum_out", c_void_p),
+        ("kgroups", c_int32), ("reserved2", c_int32),
+        ("a_outer_step", c_int64), ("a_outer_off0", c_int64), ("a_outer_off_step", c_int64), ("a_outer_extent", c_int64), ("a_group_stride", c_int64),
+        ("b_outer_step", c_int64), ("b_outer_off0", c_int64), ("b_outer_off_step", c_int64), ("b_outer_extent", c_int64), ("b_group_stride", c_int64),
     ]
 
 

@@ -15,7 +15,8 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   TSW_CHECK_ARG(g.A && g.B && g.D, "gemm: null operand");
   TSW_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0 && g.batch_outer >= 1 && g.batch_inner >= 1, "gemm: bad sizes M=%lld N=%lld K=%lld", (long long)g.M, (long long)g.N, (long long)g.K);
   TSW_CHECK_ARG((g.a_dtype | 1) == 1 && (g.b_dtype | 1) == 1 && (g.d_dtype | 1) == 1, "gemm: bad dtype");
-  TSW_CHECK_ARG(g.lda >= (g.a_mn_major ? g.M : g.K) && g.ldb >= (g.b_mn_major ? g.N : g.K) && g.ldd >= g.N, "gemm: leading dimension too small");
+  TSW_CHECK_ARG(g.kgroups >= 1 || (g.lda >= (g.a_mn_major ? g.M : g.K) && g.ldb >= (g.b_mn_major ? g.N : g.K)), "gemm: leading dimension too small");
+  TSW_CHECK_ARG(g.ldd >= g.N, "gemm: leading dimension too small");
   TSW_CHECK_ARG(g.epilogue >= TSW_EPI_NONE && g.epilogue <= TSW_EPI_MUL_AUX, "gemm: bad epilogue");
   TSW_CHECK_ARG((g.epilogue != TSW_EPI_MUL_DGELU && g.epilogue != TSW_EPI_MUL_AUX) || g.aux_in, "gemm: MUL_DGELU / MUL_AUX need aux_in");
   TSW_CHECK_ARG(!g.residual || (g.res_dtype == g.d_dtype && g.ldres >= g.N), "gemm: residual must have the output dtype");
@@ -23,6 +24,14 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   TSW_CHECK_ARG((g.A2 == nullptr) == (g.B2 == nullptr), "gemm: A2 and B2 go together");
   TSW_CHECK_ARG(!g.A2 || (g.K2 > 0 && g.lda2 >= (g.a_mn_major ? g.M : g.K2) && g.ldb2 >= (g.b_mn_major ? g.N : g.K2)),
                 "gemm: second operand pair: bad K2 / leading dimensions");
+
+  const bool grouped = g.kgroups >= 1;
+  TSW_CHECK_ARG(g.kgroups >= 0, "gemm: bad kgroups");
+  if (grouped) {
+    // the leading-dimension check above assumed a dense K: redo it for one group's columns
+    const int64_t Kg = g.K / g.kgroups;
+    TSW_CHECK_ARG(g.K % g.kgroups == 0 && g.lda >= (g.a_mn_major ? g.M : Kg) && g.ldb >= (g.b_mn_major ? g.N : Kg), "gemm: grouped contraction: bad K / leading dimensions");
+  }
 
   EpiParams ep;
   ep.D = g.D; ep.ldd = g.ldd;
@@ -51,6 +60,14 @@ extern "C" int tsw_gemm(const tsw_gemm_desc* d, void* workspace, size_t workspac
   if (g.colsum_out && (g.impl == TSW_GEMM_SIMT || !gemm_tc_supported(g, nullptr))) {
     set_error("gemm: colsum_out is a feature of the tcgen05 kernel (bf16 operands that satisfy the TMA constraints)");
     return TSW_E_UNSUPPORTED;
+  }
+  if (grouped) {
+    const char* why = nullptr;
+    if (g.impl == TSW_GEMM_SIMT || g.impl == TSW_GEMM_SKINNY || !gemm_tc_supported(g, &why)) {
+      set_error("gemm: a grouped contraction runs on the tcgen05 kernel only%s%s", why ? ": " : "", why ? why : "");
+      return TSW_E_UNSUPPORTED;
+    }
+    return gemm_tc_launch(g, ep, st);
   }
   if (g.impl == TSW_GEMM_SIMT) return gemm_simt_launch(g, ep, st);
   if (g.impl == TSW_GEMM_TCGEN05) return gemm_tc_launch(g, ep, st);

@@ -42,6 +42,11 @@ struct TcParams {
   int splits, kb_per_split;  // split-K: work item = (tile, split); partial sums are atomically added into fp32 D
   int kb_main, kb_total;     // k-blocks of A x B, and including the appended low-rank pair A2 x B2 (LoRA term)
   int epi_limit;             // columns of each tile the epilogue drains (= BN; lowered only by the TSW_GEMM_EPI_LIMIT experiment knob)
+  // grouped contraction (implicit convolution / batch folded into k): k-block kb -> group g = kb / kb_per_group; each operand's
+  // outer coordinate is  r * step + off0 + g * off_step,  its third / fourth tensor-map coordinates  bi * c2mul / g * c3mul
+  int kgroups, kb_per_group;
+  int a_step, a_off0, a_off_step, a_c2mul, a_c3mul;
+  int b_step, b_off0, b_off_step, b_c2mul, b_c3mul;
   int tma_kind;              // >= 0: the EK_* kind the TMA-store epilogue runs (bf16 output through swizzled boxes); -1: register -> global epilogue
   int64_t total_work;    // total_tiles * splits
 };
@@ -446,44 +451,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool second = kb >= p.kb_main;
           const CUtensorMap* ta = second ? &tmA2 : &tmA;
           const CUtensorMap* tb = second ? &tmB2 : &tmB;
-          const int k0 = (second ? kb - p.kb_main : kb) * TBK;
+          int g = 0, kk = second ? kb - p.kb_main : kb;
+          if (p.kgroups > 1) { g = kk / p.kb_per_group; kk -= g * p.kb_per_group; }
+          const int k0 = kk * TBK;
+          // tensor-map coordinates {inner, outer, c2, c3}: K-major operand = {k, row}, MN-major = {row, k}; the OUTER one carries the
+          // window (step / per-group offset) of a grouped contraction, plain problems have step 1 and offset 0
+          const int a_outer = (p.a_mn ? k0 : m0) * p.a_step + p.a_off0 + g * p.a_off_step;
+          const int a_inner = p.a_mn ? m0 : k0;
+          const int a2 = bi * p.a_c2mul, a3 = (p.kgroups > 1 ? g : bo) * p.a_c3mul;
+          const int nb0 = n0 + ((TWOSM || CL > 1) ? crank * (BN / 2) : 0);   // pairs: this CTA's half of the B tile
+          const int b_outer = (p.b_mn ? k0 : nb0) * p.b_step + p.b_off0 + g * p.b_off_step;
+          const int b_inner = p.b_mn ? nb0 : k0;
+          const int b2 = bi * p.b_c2mul, b3 = (p.kgroups > 1 ? g : bo) * p.b_c3mul;
           if (TWOSM) {   // own 128 rows of A, own BN/2 columns of B; completion counted on the even CTA's barrier
             if (!p.a_mn) {
-              tma_load_4d_2sm(ta, &full[stage], sa, k0, m0, bi, bo);
+              tma_load_4d_2sm(ta, &full[stage], sa, a_inner, a_outer, a2, a3);
             } else {
 #pragma unroll
-              for (int j = 0; j < TBM / 64; ++j) tma_load_4d_2sm(ta, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);
+              for (int j = 0; j < TBM / 64; ++j) tma_load_4d_2sm(ta, &full[stage], sa + j * kPanelBytes, a_inner + 64 * j, a_outer, a2, a3);
             }
             if (!p.b_mn) {
-              tma_load_4d_2sm(tb, &full[stage], sb, k0, n0 + crank * (BN / 2), bi, bo);   // box {64 k, BN/2 n}
+              tma_load_4d_2sm(tb, &full[stage], sb, b_inner, b_outer, b2, b3);   // box {64 k, BN/2 n}
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 128; ++j) tma_load_4d_2sm(tb, &full[stage], sb + j * kPanelBytes, n0 + crank * (BN / 2) + 64 * j, k0, bi, bo);
+              for (int j = 0; j < BN / 128; ++j) tma_load_4d_2sm(tb, &full[stage], sb + j * kPanelBytes, b_inner + 64 * j, b_outer, b2, b3);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
           if (!p.a_mn) {
-            tma_load_4d(ta, &full[stage], sa, k0, m0, bi, bo);                       // box {64 k, 128 m}
+            tma_load_4d(ta, &full[stage], sa, a_inner, a_outer, a2, a3);                       // box {64 k, 128 m}
           } else {
 #pragma unroll
-            for (int j = 0; j < TBM / 64; ++j) tma_load_4d(ta, &full[stage], sa + j * kPanelBytes, m0 + 64 * j, k0, bi, bo);  // box {64 m, 64 k}
+            for (int j = 0; j < TBM / 64; ++j) tma_load_4d(ta, &full[stage], sa + j * kPanelBytes, a_inner + 64 * j, a_outer, a2, a3);  // box {64 m, 64 k}
           }
           if (CL == 1) {
             if (!p.b_mn) {
-              tma_load_4d(tb, &full[stage], sb, k0, n0, bi, bo);                       // box {64 k, BN n}
+              tma_load_4d(tb, &full[stage], sb, b_inner, b_outer, b2, b3);                       // box {64 k, BN n}
             } else {
 #pragma unroll
-              for (int j = 0; j < BN / 64; ++j) tma_load_4d(tb, &full[stage], sb + j * kPanelBytes, n0 + 64 * j, k0, bi, bo);
+              for (int j = 0; j < BN / 64; ++j) tma_load_4d(tb, &full[stage], sb + j * kPanelBytes, b_inner + 64 * j, b_outer, b2, b3);
             }
           } else {   // this CTA's half of the B tile, delivered to both CTAs of the pair
             if (!p.b_mn) {
-              tma_load_4d_mc(tb, &full[stage], sb + crank * (S::kBBytes / 2), k0, n0 + crank * (BN / 2), bi, bo, (uint16_t)3);   // box {64 k, BN/2 n}
+              tma_load_4d_mc(tb, &full[stage], sb + crank * (S::kBBytes / 2), b_inner, b_outer, b2, b3, (uint16_t)3);   // box {64 k, BN/2 n}
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 128; ++j) {
                 const int jj = crank * (BN / 128) + j;
-                tma_load_4d_mc(tb, &full[stage], sb + jj * kPanelBytes, n0 + 64 * jj, k0, bi, bo, (uint16_t)3);
+                tma_load_4d_mc(tb, &full[stage], sb + jj * kPanelBytes, b_inner + 64 * j, b_outer, b2, b3, (uint16_t)3);
               }
             }
           }
@@ -684,13 +700,13 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 }  // namespace
 
 static int encode_map_cached(CUtensorMap* tm, const void* base, const cuuint64_t dims[4], const cuuint64_t strides[3], cuuint32_t box0,
-                             cuuint32_t box1, CUtensorMapSwizzle swz) {
+                             cuuint32_t box1, CUtensorMapSwizzle swz, cuuint32_t outer_step = 1) {
   MapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
   for (int i = 0; i < 4; ++i) key.dims[i] = dims[i];
   for (int i = 0; i < 3; ++i) key.strides[i] = strides[i];
-  key.box[0] = box0; key.box[1] = box1; key.swz = (uint32_t)swz;
+  key.box[0] = box0; key.box[1] = box1; key.swz = (uint32_t)swz | (outer_step << 8);
   {
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_map_cache.find(key);
@@ -698,8 +714,8 @@ static int encode_map_cached(CUtensorMap* tm, const void* base, const cuuint64_t
   }
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) { set_error("gemm(tcgen05): cuTensorMapEncodeTiled entry point unavailable"); return TSW_E_CUDA; }
-  cuuint32_t box[4] = {box0, box1, 1u, 1u};
-  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  cuuint32_t box[4] = {box0, box1 * outer_step, 1u, 1u};   // traversal stride s: the box spans box1 * s rows, every s-th is taken
+  cuuint32_t estr[4] = {1u, outer_step, 1u, 1u};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -714,17 +730,23 @@ static int encode_map_cached(CUtensorMap* tm, const void* base, const cuuint64_t
   return TSW_OK;
 }
 
-// operand stored [rows][K] (mn_major = 0) or [K][rows] (mn_major = 1); 4-D map {inner, outer, batch_inner, batch_outer}
-static int make_operand_map(CUtensorMap* tm, const void* base, int mn_major, int64_t rows, int64_t K, int64_t ld, int bi_count,
-                            int64_t s_inner, int bo_count, int64_t s_outer, int box_rows) {
-  const cuuint64_t inner = mn_major ? (cuuint64_t)rows : (cuuint64_t)K;
-  const cuuint64_t outer = mn_major ? (cuuint64_t)K : (cuuint64_t)rows;
-  cuuint64_t dims[4] = {inner, outer, (cuuint64_t)bi_count, (cuuint64_t)bo_count};
-  const cuuint64_t fallback = (cuuint64_t)ld * 2 * outer;
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, bi_count > 1 ? (cuuint64_t)s_inner * 2 : fallback,
-                           bo_count > 1 ? (cuuint64_t)s_outer * 2 : fallback};
+// operand stored [rows][K] (mn_major = 0) or [K][rows] (mn_major = 1); 4-D map {inner, outer, c2, c3}: c2 = inner batch index,
+// c3 = outer batch index — or, for a grouped contraction, the k group (extent G, stride group_stride).  outer_extent / step: the
+// window of a grouped contraction on the outer dimension (rows outside the extent are zero-filled by TMA)
+struct OperandGeom {
+  const void* base; int mn_major; int64_t rows, K, ld; int c2_count; int64_t c2_stride; int c3_count; int64_t c3_stride; int box_rows;
+  int64_t outer_extent; int step;
+};
+static int make_operand_map(CUtensorMap* tm, const OperandGeom& o) {
+  const cuuint64_t inner = o.mn_major ? (cuuint64_t)o.rows : (cuuint64_t)o.K;
+  const cuuint64_t outer = o.outer_extent > 0 ? (cuuint64_t)o.outer_extent : (o.mn_major ? (cuuint64_t)o.K : (cuuint64_t)o.rows);
+  // a dimension with one entry (or a broadcast one: stride 0) is encoded with extent 1; the kernel then always passes coordinate 0
+  const bool c2 = o.c2_count > 1 && o.c2_stride != 0, c3 = o.c3_count > 1 && o.c3_stride != 0;
+  cuuint64_t dims[4] = {inner, outer, c2 ? (cuuint64_t)o.c2_count : 1u, c3 ? (cuuint64_t)o.c3_count : 1u};
+  const cuuint64_t fallback = (cuuint64_t)o.ld * 2 * outer;
+  cuuint64_t strides[3] = {(cuuint64_t)o.ld * 2, c2 ? (cuuint64_t)o.c2_stride * 2 : fallback, c3 ? (cuuint64_t)o.c3_stride * 2 : fallback};
   for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = 16;
-  return encode_map_cached(tm, base, dims, strides, 64u, mn_major ? 64u : (cuuint32_t)box_rows, CU_TENSOR_MAP_SWIZZLE_128B);
+  return encode_map_cached(tm, o.base, dims, strides, 64u, o.mn_major ? 64u : (cuuint32_t)o.box_rows, CU_TENSOR_MAP_SWIZZLE_128B, (cuuint32_t)o.step);
 }
 
 // (M, N) bf16 matrix the epilogue writes (D, aux_out) or reads (residual, aux_in) through 32 x 32 boxes with 64-byte rows
@@ -771,6 +793,14 @@ bool gemm_tc_supported(const tsw_gemm_desc& g, const char** why) {
     return bad("batch strides must be multiples of 8 elements");
   if (g.M < 1 || g.N < 1 || g.K < 1) return bad("empty problem");
   if (g.M >= (1ll << 31) || g.N >= (1ll << 31) || g.K >= (1ll << 31)) return bad("dimension exceeds 2^31");
+  if (g.kgroups >= 1) {
+    if (g.A2) return bad("grouped contraction: no second operand pair");
+    if (g.batch_outer != 1) return bad("grouped contraction: batch_outer must be 1");
+    if (g.K % g.kgroups) return bad("grouped contraction: K must be a multiple of kgroups");
+    if (g.a_group_stride % 8 || g.b_group_stride % 8 || g.a_group_stride < 0 || g.b_group_stride < 0) return bad("grouped contraction: group strides must be non-negative multiples of 8 elements");
+    const int64_t as = g.a_outer_step ? g.a_outer_step : 1, bs = g.b_outer_step ? g.b_outer_step : 1;
+    if (as < 1 || as > 2 || bs < 1 || bs > 2) return bad("grouped contraction: outer_step must be 1 or 2 (TMA box of 256 rows)");
+  }
   if (g.A2) {
     if (!aligned16(g.A2) || !aligned16(g.B2)) return bad("second operand pair: base pointers must be 16-byte aligned");
     if (g.lda2 % 8 || g.ldb2 % 8) return bad("second operand pair: leading dimensions must be multiples of 8 elements");
@@ -783,15 +813,24 @@ template <int BN, int STAGES, typename DT, bool GENERIC, int CL, bool TWOSM = fa
 static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   using S = TcSmem<BN, STAGES, TWOSM>;
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, g.A, g.a_mn_major, g.M, g.K, g.lda, g.batch_inner, g.a_stride_inner, g.batch_outer, g.a_stride_outer, TBM);
+  const bool grouped = g.kgroups >= 1;
+  const int64_t Kg = grouped ? g.K / g.kgroups : g.K;   // contraction length seen by one tensor map
+  const int a_step = grouped && g.a_outer_step ? (int)g.a_outer_step : 1, b_step = grouped && g.b_outer_step ? (int)g.b_outer_step : 1;
+  OperandGeom ga = {g.A, g.a_mn_major, g.M, Kg, g.lda, g.batch_inner, g.a_stride_inner, grouped ? g.kgroups : g.batch_outer,
+                    grouped ? g.a_group_stride : g.a_stride_outer, TBM, grouped ? g.a_outer_extent : 0, a_step};
+  OperandGeom gb = {g.B, g.b_mn_major, g.N, Kg, g.ldb, g.batch_inner, g.b_stride_inner, grouped ? g.kgroups : g.batch_outer,
+                    grouped ? g.b_group_stride : g.b_stride_outer, BN / CL, grouped ? g.b_outer_extent : 0, b_step};
+  int rc = make_operand_map(&tmA, ga);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, g.B, g.b_mn_major, g.N, g.K, g.ldb, g.batch_inner, g.b_stride_inner, g.batch_outer, g.b_stride_outer, BN / CL);
+  rc = make_operand_map(&tmB, gb);
   if (rc) return rc;
   CUtensorMap tmA2 = tmA, tmB2 = tmB;   // second (low-rank) operand pair, same majors; unbatched
   if (g.A2) {
-    rc = make_operand_map(&tmA2, g.A2, g.a_mn_major, g.M, g.K2, g.lda2, 1, 0, 1, 0, TBM);
+    OperandGeom ga2 = {g.A2, g.a_mn_major, g.M, g.K2, g.lda2, 1, 0, 1, 0, TBM, 0, 1};
+    OperandGeom gb2 = {g.B2, g.b_mn_major, g.N, g.K2, g.ldb2, 1, 0, 1, 0, BN / CL, 0, 1};
+    rc = make_operand_map(&tmA2, ga2);
     if (rc) return rc;
-    rc = make_operand_map(&tmB2, g.B2, g.b_mn_major, g.N, g.K2, g.ldb2, 1, 0, 1, 0, BN / CL);
+    rc = make_operand_map(&tmB2, gb2);
     if (rc) return rc;
   }
   TcParams p;
@@ -804,8 +843,16 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   // tile whose loads are zero-filled and whose rows the epilogue masks
   p.total_tiles = (int64_t)((p.tiles_m + CL - 1) / CL) * p.tiles_n * p.batches;
   const int units = sm_count() / CL;   // CTAs (CL = 1) or clusters (CL = 2) that run concurrently
-  p.kb_main = (int)((g.K + TBK - 1) / TBK);
+  p.kgroups = grouped ? g.kgroups : 1;
+  p.kb_per_group = (int)((Kg + TBK - 1) / TBK);   // a ragged last k-block of a group is zero-filled by the tensor maps
+  p.kb_main = p.kgroups * p.kb_per_group;
   p.kb_total = p.kb_main + (g.A2 ? (int)((g.K2 + TBK - 1) / TBK) : 0);
+  p.a_step = a_step; p.b_step = b_step;
+  p.a_off0 = grouped ? (int)g.a_outer_off0 : 0; p.a_off_step = grouped ? (int)g.a_outer_off_step : 0;
+  p.b_off0 = grouped ? (int)g.b_outer_off0 : 0; p.b_off_step = grouped ? (int)g.b_outer_off_step : 0;
+  // coordinate multipliers: 0 where the map encodes the dimension with extent 1 (single entry or broadcast)
+  p.a_c2mul = (g.batch_inner > 1 && g.a_stride_inner != 0) ? 1 : 0; p.b_c2mul = (g.batch_inner > 1 && g.b_stride_inner != 0) ? 1 : 0;
+  p.a_c3mul = (ga.c3_count > 1 && ga.c3_stride != 0) ? 1 : 0; p.b_c3mul = (gb.c3_count > 1 && gb.c3_stride != 0) ? 1 : 0;
   const int num_kb = p.kb_total;
   p.splits = 1;
   // split-K when the output has too few tiles to occupy the machine (weight gradients: M, N ~ 1e3, K ~ 5e4): fp32 output,

@@ -8,6 +8,8 @@ Precision regimes (one per model instance, chosen by the activation dtype):
 """
 from __future__ import annotations
 
+import os
+
 import math
 import weakref
 from typing import Optional, Tuple
@@ -57,6 +59,20 @@ def shadow_cat(ps: Tuple[Optional[Tensor], ...], dtype: torch.dtype, rows_each: 
     s = full if full.dtype == dtype else K.cast(full, dtype)
     drop = lambda _r, key=key: _shadow_cache.pop(key, None)
     _shadow_cache[key] = (ver, s, tuple(None if p is None else weakref.ref(p, drop) for p in ps))
+    return s
+
+
+def shadow_taps(w: Tensor, dtype: torch.dtype) -> Tensor:
+    """(3, D, C) tap-major shadow of a Conv1d weight (D, C, 3): one (D, C) row-major matrix per tap, the layout the implicit-GEMM
+    conv stem reads (forward: K-major B of tap g; input gradient: MN-major B).  Refreshed like ``shadow``."""
+    key = ("taps", id(w), dtype)
+    ent = _shadow_cache.get(key)
+    ver = w._version
+    if ent is not None and ent[0] == ver and ent[2] == w.data_ptr() and ent[3]() is w:
+        return ent[1]
+    s = w.detach().permute(2, 0, 1).contiguous()
+    s = s if s.dtype == dtype else K.cast(s, dtype)
+    _shadow_cache[key] = (ver, s, w.data_ptr(), weakref.ref(w, lambda _r, key=key: _shadow_cache.pop(key, None)))
     return s
 
 
@@ -673,7 +689,79 @@ class _ConvK3Gelu(Function):
         return dx, dw, db, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------ conv stem, second conv, as an IMPLICIT GEMM
+def conv_implicit_ok(x: Tensor, w: Tensor, stride: int, channels_first: bool) -> bool:
+    """bf16, time-major input, channels a multiple of 64 (whole k-blocks per tap), stride 1 or 2: the grouped tcgen05 contraction
+    reads the input through strided / shifted TMA windows.  (The first conv reads the channels-first 80-bin log-mel: 46 MB of
+    im2col at the headline shape, kept on the staged path.)"""
+    return (os.environ.get("TSW_CONV_IM2COL") is None and x.is_cuda and x.dtype == torch.bfloat16 and not channels_first and w.shape[2] == 3
+            and x.shape[2] % 64 == 0 and w.shape[0] % 8 == 0 and stride in (1, 2))
+
+
+class _ConvK3GeluImplicit(Function):
+    """GELU(conv1d(x, w, b, stride, padding=1)) (+ positional table) for x (B, T, C) time-major without materialising the
+    (B * T_out, 3 C) column matrix (whisper_encoder.py:446-447,464-467).  Forward: one batched GEMM whose contraction runs over
+    3 groups (taps) of C channels — A window = input rows t * stride + tap - 1 (TMA traversal stride, zero fill outside [0, T)),
+    B group = that tap's (D, C) weight matrix.  Weight gradient: per tap one GEMM with the batch folded into k (group =
+    utterance, B window = the shifted / subsampled input).  Input gradient (stride 2): even input rows see tap 1 only (a plain
+    GEMM writing every other row), odd rows see taps 0 and 2 (a two-group GEMM writing the rows in between); stride 1: one
+    three-group GEMM.  No im2col, no col2im, the input is read where it lies."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, w: Tensor, b: Tensor, stride: int, pos: Optional[Tensor]):
+        dt = x.dtype
+        x = x.contiguous()
+        B, T, C = x.shape
+        D = w.shape[0]
+        To = (T + 2 - 3) // stride + 1
+        wt = shadow_taps(w, dt)                                   # (3, D, C)
+        pre = torch.empty((B, To, D), dtype=dt, device=x.device)
+        y = torch.empty((B, To, D), dtype=dt, device=x.device)
+        posq = shadow(pos, dt)[:To].contiguous() if pos is not None else None
+        K.gemm(x, wt, M=To, N=D, K=3 * C, lda=C, ldb=C, batch=(1, B), a_strides=(0, T * C), b_strides=(0, 0), out=y, ldd=D,
+               d_strides=(0, To * D), bias=b.detach(), aux_out=pre, epilogue=_C.EPI_GELU, residual=posq, res_strides=(0, 0),
+               impl=_C.GEMM_TCGEN05, kgroups=3, a_window=(stride, -1, 1, T, 0), b_window=(1, 0, 0, D, D * C))
+        ctx.save_for_backward(x, pre, w)
+        ctx.meta = (B, C, T, To, D, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x, pre, w = ctx.saved_tensors
+        B, C, T, To, D, stride = ctx.meta
+        dt = x.dtype
+        rows = B * To
+        dpre = K.gelu_bwd(pre.view(rows, D), dy.reshape(rows, D))
+        dw = db = dx = None
+        if ctx.needs_input_grad[1]:
+            dwt = torch.empty((3, D, C), dtype=torch.float32, device=x.device)
+            for tap in range(3):   # dW_tap[d, c] = sum over (b, t) of dpre[b, t, d] * x[b, t * stride + tap - 1, c]
+                K.gemm(dpre, x, M=D, N=C, K=B * To, a_mn=True, b_mn=True, lda=D, ldb=C, out=dwt[tap], impl=_C.GEMM_TCGEN05, kgroups=B,
+                       a_window=(1, 0, 0, To, To * D), b_window=(stride, tap - 1, 0, T, T * C))
+            dw = dwt.permute(1, 2, 0).contiguous()
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(dpre, rows, D)
+        if ctx.needs_input_grad[0]:
+            wt = shadow_taps(w, dt)
+            dx = torch.empty((B, T, C), dtype=dt, device=x.device)
+            if stride == 1:   # dx[t] = sum_tap dpre[t + 1 - tap] W_tap
+                K.gemm(dpre, wt, M=T, N=C, K=3 * D, lda=D, b_mn=True, ldb=C, batch=(1, B), a_strides=(0, To * D), b_strides=(0, 0), out=dx, ldd=C,
+                       d_strides=(0, T * C), impl=_C.GEMM_TCGEN05, kgroups=3, a_window=(1, 1, -1, To, 0), b_window=(1, 0, 0, D, D * C))
+            else:
+                # even rows 2 j (j < To): dpre[j] W_1
+                K.gemm(dpre, wt[1], M=To, N=C, K=D, lda=D, b_mn=True, ldb=C, batch=(1, B), a_strides=(0, To * D), b_strides=(0, 0), out=dx, ldd=2 * C,
+                       d_strides=(0, T * C), impl=_C.GEMM_TCGEN05)
+                # odd rows 2 j + 1 (j < T // 2): dpre[j + 1] W_0 + dpre[j] W_2 (group 0 = tap 0, group 1 = tap 2; dpre[To] reads as zero)
+                if T // 2 > 0:
+                    K.gemm(dpre, wt, M=T // 2, N=C, K=2 * D, lda=D, b_mn=True, ldb=C, batch=(1, B), a_strides=(0, To * D), b_strides=(0, 0),
+                           out=dx.view(-1)[C:], ldd=2 * C, d_strides=(0, T * C), impl=_C.GEMM_TCGEN05, kgroups=2,
+                           a_window=(1, 1, -1, To, 0), b_window=(1, 0, 0, D, 2 * D * C))
+        return dx, dw, db, None, None
+
+
 def conv_k3_gelu(x: Tensor, w: Tensor, b: Tensor, stride: int, channels_first: bool, pos: Optional[Tensor] = None) -> Tensor:
+    if conv_implicit_ok(x, w, stride, channels_first):
+        return _ConvK3GeluImplicit.apply(x, w, b, stride, pos)
     return _ConvK3Gelu.apply(x, w, b, stride, channels_first, pos)
 
 

@@ -120,11 +120,14 @@ def gemm(
     alpha: float = 1.0, beta: float = 0.0, impl: int = _C.GEMM_AUTO, alpha_dev: Optional[Tensor] = None,
     a2: Optional[Tensor] = None, b2: Optional[Tensor] = None, K2: int = 0, lda2: Optional[int] = None, ldb2: Optional[int] = None,
     colsum_out: Optional[Tensor] = None,
+    kgroups: int = 0, a_window: Optional[Tuple[int, int, int, int, int]] = None, b_window: Optional[Tuple[int, int, int, int, int]] = None,
 ) -> Tensor:
     """D = epilogue(alpha * A @ B) with the operand layouts of include/tsw.h.  ``a``/``b`` are only used for their
     storage (data_ptr, dtype): the logical shapes come from M/N/K, the majors and the leading dimensions.
     batch = (outer, inner); *_strides = (outer stride, inner stride) in elements.
-    a2 / b2 / K2: optional second operand pair appended along the contraction (D = epilogue(alpha (A B + A2 B2)))."""
+    a2 / b2 / K2: optional second operand pair appended along the contraction (D = epilogue(alpha (A B + A2 B2))).
+    kgroups / a_window / b_window: grouped contraction of include/tsw.h (implicit convolution, batch folded into k);
+    a window is (outer_step, outer_off0, outer_off_step, outer_extent, group_stride)."""
     require_cuda(a, b, out, bias, residual, aux_in, aux_out, a2, b2)
     lib = _C.load()
     bo, bi = batch
@@ -167,6 +170,11 @@ def gemm(
         g.A2, g.B2, g.K2 = ptr(a2), ptr(b2), K2
         g.lda2 = lda2 if lda2 is not None else (M if a_mn else K2)
         g.ldb2 = ldb2 if ldb2 is not None else (N if b_mn else K2)
+    if kgroups >= 1:
+        g.kgroups = kgroups
+        aw, bw = a_window or (1, 0, 0, 0, 0), b_window or (1, 0, 0, 0, 0)
+        g.a_outer_step, g.a_outer_off0, g.a_outer_off_step, g.a_outer_extent, g.a_group_stride = aw
+        g.b_outer_step, g.b_outer_off0, g.b_outer_off_step, g.b_outer_extent, g.b_group_stride = bw
     if GEMM_PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

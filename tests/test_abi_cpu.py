@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib_path):
     missing = [n for n in declared_symbols() if not hasattr(lib, n)]
     assert not missing, missing
     lib.tsw_abi_version.restype = ctypes.c_int
-    assert lib.tsw_abi_version() == 3
+    assert lib.tsw_abi_version() == 4
 
 
 def test_ctypes_signatures_cover_the_header(lib_path):

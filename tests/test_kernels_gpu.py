@@ -179,6 +179,48 @@ def test_im2col_matches_conv1d(K, stride, cf):
         assert rel_err(din, xr.grad) < 1e-6
 
 
+@pytest.mark.parametrize("cfg", [(2, 64, 101, 128, 2, True), (3, 128, 300, 192, 2, False), (2, 64, 97, 64, 1, False), (2, 384, 1000, 384, 2, True),
+                                 (1, 64, 1, 64, 2, False), (2, 64, 2, 72, 2, True)])
+def test_conv_stem_implicit_gemm(K, cfg, monkeypatch):
+    """Second conv of the stem (whisper_encoder.py:446-447,464-467) as a grouped tcgen05 contraction — strided / shifted TMA
+    windows of the time-major input, nothing materialised — against F.conv1d in fp32 (forward, weight / bias / input gradients)
+    and against the staged im2col path on the same bf16 inputs; odd and tiny T, several row tiles, stride 1 and 2."""
+    from robustsq_whisper_b200 import functional as TF
+    torch.manual_seed(31)
+    B, C, T, D, stride, with_pos = cfg
+    dt = torch.bfloat16
+    x = (torch.randn(B, T, C) * 0.5).to(dt)
+    w = (torch.randn(D, C, 3) * (1.0 / math.sqrt(3 * C))).to(dt).float()
+    bias = torch.randn(D) * 0.1
+    To = (T + 2 - 3) // stride + 1
+    pos = torch.randn(To + 3, D) * 0.2 if with_pos else None
+    gy = (torch.randn(B, To, D) * 0.3).to(dt)
+    # fp32 reference
+    xr, wr, br = x.float().requires_grad_(True), w.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = F.gelu(F.conv1d(xr.permute(0, 2, 1), wr, br, stride=stride, padding=1)).permute(0, 2, 1)
+    if with_pos:
+        ref = ref + pos[:To]
+    ref.backward(gy.float())
+
+    def run():
+        xs = x.cuda().requires_grad_(True)
+        ws, bs = w.cuda().requires_grad_(True), bias.cuda().requires_grad_(True)
+        ps = pos.cuda() if with_pos else None
+        y = TF.conv_k3_gelu(xs, ws, bs, stride, False, ps)
+        y.backward(gy.cuda())
+        return y.detach(), xs.grad, ws.grad, bs.grad
+
+    assert TF.conv_implicit_ok(x.cuda(), w.cuda(), stride, False)
+    y, dx, dw, db = run()
+    monkeypatch.setenv("TSW_CONV_IM2COL", "1")
+    assert not TF.conv_implicit_ok(x.cuda(), w.cuda(), stride, False)
+    y0, dx0, dw0, db0 = run()
+    for name, got, staged, want in (("y", y, y0, ref), ("dx", dx, dx0, xr.grad), ("dw", dw, dw0, wr.grad), ("db", db, db0, br.grad)):
+        assert got.shape == want.shape, name
+        assert rel_err(got.float(), want) < 1.5e-2, f"{name}: {rel_err(got.float(), want)}"
+        assert rel_err(got.float(), staged.float()) < 1.5e-2, f"{name} vs im2col path: {rel_err(got.float(), staged.float())}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_softmax_masks_fwd_bwd(K, dtype):
     torch.manual_seed(4)
