@@ -640,6 +640,7 @@ struct FmhaBwdParams {
   const float* lse;    // (B, H, Sq)
   const float* delta;  // (B, H, Sq) rowsum(dO * O)
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
+  uint32_t st256;      // dk / dv rows are 32-byte aligned: 256-bit stores
 };
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -966,6 +967,341 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(s.tmem_slot); }
 }
 
+// ================================================================================================ backward, ONE query tile (Sq <= 128)
+// Decoder cross-attention (108 token rows against 1516 memory frames) and decoder self-attention: with a single query tile the
+// key-tile-stationary kernel above has nothing to pipeline inside a work item (one S / dP / dV / dK / dQ round trip per item,
+// Q and dO re-fetched and dQ reduced through L2 once per key tile): 293 us per call at 32 x 16 x 108 x 1516 (this kernel: 192 us;
+// decoder self-attention 54 -> 45 us, 16 queries x 500 keys 128 -> 98 us).  Here the work
+// item is a whole (batch, head): Q and dO are loaded once, the key tiles stream through a 3-stage K / V ring, dQ accumulates
+// in TMEM over the item and is written once (plain fp32 stores: no zero-fill, no reduce-add), dV / dK of a key tile are complete
+// after one MMA each and are drained while the next tile's scores and exponentials run.
+//   warp 0       TMA producer (Q / dO double-buffered across items, K / V ring)
+//   warp 1       TMEM allocator + MMA issuer; S / dP of tile g + 1 are issued as soon as tile g's are in registers
+//   warps 4-19   gradient warps: P / dS of tile g (thread = query row x 32-key slice)
+//   warps 20-23  drain warps: dV / dK of tile g (thread = key row), dQ at the end of an item; TMEM reads (64 B / clk / SM) are the
+//                kernel's floor — 192 KB per key tile — so the drain runs beside the next tile's exponentials, not in line with them
+constexpr int FQ1_THREADS = 768;   // 24 warps; roles are aligned to warpgroups of 4 (setmaxnreg is a warpgroup-wide instruction)
+constexpr int FQ1_KSTAGES = 3;
+
+struct FmhaBwdQ1Smem {
+  unsigned char q[2][kTileBytes], dO[2][kTileBytes];
+  unsigned char k[FQ1_KSTAGES][kTileBytes], v[FQ1_KSTAGES][kTileBytes];
+  unsigned char p[2 * kTileBytes];    // [q][key] bf16, two 64-key panels
+  unsigned char ds[2 * kTileBytes];
+  uint64_t q_full[2], q_empty[2], kv_full[FQ1_KSTAGES], kv_empty[FQ1_KSTAGES], s_full, s_drained, pds_full, g_done, acc_free, dq_full, dq_free;
+  uint32_t tmem_slot;
+};
+
+// 256-bit stores (sm_100 STG.256): the rows of a warp are 2-4 KB apart, so every store instruction costs one LSU pass per lane
+// whatever its width: half the instructions, half the passes.
+// 16 scores + 16 dP of one row -> 8 packed bf16 pairs of P and of dS = P (dP - delta) scale
+template <bool MASKED>
+__device__ __forceinline__ void bwd_chunk16(const float* sv, const float* dpv, float scale_log2, float lse2, float scale, float dlt_s, int first_key,
+                                            int row_limit, uint32_t* pk, uint32_t* dk_) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float p0 = ex2_approx(fmaf(sv[i], scale_log2, -lse2));
+    float p1 = ex2_approx(fmaf(sv[i + 1], scale_log2, -lse2));
+    if (MASKED) { if (first_key + i >= row_limit) p0 = 0.f; if (first_key + i + 1 >= row_limit) p1 = 0.f; }
+    const float d0 = p0 * fmaf(dpv[i], scale, -dlt_s), d1 = p1 * fmaf(dpv[i + 1], scale, -dlt_s);
+    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1), db = __floats2bfloat162_rn(d0, d1);
+    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+    dk_[i >> 1] = *reinterpret_cast<const uint32_t*>(&db);
+  }
+}
+
+// 32 fp32 accumulator words -> 32 bf16 = 64 contiguous bytes of one row
+__device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const uint32_t* v, uint32_t st256) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
+  if (st256) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 16 * i), "r"(w[8 * i]), "r"(w[8 * i + 1]), "r"(w[8 * i + 2]),
+                   "r"(w[8 * i + 3]), "r"(w[8 * i + 4]), "r"(w[8 * i + 5]), "r"(w[8 * i + 6]), "r"(w[8 * i + 7]) : "memory");
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+}
+
+struct Q1Item { int b, h, klimit, n_act; };
+__device__ __forceinline__ Q1Item q1_item(const FmhaBwdParams& p, int w) {
+  Q1Item I;
+  I.h = w % p.H; I.b = w / p.H;
+  I.klimit = p.Sk;
+  if (p.key_len) I.klimit = min(I.klimit, p.key_len[I.b]);
+  I.klimit = max(I.klimit, 0);
+  I.n_act = (I.klimit + FK - 1) / FK;   // key tiles some query can see (a causal mask only trims inside tiles: Sq <= 128)
+  return I;
+}
+
+__global__ void __launch_bounds__(FQ1_THREADS, 1)
+fmha_bwd_q1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmdO, const FmhaBwdParams p, float* __restrict__ dq32) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  FmhaBwdQ1Smem& s = *reinterpret_cast<FmhaBwdQ1Smem*>(smem_raw);
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0 && (smem_u32(smem_raw) & 1023u) != 0) { printf("fmha_bwd_q1: dynamic smem not 1024-aligned\n"); __trap(); }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmdO);
+    for (int i = 0; i < 2; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
+    for (int i = 0; i < FQ1_KSTAGES; ++i) { mbar_init(&s.kv_full[i], 1); mbar_init(&s.kv_empty[i], 1); }
+    mbar_init(&s.s_full, 1); mbar_init(&s.s_drained, 16); mbar_init(&s.pds_full, 16); mbar_init(&s.g_done, 1); mbar_init(&s.acc_free, 4);
+    mbar_init(&s.dq_full, 1); mbar_init(&s.dq_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t t_s = s.tmem_slot, t_dp = t_s + 128, t_dv = t_s + 256, t_dk = t_s + 320, t_dq = t_s + 384;
+  const int step = gridDim.x, total = p.total;   // total = B * H items
+  const int n_kt = p.n_kt;
+
+  if (warp < 4) {
+    reg_dec<40>();
+    if (warp == 0) {
+      // ===================================================== TMA producer
+      if (lane == 0) {
+        int it = 0, st = 0; uint32_t ph = 0;
+        for (int w = blockIdx.x; w < total; w += step) {
+          const Q1Item I = q1_item(p, w);
+          if (I.n_act == 0) continue;
+          const int qb = it & 1;
+          mbar_wait(&s.q_empty[qb], ((it >> 1) & 1) ^ 1);
+          mbar_expect_tx(&s.q_full[qb], 2 * kTileBytes);
+          tma_load_4d(&tmQ, &s.q_full[qb], s.q[qb], I.h * FD, 0, I.b, 0);
+          tma_load_4d(&tmdO, &s.q_full[qb], s.dO[qb], I.h * FD, 0, I.b, 0);
+          for (int j = 0; j < I.n_act; ++j) {
+            mbar_wait(&s.kv_empty[st], ph ^ 1);
+            mbar_expect_tx(&s.kv_full[st], 2 * kTileBytes);
+            tma_load_4d(&tmK, &s.kv_full[st], s.k[st], I.h * FD, j * FK, I.b, 0);
+            tma_load_4d(&tmV, &s.kv_full[st], s.v[st], I.h * FD, j * FK, I.b, 0);
+            if (++st == FQ1_KSTAGES) { st = 0; ph ^= 1; }
+          }
+          ++it;
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================== MMA issuer (whole warp walks the loop; one elected lane issues)
+      const bool leader_lane = elect_one();
+      const uint32_t id_s = idesc_bf16(128, 128, 0, 0);   // S, dP: K-major x K-major, N = 128 keys
+      const uint32_t id_g = idesc_bf16(128, 64, 1, 1);    // dV, dK: A = P^T / dS^T (MN-major), B = dO / Q (MN-major), N = 64
+      const uint32_t id_q = idesc_bf16(128, 64, 0, 1);    // dQ: A = dS (K-major over keys), B = K tile (MN-major), N = 64
+      const uint32_t ka = smem_u32(s.k[0]), va = smem_u32(s.v[0]), pa = smem_u32(s.p), dsa = smem_u32(s.ds);
+      const uint32_t qa = smem_u32(s.q[0]), oa = smem_u32(s.dO[0]);
+      const uint64_t dP_mn = make_smem_desc(pa, kTileBytes, 1024), dS_mn = make_smem_desc(dsa, kTileBytes, 1024);
+      const uint64_t dS_k0 = make_smem_desc(dsa, 16, 1024), dS_k1 = make_smem_desc(dsa + kTileBytes, 16, 1024);
+      // ---- scores cursor: one key tile ahead of the gradient MMAs, across work items
+      int sw = blockIdx.x, s_j = 0, s_n = 0, s_it = -1, s_st = 0; uint32_t s_ph = 0;
+      auto next_item = [&]() -> bool {
+        while (sw < total) {
+          const Q1Item I = q1_item(p, sw);
+          sw += step;
+          if (I.n_act > 0) { s_n = I.n_act; s_j = 0; ++s_it; return true; }
+        }
+        return false;
+      };
+      bool s_valid = next_item();
+      auto issue_scores = [&]() {
+        const int qb = s_it & 1;
+        if (s_j == 0) mbar_wait(&s.q_full[qb], (s_it >> 1) & 1);
+        mbar_wait(&s.kv_full[s_st], s_ph);
+        tc_fence_after();
+        const uint64_t qd = make_smem_desc(qa + qb * kTileBytes, 16, 1024), od = make_smem_desc(oa + qb * kTileBytes, 16, 1024);
+        const uint64_t kd = make_smem_desc(ka + s_st * kTileBytes, 16, 1024), vd = make_smem_desc(va + s_st * kTileBytes, 16, 1024);
+        if (leader_lane) {
+          umma_bf16_c<false>(t_s, qd, kd, id_s);
+#pragma unroll
+          for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_s, desc_advance(qd, k * 32), desc_advance(kd, k * 32), id_s);
+          umma_bf16_c<false>(t_dp, od, vd, id_s);
+#pragma unroll
+          for (int k = 1; k < FD / 16; ++k) umma_bf16_c<true>(t_dp, desc_advance(od, k * 32), desc_advance(vd, k * 32), id_s);
+          umma_commit(&s.s_full);
+        }
+        __syncwarp();
+        if (++s_st == FQ1_KSTAGES) { s_st = 0; s_ph ^= 1; }
+        if (++s_j == s_n) s_valid = next_item();
+      };
+      if (s_valid) issue_scores();
+      int g = 0, it = 0, st = 0;
+      for (int w = blockIdx.x; w < total; w += step) {
+        const Q1Item I = q1_item(p, w);
+        if (I.n_act == 0) continue;
+        const int qb = it & 1;
+        const uint64_t qd = make_smem_desc(qa + qb * kTileBytes, kTileBytes, 1024), od = make_smem_desc(oa + qb * kTileBytes, kTileBytes, 1024);
+        for (int j = 0; j < I.n_act; ++j, ++g) {
+          if (s_valid) {
+            mbar_wait(&s.s_drained, g & 1);    // S / dP of tile g are in the gradient warps' registers
+            tc_fence_after();
+            issue_scores();                    // tile g + 1: runs while the gradient warps exponentiate tile g
+          }
+          mbar_wait(&s.pds_full, g & 1);       // P, dS of tile g in smem
+          if (g > 0) mbar_wait(&s.acc_free, (g - 1) & 1);                 // dV / dK of tile g - 1 are in registers
+          if (j == 0 && it > 0) mbar_wait(&s.dq_free, (it - 1) & 1);      // dQ of the previous item is in registers
+          tc_fence_after();
+          const uint64_t dK_mn = make_smem_desc(ka + st * kTileBytes, kTileBytes, 1024);   // MN-major view of K (dQ)
+          if (leader_lane) {
+            // dV = P^T dO, dK = dS^T Q: reduction over the 128 queries, complete after this tile
+            umma_bf16_c<false>(t_dv, dP_mn, od, id_g);
+#pragma unroll
+            for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dv, desc_advance(dP_mn, k * 2048), desc_advance(od, k * 2048), id_g);
+            umma_bf16_c<false>(t_dk, dS_mn, qd, id_g);
+#pragma unroll
+            for (int k = 1; k < FQ / 16; ++k) umma_bf16_c<true>(t_dk, desc_advance(dS_mn, k * 2048), desc_advance(qd, k * 2048), id_g);
+            // dQ += dS K (reduction over the 128 keys), accumulated over the item's key tiles
+            umma_bf16(t_dq, dS_k0, dK_mn, id_q, j > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < FK / 16; ++k)
+              umma_bf16_c<true>(t_dq, desc_advance(k < 4 ? dS_k0 : dS_k1, (k & 3) * 32), desc_advance(dK_mn, k * 2048), id_q);
+            umma_commit(&s.g_done);                       // P / dS smem free, dV / dK final
+            umma_commit(&s.kv_empty[st]);
+            if (j + 1 == I.n_act) { umma_commit(&s.dq_full); umma_commit(&s.q_empty[qb]); }
+          }
+          __syncwarp();
+          if (++st == FQ1_KSTAGES) st = 0;
+        }
+        ++it;
+      }
+    }
+  } else if (warp < 20) {
+    // ===================================================== gradient warps: P / dS of every key tile
+    reg_inc<88>();   // 4 x 32 x 40 + 16 x 32 x 88 + 4 x 32 x 64 = 58368 <= the 768 x 80 = 61440 registers the CTA was launched with
+    const int quarter = warp & 3;                     // TMEM lane quarter
+    const int part = (warp - 4) >> 2;                 // which 32-key slice this warp handles
+    const int r = quarter * 32 + lane;                // query row
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int c0 = part * 32;
+    const int poff = (part >> 1) * kTileBytes + r * 128;
+    const int ubase = (part & 1) * 4;
+    int g = 0;
+    for (int w = blockIdx.x; w < total; w += step) {
+      const Q1Item I = q1_item(p, w);
+      if (I.n_act == 0) continue;
+      float lse2 = -INFINITY, dlt = 0.f;
+      if (r < p.Sq) {
+        const int64_t si = ((int64_t)I.b * p.H + I.h) * p.Sq + r;
+        lse2 = __ldg(p.lse + si) * 1.44269504088896340736f; dlt = __ldg(p.delta + si);
+      }
+      int row_limit = 0;
+      if (r < p.Sq && lse2 > -INFINITY) {
+        row_limit = I.klimit;
+        if (p.causal) row_limit = min(row_limit, r + 1 + (p.Sk - p.Sq));
+      }
+      for (int j = 0; j < I.n_act; ++j, ++g) {
+        const int kv0 = j * FK;
+        mbar_wait(&s.s_full, g & 1);
+        tc_fence_after();
+        uint32_t pk[16], dk_[16];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {   // 16 keys at a time keeps the live set inside 88 registers
+          float sv[16], dpv[16];
+          tmem_ld16(t_s + lane_off + c0 + 16 * hf, sv);
+          tmem_ld16(t_dp + lane_off + c0 + 16 * hf, dpv);
+          if (hf == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.s_drained);          // the MMA warp may overwrite S / dP with the next tile
+          }
+          const int k0 = kv0 + c0 + 16 * hf;
+          if (k0 + 16 <= row_limit) bwd_chunk16<false>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, k0, row_limit, pk + 8 * hf, dk_ + 8 * hf);
+          else bwd_chunk16<true>(sv, dpv, p.scale_log2, lse2, p.scale, dlt * p.scale, k0, row_limit, pk + 8 * hf, dk_ + 8 * hf);
+        }
+        if (g > 0) mbar_wait(&s.g_done, (g - 1) & 1);   // the MMAs of the previous tile have read P / dS
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int u = (ubase + t) ^ (r & 7);
+          *reinterpret_cast<uint4*>(s.p + poff + (u << 4)) = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          *reinterpret_cast<uint4*>(s.ds + poff + (u << 4)) = make_uint4(dk_[4 * t], dk_[4 * t + 1], dk_[4 * t + 2], dk_[4 * t + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.pds_full);
+      }
+    }
+  } else {
+    // ===================================================== drain warps: dV / dK of every key tile (thread = key row), dQ of every item
+    // (thread = query row): TMEM -> registers -> release -> 256-bit global stores, while the gradient warps are on the next tile
+    reg_dec<64>();
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int64_t dcols = (int64_t)p.H * FD;
+    int g = 0, it = 0;
+    for (int w = blockIdx.x; w < total; w += step) {
+      const Q1Item I = q1_item(p, w);
+      // key tiles no query can see (beyond key_len): zero gradients
+      for (int j = I.n_act; j < n_kt; ++j) {
+        const int key = j * FK + r;
+        if (key < p.Sk) {
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          uint4* dvrow = reinterpret_cast<uint4*>(p.dv + ((int64_t)I.b * p.Sk + key) * p.lddv + I.h * FD);
+          uint4* dkrow = reinterpret_cast<uint4*>(p.dk + ((int64_t)I.b * p.Sk + key) * p.lddk + I.h * FD);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) { dvrow[c] = z; dkrow[c] = z; }
+        }
+      }
+      if (I.n_act == 0) {
+        if (r < p.Sq) {
+          float4* dqrow = reinterpret_cast<float4*>(dq32 + ((int64_t)I.b * p.Sq + r) * dcols + I.h * FD);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) dqrow[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        continue;
+      }
+      for (int j = 0; j < I.n_act; ++j, ++g) {
+        const bool last = j + 1 == I.n_act;
+        mbar_wait(&s.g_done, g & 1);   // dV / dK of this tile are final
+        tc_fence_after();
+        const int key = j * FK + r;
+        const bool live = key < p.Sk;
+        __nv_bfloat16* dvrow = p.dv + ((int64_t)I.b * p.Sk + key) * p.lddv + I.h * FD;
+        __nv_bfloat16* dkrow = p.dk + ((int64_t)I.b * p.Sk + key) * p.lddk + I.h * FD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {   // 32 columns at a time: dV low / high half, dK low / high half
+          uint32_t v[32];
+          tmem_ld32_async((c < 2 ? t_dv : t_dk) + lane_off + (c & 1) * 32, v);
+          tmem_ld_wait();
+          tmem_ld_fence32(v);
+          if (c == 3) {   // everything is in registers: the next tile's dV / dK MMAs may overwrite the accumulators
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.acc_free);
+          }
+          if (live) store32_bf16((c < 2 ? dvrow : dkrow) + (c & 1) * 32, v, p.st256);
+        }
+        if (last) {
+          mbar_wait(&s.dq_full, it & 1);
+          tc_fence_after();
+          float* dqrow = dq32 + ((int64_t)I.b * p.Sq + r) * dcols + I.h * FD;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32_async(t_dq + lane_off + c * 32, v);
+            tmem_ld_wait();
+            tmem_ld_fence32(v);
+            if (c == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s.dq_free);
+            }
+            if (r < p.Sq) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(dqrow + c * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+          }
+        }
+      }
+      ++it;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc<512>(s.tmem_slot); }
+}
+
 // delta[b,h,i] = sum_c dO[b,i,h*64+c] * O[b,i,h*64+c]; 8 lanes per (row, head), 16 bytes of each tensor per lane: a warp reads
 // four whole 128-byte head rows of O and of dO per instruction
 __global__ void __launch_bounds__(256)
@@ -1171,7 +1507,10 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
   const int64_t dcols = H * FD;
   float* dq32 = (float*)workspace;                       // (B, Sq, H*64) fp32 accumulator
   float* delta = (float*)((char*)workspace + (size_t)(B * Sq * dcols) * 4);
-  TSW_CUDA(cudaMemsetAsync(dq32, 0, (size_t)(B * Sq * dcols) * 4, st));
+  // one query tile (decoder cross- / self-attention): (batch, head)-stationary kernel, dQ written once (no zero-fill, no reduce-add)
+  static const bool no_q1 = getenv("TSW_FMHA_BWD_NO_Q1") != nullptr;
+  const bool q1 = Sq <= FQ && !no_q1;
+  if (!q1) TSW_CUDA(cudaMemsetAsync(dq32, 0, (size_t)(B * Sq * dcols) * 4, st));
   {
     const int64_t groups = B * Sq * H;   // 8 lanes each
     fmha_delta_kernel<<<(unsigned)((groups + 31) / 32), 256, 0, st>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)dO, ldo, lddo, (int)B, (int)H, (int)Sq, delta);
@@ -1198,15 +1537,29 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
     TSW_CUDA(cudaMemsetAsync(dq_colsum, 0, sizeof(float) * (size_t)dcols, st));
     TSW_CUDA(cudaMemsetAsync(dv_colsum, 0, sizeof(float) * (size_t)dcols, st));
   }
-  static bool attr_done = false;
-  const size_t smem = sizeof(FmhaBwdSmem);
-  if (!attr_done) {
-    TSW_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+  if (q1) {
+    static bool attr1_done = false;
+    const size_t smem1 = sizeof(FmhaBwdQ1Smem);
+    if (!attr1_done) {
+      TSW_CUDA(cudaFuncSetAttribute(fmha_bwd_q1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+      attr1_done = true;
+    }
+    p.total = (int)(B * H);   // work item = (batch, head)
+    p.st256 = ((reinterpret_cast<uintptr_t>(dk) | reinterpret_cast<uintptr_t>(dv)) % 32 == 0 && ldk % 16 == 0 && ldv % 16 == 0) ? 1u : 0u;
+    const unsigned grid1 = (unsigned)std::min<int64_t>(p.total, sm_count());
+    fmha_bwd_q1_kernel<<<grid1, FQ1_THREADS, smem1, st>>>(tq, tk, tv, tdo, p, dq32);
+    TSW_LAUNCH_CHECK();
+  } else {
+    static bool attr_done = false;
+    const size_t smem = sizeof(FmhaBwdSmem);
+    if (!attr_done) {
+      TSW_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_done = true;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
+    fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
+    TSW_LAUNCH_CHECK();
   }
-  const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
-  fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
-  TSW_LAUNCH_CHECK();
   // dq (B * Sq rows, row stride ldq) bf16 <- contiguous fp32 accumulator
   if (dq_colsum) {
     const int64_t rows = B * Sq;

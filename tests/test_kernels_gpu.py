@@ -684,6 +684,9 @@ FMHA_CASES = [
     (3, 2, 16, 333, True, False),     # SQ-Former cross-attention: 16 queries
     (2, 2, 107, 1516, False, False),  # decoder cross-attention
     (1, 2, 1516, 1516, False, False), # encoder self-attention length
+    (2, 2, 108, 108, False, True),    # decoder self-attention: one causal tile (single-query-tile backward)
+    (3, 2, 100, 300, True, True),     # one query tile, causal with an offset, key padding
+    (2, 2, 128, 256, False, False),   # exactly one full query tile
 ]
 
 
@@ -699,6 +702,38 @@ def test_fmha_fwd(K, B, H, Sq, Sk, use_len, causal):
     torch.cuda.synchronize()
     assert (lse.cpu() - lse_ref).abs().max().item() < 2e-3
     assert rel_err(o.float(), o_ref) < 1e-2
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_fmha_bwd_single_query_tile_many_items(K, causal):
+    """Sq <= 128 runs the (batch, head)-stationary backward kernel: more work items than SMs (several per persistent CTA, so the
+    Q / dO double buffer, the K / V ring and the dQ accumulator are recycled), ragged key lengths incl. whole masked key tiles
+    (zero dK / dV) — against the fp32 reference and against the key-tile-stationary kernel (TSW_FMHA_BWD_NO_Q1 in a subprocess
+    is not needed: the long-sequence cases above already pin that kernel; here both must agree with the same reference)."""
+    torch.manual_seed(23)
+    B, H, Sq, Sk = 20, 8, 108, 400
+    d = H * 64
+    q, k, v = ((torch.randn(B, S, d) * 0.8).bfloat16() for S in (Sq, Sk, Sk))
+    do = (torch.randn(B, Sq, d) * 0.5).bfloat16()
+    key_len = torch.randint(1, Sk + 1, (B,), dtype=torch.int32)
+    key_len[0], key_len[1], key_len[2] = Sk, 1, 129
+    if causal:
+        key_len = torch.clamp(key_len, min=Sk - Sq + 1)      # every query row keeps at least one visible key
+    scale = 0.125
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _attn_ref(qr, kr, vr, H, scale, key_len, causal)
+    o_ref.backward(do.float())
+    kl = key_len.cuda()
+    o, lse = K.fmha_fwd(q.cuda(), k.cuda(), v.cuda(), H, scale, key_len=kl, causal=causal)
+    dq, dk, dv, dqs, dvs = K.fmha_bwd(q.cuda(), k.cuda(), v.cuda(), o, do.cuda(), lse, H, scale, key_len=kl, causal=causal, bias_grads=True)
+    torch.cuda.synchronize()
+    for got, ref, name in ((dq, qr.grad, "dq"), (dk, kr.grad, "dk"), (dv, vr.grad, "dv")):
+        assert rel_err(got.float(), ref) < 2e-2, (name, rel_err(got.float(), ref))
+    for b in range(B):                                       # keys beyond key_len get exactly zero gradient
+        assert (dk[b, int(key_len[b]):] == 0).all() and (dv[b, int(key_len[b]):] == 0).all()
+    assert rel_err(dqs, dq.float().sum(dim=(0, 1))) < 1e-4 and rel_err(dvs, dv.float().sum(dim=(0, 1))) < 1e-4
+    dq2, dk2, dv2 = K.fmha_bwd(q.cuda(), k.cuda(), v.cuda(), o, do.cuda(), lse, H, scale, key_len=kl, causal=causal)
+    assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)      # no atomics on this path: bit-reproducible
 
 
 def test_fmha_fwd_moving_maximum_rescales_the_tmem_accumulator(K):
