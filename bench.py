@@ -503,10 +503,11 @@ def run_b200(args):
                          "achieved": achieved_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel on its most frequent shape
-                         # (48512 x 1024 x 1024, 288 launches / step) from profiles/r1_gemm_tc_48512x1024x1024.ncu-rep;
-                         # algorithmic A + B + D of that launch = 200.9 MB
-                         "traffic": 160.2e6 if args.model == "medium" else None,
-                         "traffic_shape": "M=48512 N=1024 K=1024 bf16 (one launch, ncu --set full)" if args.model == "medium" else None,
+                         # (48512 x 1024 x 1024 with bias + residual: the attention out-projection) from
+                         # profiles/r2b_gemm_tma_48512x1024x1024_bias_res.ncu-rep: 201.0 MB read + 72.9 MB written; algorithmic
+                         # A + B + residual + D of that launch = 300.3 MB (the tail of D is still dirty in L2 when the kernel ends)
+                         "traffic": 273.9e6 if args.model == "medium" else None,
+                         "traffic_shape": "M=48512 N=1024 K=1024 bf16, bias + residual epilogue (one launch, ncu --set full)" if args.model == "medium" else None,
                          "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
                          "launches_timed": len(tc), "share_of_step": gemm_share, "ms_per_step_while_timed": ms_prof},
             "clocks": sampler.summary(),

@@ -1565,7 +1565,9 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
     const int64_t rows = B * Sq;
     const int cols8 = (int)(dcols / 8);
     const unsigned gx = (unsigned)((cols8 + 31) / 32);
-    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * 8 / gx, (rows + 63) / 64));
+    // row chunks sized for the LONGER of the two tensors (decoder cross-attention: 3 456 dq rows but 48 512 dv rows — 54 chunks left the
+    // dv half of the launch at 37 us)
+    int64_t chunks = std::max<int64_t>(1, std::min<int64_t>((int64_t)sm_count() * 8 / gx, (std::max<int64_t>(rows, B * Sk) + 63) / 64));
     chunks = std::min<int64_t>(chunks, 65535);
     const int64_t rpc = (rows + chunks - 1) / chunks;
     const int64_t rows_v = B * Sk, rpc_v = (rows_v + chunks - 1) / chunks;

@@ -215,36 +215,25 @@ __device__ __forceinline__ void tma_chunk_math(const uint32_t* r, float alpha, c
   }
 }
 
-// Column sums of a finished 32 x 32 bf16 box (the bias gradient riding in the producer's epilogue): ones(16 x 16) x box on the
-// warp-level tensor-core path — ldmatrix.trans feeds the rows of the box as the k index of mma.m16n8k16, fp32 accumulation,
-// every row of the product holds the sums.  ~25 instructions per box where a shuffle transpose-reduce takes ~120.
+// Column sums of a finished 32 x 32 bf16 box (the bias gradient riding in the producer's epilogue): lane = (column pair, row
+// parity) reads its 32-bit word of 16 rows — for a fixed row the 16 words of the swizzled 64-byte row are 16 distinct banks, the two
+// row parities take the two halves of the 128-byte bank window — and adds them as packed fp32 pairs; one shuffle folds the
+// parities, lanes 0-15 issue one 8-byte atomic each.  (A first version did ones(16 x 16) x box with ldmatrix + mma.sync: fewer
+// instructions, but every legacy HMMA takes the tensor pipe away from the tcgen05 main loop — 379 us against 326 us for the
+// same GEMM without the sums.)
 __device__ __forceinline__ void box_colsum(const unsigned char* boxD, int lane, float* colsum_n) {
-  float acc[4][4];
+  const int w = lane & 15;
+  const unsigned char* base = boxD + (lane >> 4) * 64 + ((w & 3) << 2);
+  const int u = w >> 2;
+  float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-  const uint32_t ones = 0x3F803F80u;   // bf16 {1, 1}
-  const int mi = lane >> 3;
-#pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-#pragma unroll
-    for (int jp = 0; jp < 2; ++jp) {
-      const int row = 16 * ks + (mi & 1) * 8 + (lane & 7);
-      const int unit = 2 * jp + (mi >> 1);
-      const uint32_t addr = smem_u32(boxD + row * 64 + ((unit ^ ((row >> 1) & 3)) << 4));
-      uint32_t b0, b1, b2, b3;
-      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
-      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
-                   : "+f"(acc[2 * jp][0]), "+f"(acc[2 * jp][1]), "+f"(acc[2 * jp][2]), "+f"(acc[2 * jp][3]) : "r"(ones), "r"(b0), "r"(b1));
-      asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %4, %4, %4}, {%5, %6}, {%0, %1, %2, %3};"
-                   : "+f"(acc[2 * jp + 1][0]), "+f"(acc[2 * jp + 1][1]), "+f"(acc[2 * jp + 1][2]), "+f"(acc[2 * jp + 1][3]) : "r"(ones), "r"(b2), "r"(b3));
-    }
+  for (int i = 0; i < 16; ++i) {   // row = (lane >> 4) + 2 i: its swizzle term is i & 3
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(base + i * 128 + ((u ^ (i & 3)) << 4));
+    acc = fadd2(acc, bf16x2_as_float2(v));
   }
-  // accumulator registers 0, 1 of lane l: product row l / 4 (all rows are equal), columns 2 (l % 4) + {0, 1} of each 8-column block:
-  // lanes 0-15 take block l / 4 each
-  const int j = lane >> 2;
-  const float v0 = j == 0 ? acc[0][0] : j == 1 ? acc[1][0] : j == 2 ? acc[2][0] : acc[3][0];
-  const float v1 = j == 0 ? acc[0][1] : j == 1 ? acc[1][1] : j == 2 ? acc[2][1] : acc[3][1];
-  if (lane < 16) atomicAdd(reinterpret_cast<float2*>(colsum_n + 8 * j + 2 * (lane & 3)), make_float2(v0, v1));
+  acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
+  acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+  if (lane < 16) atomicAdd(reinterpret_cast<float2*>(colsum_n + 2 * w), acc);
 }
 
 template <int BN, int CL, bool TWOSM>

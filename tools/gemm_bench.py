@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from robustsq_whisper_b200 import kernels as K, _C
 
-def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=False, aux=False, res=False, iters=10, batch=(1,1), rowmod=0):
+def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=False, aux=False, res=False, iters=10, batch=(1,1), rowmod=0, colsum=False):
     dev = "cuda"
     nb = batch[0] * batch[1]
     a = torch.randn((nb, Kd, M) if a_mn else (nb, M, Kd), device=dev).bfloat16()
@@ -17,6 +17,7 @@ def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=Fals
     if epi in (2, 4): kw["aux_in"] = torch.randn_like(d)
     if res: kw["residual"] = torch.randn_like(d)
     if rowmod: kw["res_row_mod"] = rowmod
+    if colsum: kw["colsum_out"] = torch.empty(N, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(2): K.gemm(a, b, **kw)
     ts = []
@@ -27,12 +28,14 @@ def bench(M, N, Kd, a_mn=False, b_mn=False, epi=0, out=torch.bfloat16, bias=Fals
         ts.append(e0.elapsed_time(e1))
     ts.sort(); t = ts[len(ts) // 2]
     fl = 2.0 * M * N * Kd * nb
-    print(f"M={M:6d} N={N:5d} K={Kd:6d} nb={nb:4d} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} bias={int(bias)} aux={int(aux)} res={int(res)} out={'bf16' if out==torch.bfloat16 else 'f32'}: {t:8.3f} ms  {fl / t / 1e9:8.1f} TF/s")
+    print(f"M={M:6d} N={N:5d} K={Kd:6d} nb={nb:4d} a_mn={int(a_mn)} b_mn={int(b_mn)} epi={epi} bias={int(bias)} aux={int(aux)} res={int(res)} colsum={int(colsum)} out={'bf16' if out==torch.bfloat16 else 'f32'}: {t:8.3f} ms  {fl / t / 1e9:8.1f} TF/s")
 
 S = 48512
 bench(S, 4096, 1024, b_mn=True)
 bench(S, 4096, 1024, b_mn=True, res=True)
 bench(S, 4096, 1024, b_mn=True, epi=4)
+bench(S, 4096, 1024, b_mn=True, epi=4, colsum=True)
+bench(S, 1024, 4096, b_mn=True, colsum=True)
 bench(S, 4096, 1024, bias=True, epi=3, aux=True)
 bench(S, 4096, 1024, bias=True, epi=1)
 bench(S, 1024, 1024, bias=True, res=True)
