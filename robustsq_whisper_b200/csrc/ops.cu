@@ -863,7 +863,8 @@ extern "C" int tsw_layernorm_bwd(const void* dy, const void* x, const float* gam
   const int es = dtype == TSW_F32 ? 4 : 2;
   static const int ln_cons = getenv("TSW_LN_CONS") ? atoi(getenv("TSW_LN_CONS")) : 512;   // consumer threads per CTA: 512 (one CTA / SM) | 256 (two)
   const int ncons = (ln_cons == 256 && tpr <= 256) ? 256 : 512;
-  if (dgamma && tpr <= ncons && rows >= 4096 && rows % 4 == 0 && !two_pass) {
+  static const int64_t min_rows = getenv("TSW_LN_TMA_MIN_ROWS") ? atoll(getenv("TSW_LN_TMA_MIN_ROWS")) : 2048;   // decoder rows (32 x 108 = 3456): 37.9 us for the three-launch two-pass form, 23.6 us single pass
+  if (dgamma && tpr <= ncons && rows >= min_rows && rows % 4 == 0 && !two_pass) {
     // single pass: dx, the parameter gradients and (optionally) the column sums of dx from one sweep (large activations; small
     // ones stay on the two-pass form, whose parameter pass spreads over more CTAs than there are row groups).  rows % 4 and a
     // stage of a multiple of 4 rows: the per-tile slices of the fp32 statistics are then whole, aligned 16-byte units.

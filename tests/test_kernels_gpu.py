@@ -81,11 +81,11 @@ def test_layernorm_fwd_bwd(K, dtype, d, rows):
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
 
 
-@pytest.mark.parametrize("d,rows", [(1024, 5004), (768, 9000), (384, 4100), (512, 4096), (1024, 5003)])
+@pytest.mark.parametrize("d,rows", [(1024, 5004), (768, 9000), (384, 4100), (512, 4096), (1024, 5003), (1024, 3456), (768, 2048), (1024, 1000)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_layernorm_bwd_single_pass(K, d, rows, with_res):
-    """rows >= 4096 (a multiple of 4) take the TMA-staged single-pass kernel (dx + dgamma / dbeta [+ column sums of dx] from
-    one sweep over dy and x); 5003 rows stay on the two-pass form."""
+    """rows >= 2048 (a multiple of 4) take the TMA-staged single-pass kernel (dx + dgamma / dbeta [+ column sums of dx] from
+    one sweep over dy and x; 3456 = the decoder's 32 x 108 token rows); 5003 and 1000 rows stay on the two-pass form."""
     torch.manual_seed(3)
     dt = torch.bfloat16
     x = (torch.randn(rows, d) * 2 + 0.3).to(dt)
