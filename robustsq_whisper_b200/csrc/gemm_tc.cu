@@ -47,6 +47,7 @@ struct TcParams {
   int kgroups, kb_per_group;
   int a_step, a_off0, a_off_step, a_c2mul, a_c3mul;
   int b_step, b_off0, b_off_step, b_c2mul, b_c3mul;
+  int dynamic;               // 1: the grid has one cluster per work item and running clusters pull the list through cluster launch control
   int tma_kind;              // >= 0: the EK_* kind the TMA-store epilogue runs (bf16 output through swizzled boxes); -1: register -> global epilogue
   int64_t total_work;    // total_tiles * splits
 };
@@ -161,6 +162,49 @@ __device__ __forceinline__ void epi_rows(const EpiParams& ep, bool split_atomic,
   }
 }
 
+// ================================================================================ work list of a persistent CTA (pair)
+// static:  item = first + i * step (round-robin over the clusters that were launched).
+// dynamic: the grid has ONE cluster per work item; a scheduler warp keeps asking cluster launch control for the next not-yet-
+//          launched cluster (tc_ptx.cuh) and every consumer — the TMA thread, the MMA thread, the eight epilogue warps, the
+//          scheduler itself — reads the 16-byte answers from a two-slot ring (full / empty mbarriers; the multicast form delivers
+//          each answer to both CTAs of a pair).  Whatever SMs are free when the kernel starts pull the whole list: with a
+//          gradient all-reduce holding a few SMs, the static round-robin's late CTAs would start their share only after the
+//          others have finished theirs — each overlapped GEMM then takes up to twice as long.
+constexpr int kClcConsumers = 2 + TC_EPI_WARPS + 1;
+// ONE answer in flight per cluster: with two, the clusters that ask first take two items each out of a short list (3 072 x 1 024
+// weight gradient, 144 items on 74 clusters: three rounds instead of two, 0.224 -> 0.314 ms)
+constexpr int kClcSlots = 1;
+struct ClcRing { uint64_t* full; uint64_t* empty; unsigned char* resp; };
+struct WorkCursor { int w; int slot; uint32_t phase; };
+
+// one thread; -> false when the list is exhausted
+template <int CL>
+__device__ __forceinline__ bool work_next_thread(const TcParams& p, const ClcRing& r, WorkCursor& c, int w_step, int total_work) {
+  if (!p.dynamic) { c.w += w_step; return c.w < total_work; }
+  mbar_wait(&r.full[c.slot], c.phase);
+  uint32_t x;
+  const bool ok = clc_decode(r.resp + 16 * c.slot, x);
+  fence_proxy_async_smem();   // the async proxy overwrites the slot once it is released
+  mbar_arrive(&r.empty[c.slot]);
+  if (++c.slot == kClcSlots) { c.slot = 0; c.phase ^= 1; }
+  c.w = (int)x / CL;
+  return ok;
+}
+// a whole (converged) warp; lane 0 releases the slot
+template <int CL>
+__device__ __forceinline__ bool work_next_warp(const TcParams& p, const ClcRing& r, WorkCursor& c, int w_step, int total_work, int lane) {
+  if (!p.dynamic) { c.w += w_step; return c.w < total_work; }
+  mbar_wait(&r.full[c.slot], c.phase);
+  uint32_t x;
+  const bool ok = clc_decode(r.resp + 16 * c.slot, x);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&r.empty[c.slot]);
+  if (++c.slot == kClcSlots) { c.slot = 0; c.phase ^= 1; }
+  c.w = (int)x / CL;
+  return ok;
+}
+
 // ================================================================================ TMA-store epilogue (bf16 outputs)
 // Lane = accumulator row straight out of tcgen05.ld: the fused arithmetic runs on the lane's 32 columns, the result is packed
 // to bf16 and written as one 64-byte row of a 32 x 32 box (SWIZZLE_64B: 16-byte unit j of row r lives at j ^ ((r >> 1) & 3),
@@ -239,7 +283,8 @@ __device__ __forceinline__ void box_colsum(const unsigned char* boxD, int lane, 
 template <int BN, int CL, bool TWOSM>
 __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, const CUtensorMap* tmAO, const CUtensorMap* tmIn, const TcParams& p,
                                              const EpiParams& ep, unsigned char* stg_all, uint64_t* ibars_all, uint64_t* tfull, uint64_t* tempty,
-                                             uint32_t tmem_base, int warp, int lane, int crank, int w_first, int w_step, int tiles_per_batch) {
+                                             uint32_t tmem_base, int warp, int lane, int crank, int w_first, int w_step, int tiles_per_batch,
+                                             const ClcRing& ring) {
   constexpr uint32_t kBoxBytes = 32 * 64;
   const int q = warp & 3;            // TMEM lane quarter this warp may access
   const int half = (warp - 4) >> 2;  // which of the tile's 32-column chunks (even / odd) this warp drains
@@ -271,12 +316,16 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, const CUten
   int k = 0;        // boxes this warp has produced (input kinds: slot = k & 1, barrier parity = (k >> 1) & 1)
   int issued = 0;   // input boxes requested so far
   int as = 0; uint32_t aphase = 0;
-  int w = w_first, m0 = 0, n0t = 0, bi = 0, bo = 0;
-  if (w < total_work) locate(w, m0, n0t, bi, bo);
-  while (w < total_work) {
+  int m0 = 0, n0t = 0, bi = 0, bo = 0;
+  WorkCursor cur = {w_first, 0, 0u};
+  bool have = w_first < total_work;
+  if (have) locate(w_first, m0, n0t, bi, bo);
+  while (have) {
     const bool active = m0 < (int)p.M;   // else: phantom tile of an odd pair / rows beyond M — nothing to load or store
     const int nchunks = min(BN, (int)p.N - n0t) / 64;   // N % 64 == 0 (host): both halves have the same count
-    const int wn = w + w_step;
+    // the work item after this one is resolved now (its operand box is requested during this tile's last chunk)
+    const bool has_next = work_next_warp<CL>(p, ring, cur, w_step, total_work, lane);
+    const int wn = has_next ? cur.w : total_work;
     int m0n = 0, n0tn = 0, bin = 0, bon = 0;
     if (wn < total_work) locate(wn, m0n, n0tn, bin, bon);
     if (has_in && active && issued == k) {   // first box of the run (or the tile before was inactive): request it now
@@ -342,7 +391,7 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* tmD, const CUten
     __syncwarp();
     if (lane == 0) { if (TWOSM) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
     if (++as == 2) { as = 0; aphase ^= 1; }
-    w = wn; m0 = m0n; n0t = n0tn; bi = bin; bo = bon;
+    have = has_next; m0 = m0n; n0t = n0tn; bi = bin; bo = bon;
   }
   if (lane == 0) tma_store_wait_read<0>();   // shared memory must outlive the last reads
 }
@@ -380,8 +429,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES;   // [2]
   uint64_t* tempty = tfull + 2;          // [2]
   uint64_t* ibars = tempty + 2;          // [2 * TC_EPI_WARPS] input boxes of the TMA epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ibars + 2 * TC_EPI_WARPS);
-  static_assert((2 * STAGES + 4 + 2 * TC_EPI_WARPS) * 8 + 4 <= S::kBarBytes, "barrier block overflows");
+  uint64_t* clc_full = ibars + 2 * TC_EPI_WARPS;   // [2] dynamic work list: answer landed
+  uint64_t* clc_empty = clc_full + 2;              // [2] every consumer has read it
+  uint64_t* clc_peer = clc_empty + 2;              // [2] (leader CTA) the peer's slot is free and armed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(clc_peer + 2);
+  static_assert((2 * STAGES + 4 + 2 * TC_EPI_WARPS + 6) * 8 + 4 <= S::kBarBytes - 32, "barrier block overflows");
+  const ClcRing ring = {clc_full, clc_empty, reinterpret_cast<unsigned char*>(bars) + S::kBarBytes - 32};   // two 16-byte answers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
@@ -397,6 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], TWOSM ? 1 : CL); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TWOSM ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&ibars[i], 1);
+    for (int i = 0; i < kClcSlots; ++i) { mbar_init(&clc_full[i], 1); mbar_init(&clc_empty[i], kClcConsumers); mbar_init(&clc_peer[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) { if (TWOSM) tmem_alloc_2sm<TMEM_COLS>(tmem_slot); else tmem_alloc<TMEM_COLS>(tmem_slot); }
@@ -422,7 +476,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = w_first; w < total_work; w += w_step) {   // 32-bit tile arithmetic: the 64-bit divisions cost ~1 us per tile switch
+      WorkCursor cur = {w_first, 0, 0u};
+      for (bool have = w_first < total_work; have; have = work_next_thread<CL>(p, ring, cur, w_step, total_work)) {
+        const int w = cur.w;           // 32-bit tile arithmetic: the 64-bit divisions cost ~1 us per tile switch
         const int t = w / p.splits;
         const int sp = w - t * p.splits;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
@@ -498,13 +554,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
+    if (lane == 0 && TWOSM && crank != 0) {
+      // the odd CTA of a pair issues nothing, but it is one of the consumers the dynamic work list counts on
+      WorkCursor cur = {w_first, 0, 0u};
+      if (p.dynamic) { while (work_next_thread<CL>(p, ring, cur, w_step, total_work)) {} }
+    }
     if (lane == 0 && (!TWOSM || crank == 0)) {
       const uint32_t idesc = make_idesc(p.a_mn, p.b_mn, BN, TWOSM ? 2 * TBM : TBM);
       const uint32_t a_lbo = p.a_mn ? kPanelBytes : 16, b_lbo = p.b_mn ? kPanelBytes : 16;
       const uint32_t a_kstep = p.a_mn ? 16 * 128 : 32, b_kstep = p.b_mn ? 16 * 128 : 32;  // bytes per UMMA_K = 16
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int w = w_first; w < total_work; w += w_step) {
+      WorkCursor cur = {w_first, 0, 0u};
+      for (bool have = w_first < total_work; have; have = work_next_thread<CL>(p, ring, cur, w_step, total_work)) {
+        const int w = cur.w;
         const int sp = w % p.splits;
         const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -532,13 +595,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (warp == 3) {
+    // ===================================================== dynamic work list: keep one answer ahead of the consumers
+    if (p.dynamic) {
+      WorkCursor cur = {0, 0, 0u};
+      while (true) {
+        mbar_wait(&clc_empty[cur.slot], cur.phase ^ 1);   // all of this CTA's consumers have read the slot's previous answer
+        if (lane == 0) {
+          mbar_expect_tx(&clc_full[cur.slot], 16);
+          if (CL == 2) {
+            if (crank != 0) mbar_arrive_leader(&clc_peer[cur.slot]);      // this CTA's slot is free and armed
+            else mbar_wait(&clc_peer[cur.slot], cur.phase);
+          }
+          if (crank == 0) {
+            if (CL == 2) clc_try_cancel_mc(ring.resp + 16 * cur.slot, &clc_full[cur.slot]);
+            else clc_try_cancel(ring.resp + 16 * cur.slot, &clc_full[cur.slot]);
+          }
+        }
+        __syncwarp();
+        if (!work_next_warp<CL>(p, ring, cur, w_step, total_work, lane)) break;
+      }
+    }
   } else if (warp >= 4) {
     // ===================================================== epilogue
     bool drained = false;
     if constexpr (sizeof(DT) == 2 && BN % 64 == 0) {
       if (p.tma_kind >= 0) {   // TMEM -> registers (lane = row) -> swizzled bf16 boxes -> TMA store
         epilogue_tma<BN, CL, TWOSM>(&tmD, &tmAO, &tmIn, p, ep, reinterpret_cast<unsigned char*>(stg_base), ibars, tfull, tempty, tmem_base, warp,
-                                    lane, crank, w_first, w_step, tiles_per_batch);
+                                    lane, crank, w_first, w_step, tiles_per_batch, ring);
         drained = true;
       }
     }
@@ -556,7 +640,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     DT* const AOp = reinterpret_cast<DT*>(ep.aux_out);
     const int64_t row4 = 4 * ep.ldd;
     int as = 0; uint32_t aphase = 0;
-    for (int w = w_first; w < total_work; w += w_step) {
+    WorkCursor cur = {w_first, 0, 0u};
+    bool have = w_first < total_work;
+    while (have) {
+      const int w = cur.w;
+      const bool has_next = work_next_warp<CL>(p, ring, cur, w_step, total_work, lane);
       const int t = w / p.splits;
       const bool first_split = (w - t * p.splits) == 0;
       const int bt = t / tiles_per_batch;
@@ -572,7 +660,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (GENERIC) {
         // pull the NEXT tile's extra epilogue operand (residual | aux_in | old D) into L2 now: its loads then hit L2
         // (~250 cycles) instead of DRAM (~800) when that tile's epilogue runs one main loop later
-        const int wn = w + w_step;
+        const int wn = has_next ? cur.w : total_work;
         const DT* src = Rp ? Rp : ((ep.epilogue == TSW_EPI_MUL_DGELU || ep.epilogue == TSW_EPI_MUL_AUX) ? AIp : (ep.beta != 0.f ? Dp : nullptr));
         if (src != nullptr && wn < total_work && ep.res_row_mod == 0) {
           const int tn = wn / p.splits;
@@ -648,6 +736,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) { if (TWOSM) mbar_arrive_leader(&tempty[as]); else mbar_arrive(&tempty[as]); }
       if (++as == 2) { as = 0; aphase ^= 1; }
+      have = has_next;
     }
     }
   }
@@ -893,7 +982,10 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
     TSW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::kBytes));
     attr_done = true;
   }
-  const int grid = (int)std::min<int64_t>(p.total_work, units) * CL;
+  // dynamic work list (cluster launch control): one cluster per work item, the clusters that get SMs pull the rest
+  static const bool static_sched = getenv("TSW_GEMM_STATIC") != nullptr;
+  p.dynamic = (!static_sched && p.total_work > units) ? 1 : 0;   // a list that fits in one wave has nothing to balance
+  const int grid = (int)(p.dynamic ? p.total_work : std::min<int64_t>(p.total_work, units)) * CL;
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = S::kBytes; cfg.stream = st;

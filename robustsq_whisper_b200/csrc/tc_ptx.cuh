@@ -198,6 +198,33 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 // generic-proxy writes to shared memory become visible to the async proxy (TMA) that reads them next
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- cluster launch control (sm_100): a running cluster cancels the launch of a not-yet-started cluster of its own grid and takes
+// over that cluster's work.  The grid has one cluster per work item; whatever share of the SMs is free (a co-running NCCL kernel
+// keeps some) pulls the whole list, instead of a static round-robin in which the late CTAs' share starts after the others' ends.
+// The 16-byte response lands in shared memory and completes 16 bytes on the mbarrier — in every CTA of the cluster (same offsets)
+// with the multicast form.
+__device__ __forceinline__ void clc_try_cancel(void* resp, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+               ::"r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void clc_try_cancel_mc(void* resp, uint64_t* bar) {
+  asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+               ::"r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+// -> true and the x index of the first CTA of the cancelled cluster, or false (nothing left to take: stop asking)
+__device__ __forceinline__ bool clc_decode(const void* resp, uint32_t& ctaid_x) {
+  uint32_t x = 0, valid;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%2];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %1, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, _, _, _}, r;\n\t}"
+      : "+r"(x), "=r"(valid) : "r"(smem_u32(resp)) : "memory");
+  ctaid_x = x;
+  return valid != 0;
+}
+
 // advance the 14-bit start-address field of a precomputed descriptor by `bytes` (tile buffers live below 256 KB, so the
 // field never carries): 1-2 integer instructions per MMA instead of rebuilding the 64-bit descriptor
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
