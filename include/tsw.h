@@ -49,6 +49,12 @@ int tsw_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * tile schedule a persistent CTA that has to wait for an SM held by a long all-reduce kernel delays the whole launch.
  * n_sm even, 0 restores the full machine.  Process-wide. */
 int tsw_set_sm_reserve(int n_sm);
+/* Work lists of the persistent kernels.  The tcgen05 GEMM always pulls its list dynamically (cluster launch control: one cluster
+ * per work item, the clusters that hold an SM cancel and take over the ones not yet launched), which is neutral on an idle GPU and
+ * keeps a co-running all-reduce from delaying a static share of the tiles.  The attention backward can do the same (unmasked
+ * launches with more (batch, head, key tile) items than SMs); it is 2 % slower on an idle GPU, so this is opt-in: mode 1 = dynamic,
+ * 0 = static round-robin (default; TSW_FMHA_DYNAMIC=1 in the environment switches the default).  Process-wide. */
+int tsw_set_fmha_work_list(int dynamic);
 
 /* ------------------------------------------------------------------------------------------------ K1 log-mel
  * Replaces OpenAIWhisperEncoder.log_mel_spectrogram, whisper_encoder.py:99-129 (torch.stft -> |.|^2 ->

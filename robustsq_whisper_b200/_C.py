@@ -53,6 +53,7 @@ SIGNATURES = {
     "tsw_last_error": (c_char_p, []),
     "tsw_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "tsw_set_sm_reserve": (c_int, [_I]),
+    "tsw_set_fmha_work_list": (c_int, [_I]),
     "tsw_logmel_init": (c_int, [_P, _I, _I]),
     "tsw_logmel_workspace_bytes": (_SZ, [_I64, _I64, _I]),
     "tsw_logmel_fwd": (c_int, [_P, _I64, _I64, _I64, _P, _I, _P, _SZ, _P]),

@@ -35,6 +35,7 @@ void set_error(const char* fmt, ...);
 inline cudaStream_t as_stream(tsw_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached per device
+extern int g_fmha_dynamic;  // tsw_set_fmha_work_list
 
 template <typename T> struct DT;
 template <> struct DT<float> { static constexpr int code = TSW_F32; };

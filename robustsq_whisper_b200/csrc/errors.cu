@@ -1,4 +1,5 @@
 // Error reporting + device queries for libtsw_sm100.so
+#include <cstdlib>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -12,6 +13,7 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 static int g_sm_reserve = 0;   // SMs the persistent kernels leave free (for NCCL's kernels in data-parallel runs)
+int g_fmha_dynamic = getenv("TSW_FMHA_DYNAMIC") != nullptr && atoi(getenv("TSW_FMHA_DYNAMIC")) != 0 ? 1 : 0;
 int sm_count() {
   static int cached[64] = {0};
   int dev = 0;
@@ -28,6 +30,11 @@ int sm_count() {
 extern "C" int tsw_set_sm_reserve(int n_sm) {
   TSW_CHECK_ARG(n_sm >= 0 && n_sm % 2 == 0 && n_sm <= 64, "set_sm_reserve: expected an even count in [0, 64]");
   tsw::g_sm_reserve = n_sm;
+  return TSW_OK;
+}
+extern "C" int tsw_set_fmha_work_list(int dynamic) {
+  TSW_CHECK_ARG(dynamic == 0 || dynamic == 1, "set_fmha_work_list: expected 0 or 1");
+  tsw::g_fmha_dynamic = dynamic;
   return TSW_OK;
 }
 extern "C" int tsw_abi_version(void) { return TSW_ABI_VERSION; }

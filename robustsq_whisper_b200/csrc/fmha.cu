@@ -641,6 +641,7 @@ struct FmhaBwdParams {
   const float* delta;  // (B, H, Sq) rowsum(dO * O)
   __nv_bfloat16 *dk, *dv; int64_t lddk, lddv;
   uint32_t st256;      // dk / dv rows are 32-byte aligned: 256-bit stores
+  int dynamic;         // key-tile-stationary kernel: the grid has one CTA per work item (cluster launch control work list)
 };
 
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -670,7 +671,8 @@ struct FmhaBwdSmem {
   unsigned char ds[2 * kTileBytes];
   unsigned char dq[kTileBytes];       // fp32 staging: 4 dQ warps x one panel of [32 rows][128 B], SW128
   uint64_t k_full[2], k_empty[2], v_full, v_empty, q_full[FB_QSTAGES], q_empty[FB_QSTAGES], s_full, s_drained, pds_full, pds_empty, dq_full[2], dq_empty[2],
-      acc_full;
+      acc_full, wl_full, wl_empty;
+  alignas(16) unsigned char wl_resp[16];   // dynamic work list: the cluster-launch-control answer
   uint32_t tmem_slot;
 };
 
@@ -722,6 +724,8 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < FB_QSTAGES; ++i) { mbar_init(&s.q_full[i], 1); mbar_init(&s.q_empty[i], 1); }
     mbar_init(&s.s_full, 1); mbar_init(&s.s_drained, 16); mbar_init(&s.pds_full, 16); mbar_init(&s.pds_empty, 1);
     mbar_init(&s.acc_full, 1);
+    // readers of the work list: TMA thread, MMA warp, 16 gradient warps, 4 dQ warps, the scheduler warp
+    worklist_init(WorkList{&s.wl_full, &s.wl_empty, s.wl_resp, 0, 0, 0}, 1 + 1 + 16 + 4 + 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(&s.tmem_slot);
@@ -730,15 +734,19 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t t_s = s.tmem_slot, t_dp = t_s + 128, t_dv = t_s + 256, t_dk = t_s + 320, t_dq = t_s + 384;   // dQ: 2 x 64 columns
   const int step = gridDim.x;
+  // gridDim.x == p.total: one CTA per work item, the CTAs that got an SM pull the rest of the list (tc_ptx.cuh)
+  const WorkList wl = {&s.wl_full, &s.wl_empty, s.wl_resp, p.dynamic, step, p.total};
 
   if (warp < FB_GRAD_WARP0) {
     reg_dec<40>();
+    if (warp == 2) worklist_schedule(wl, lane);
     if (warp == 0) {
       // ===================================================== TMA producer
       if (lane == 0) {
         int j = 0, st = 0; uint32_t ph = 0;
-        for (int w = blockIdx.x; w < p.total; w += step) {
-          const BwdItem I = bwd_item(p, w);
+        WorkPos pos = {(int)blockIdx.x, 0u};
+        for (bool have = pos.w < p.total; have; have = worklist_next_thread(wl, pos)) {
+          const BwdItem I = bwd_item(p, pos.w);
           if (I.n_it == 0) continue;
           const int kb = j & 1;
           mbar_wait(&s.k_empty[kb], ((j >> 1) & 1) ^ 1);
@@ -769,14 +777,21 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint64_t dP_mn = make_smem_desc(pa, kTileBytes, 1024), dS_mn = make_smem_desc(dsa, kTileBytes, 1024);
       const uint64_t dS_k0 = make_smem_desc(dsa, 16, 1024), dS_k1 = make_smem_desc(dsa + kTileBytes, 16, 1024);
       // ---- scores cursor: runs exactly one query tile ahead of the gradient MMAs, across work items
-      int sw = blockIdx.x, sj = -1, s_it = 0, s_nit = 0, sst = 0; uint32_t sph = 0;
+      // the cursor walks the work list (one reader of the dynamic list: this warp); the items it has started are queued for the
+      // gradient-MMA loop below, which follows at most one item behind
+      int sj = -1, s_it = 0, s_nit = 0, sst = 0; uint32_t sph = 0;
+      WorkPos spos = {(int)blockIdx.x, 0u};
+      bool s_first = true;
+      int fifo[4], f_head = 0, f_tail = 0;
+      // the list is advanced only when the cursor needs the next item (the answer for the item after that is requested once every
+      // role has moved on: asking earlier would wait on roles that wait on this warp)
       auto next_item = [&]() -> bool {
-        while (sw < p.total) {
-          const BwdItem I = bwd_item(p, sw);
-          sw += step;
-          if (I.n_it > 0) { s_nit = I.n_it; s_it = 0; ++sj; return true; }
+        while (true) {
+          if (s_first) { s_first = false; if (spos.w >= p.total) return false; }
+          else if (!worklist_next_warp(wl, spos, lane)) return false;
+          const BwdItem I = bwd_item(p, spos.w);
+          if (I.n_it > 0) { s_nit = I.n_it; s_it = 0; ++sj; fifo[f_tail & 3] = spos.w; ++f_tail; return true; }
         }
-        return false;
       };
       bool s_valid = next_item();
       auto issue_scores = [&]() {
@@ -802,9 +817,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       if (s_valid) issue_scores();
       int g = 0, j = 0, st = 0;
-      for (int w = blockIdx.x; w < p.total; w += step) {
-        const BwdItem I = bwd_item(p, w);
-        if (I.n_it == 0) continue;
+      while (f_head < f_tail) {   // the cursor is always at least as far as this loop: an empty queue means the list is done
+        const BwdItem I = bwd_item(p, fifo[f_head & 3]);
+        ++f_head;
         const int kb = j & 1;
         const uint64_t dK_mn = make_smem_desc(ka + kb * kTileBytes, kTileBytes, 1024);   // MN-major view of K (dQ)
         for (int it = 0; it < I.n_it; ++it, ++g) {
@@ -853,8 +868,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int poff = (part >> 1) * kTileBytes + r * 128;   // 64-key panel + row
     const int ubase = (part & 1) * 4;                 // first 16-byte unit of the slice inside the 128-byte panel row
     int g = 0, j = 0;
-    for (int w = blockIdx.x; w < p.total; w += step) {
-      const BwdItem I = bwd_item(p, w);
+    WorkPos pos = {(int)blockIdx.x, 0u};
+    for (bool have = pos.w < p.total; have; have = worklist_next_warp(wl, pos, lane)) {
+      const BwdItem I = bwd_item(p, pos.w);
       const int key = I.kv0 + r;
       __nv_bfloat16* dvrow = p.dv + ((int64_t)I.b * p.Sk + key) * p.lddv + I.h * FD + part * 16;
       __nv_bfloat16* dkrow = p.dk + ((int64_t)I.b * p.Sk + key) * p.lddk + I.h * FD + part * 16;
@@ -929,8 +945,9 @@ fmha_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
     unsigned char* stage = s.dq + quarter * 4096;   // one panel of [32 rows][32 fp32]
     int g = 0;
-    for (int w = blockIdx.x; w < p.total; w += step) {
-      const BwdItem I = bwd_item(p, w);
+    WorkPos pos = {(int)blockIdx.x, 0u};
+    for (bool have = pos.w < p.total; have; have = worklist_next_warp(wl, pos, lane)) {
+      const BwdItem I = bwd_item(p, pos.w);
       for (int it = 0; it < I.n_it; ++it, ++g) {
         const int q0 = bwd_qtile(I, it) * FQ + quarter * 32;
         mbar_wait(&s.dq_full[g & 1], (g >> 1) & 1);
@@ -1556,7 +1573,11 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
       TSW_CUDA(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done = true;
     }
-    const unsigned grid = (unsigned)std::min<int64_t>(p.total, sm_count());   // persistent: one CTA per SM
+    // persistent, one CTA per SM; with more items than SMs the grid has one CTA per item and the resident CTAs pull the list
+    // (opt-in, tsw_set_fmha_work_list: 2 % slower on an idle GPU; unmasked launches only: with key padding / a causal mask some items have no visible query tile, the scores cursor would
+    // then need two answers in a row while the other roles still wait on it)
+    p.dynamic = (g_fmha_dynamic && p.total > sm_count() && !key_len && !causal) ? 1 : 0;
+    const unsigned grid = (unsigned)(p.dynamic ? p.total : std::min<int64_t>(p.total, sm_count()));
     fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
     TSW_LAUNCH_CHECK();
   }

@@ -225,6 +225,47 @@ __device__ __forceinline__ bool clc_decode(const void* resp, uint32_t& ctaid_x) 
   return valid != 0;
 }
 
+// ---- the work list of a persistent single-CTA kernel: static round-robin (item = first + i * step) or dynamic through cluster
+// launch control (grid = one CTA per item; a scheduler warp keeps ONE answer in flight, every role reads it from an mbarrier-guarded
+// slot and moves on at its own pace).  `consumers` arrivals release the slot: one per reading thread / warp, the scheduler included.
+struct WorkList { uint64_t* full; uint64_t* empty; unsigned char* resp; int dynamic, step, total; };
+struct WorkPos { int w; uint32_t phase; };
+__device__ __forceinline__ void worklist_init(const WorkList& wl, int consumers) { mbar_init(wl.full, 1); mbar_init(wl.empty, (uint32_t)consumers); }
+__device__ __forceinline__ bool worklist_next_thread(const WorkList& wl, WorkPos& c) {
+  if (!wl.dynamic) { c.w += wl.step; return c.w < wl.total; }
+  mbar_wait(wl.full, c.phase);
+  uint32_t x;
+  const bool ok = clc_decode(wl.resp, x);
+  fence_proxy_async_smem();   // the async proxy overwrites the answer once the slot is released
+  mbar_arrive(wl.empty);
+  c.phase ^= 1;
+  c.w = (int)x;
+  return ok;
+}
+__device__ __forceinline__ bool worklist_next_warp(const WorkList& wl, WorkPos& c, int lane) {
+  if (!wl.dynamic) { c.w += wl.step; return c.w < wl.total; }
+  mbar_wait(wl.full, c.phase);
+  uint32_t x;
+  const bool ok = clc_decode(wl.resp, x);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(wl.empty);
+  c.phase ^= 1;
+  c.w = (int)x;
+  return ok;
+}
+// the scheduler warp's whole life (dynamic lists only)
+__device__ __forceinline__ void worklist_schedule(const WorkList& wl, int lane) {
+  if (!wl.dynamic) return;
+  WorkPos c = {0, 0u};
+  while (true) {
+    mbar_wait(wl.empty, c.phase ^ 1);   // every role has read the previous answer
+    if (lane == 0) { mbar_expect_tx(wl.full, 16); clc_try_cancel(wl.resp, wl.full); }
+    __syncwarp();
+    if (!worklist_next_warp(wl, c, lane)) break;
+  }
+}
+
 // advance the 14-bit start-address field of a precomputed descriptor by `bytes` (tile buffers live below 256 KB, so the
 // field never carries): 1-2 integer instructions per MMA instead of rebuilding the 64-bit descriptor
 __device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }

@@ -704,6 +704,33 @@ def test_fmha_fwd(K, B, H, Sq, Sk, use_len, causal):
     assert rel_err(o.float(), o_ref) < 1e-2
 
 
+def test_fmha_bwd_dynamic_work_list(K):
+    """More (batch, head, key tile) items than SMs, no mask: with tsw_set_fmha_work_list(1) the key-tile-stationary backward pulls
+    its work list through cluster launch control; dK / dV must be bit-equal to the static round-robin (per-item arithmetic does
+    not depend on which CTA runs the item), dQ equal up to the order of its fp32 reduce-adds."""
+    from robustsq_whisper_b200 import _C
+    torch.manual_seed(24)
+    B, H, S = 3, 8, 900
+    d = H * 64
+    q, k, v, do = ((torch.randn(B, S, d) * 0.8).bfloat16().cuda() for _ in range(4))
+    qr, kr, vr = (t.float().cpu().requires_grad_(True) for t in (q, k, v))
+    o_ref, _ = _attn_ref(qr, kr, vr, H, 0.125)
+    o_ref.backward(do.float().cpu())
+    o, lse = K.fmha_fwd(q, k, v, H, 0.125)
+    lib = _C.load()
+    try:
+        _C.check(lib.tsw_set_fmha_work_list(1), "tsw_set_fmha_work_list")
+        dq1, dk1, dv1 = K.fmha_bwd(q, k, v, o, do, lse, H, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        _C.check(lib.tsw_set_fmha_work_list(0), "tsw_set_fmha_work_list")
+    dq0, dk0, dv0 = K.fmha_bwd(q, k, v, o, do, lse, H, 0.125)
+    assert torch.equal(dk1, dk0) and torch.equal(dv1, dv0)
+    assert rel_err(dq1.float(), dq0.float()) < 4e-3
+    for got, ref, name in ((dq1, qr.grad, "dq"), (dk1, kr.grad, "dk"), (dv1, vr.grad, "dv")):
+        assert rel_err(got.float(), ref) < 2e-2, (name, rel_err(got.float(), ref))
+
+
 @pytest.mark.parametrize("causal", [False, True])
 def test_fmha_bwd_single_query_tile_many_items(K, causal):
     """Sq <= 128 runs the (batch, head)-stationary backward kernel: more work items than SMs (several per persistent CTA, so the

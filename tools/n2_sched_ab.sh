@@ -10,7 +10,8 @@ run() {  # tag env...
   env "$@" timeout 300 $TR --master-port $((29600 + RANDOM % 200)) bench.py --gpus $N --steps 6 --warmup 3 > gpurun_out/ab_${N}_$tag.json 2> gpurun_out/ab_${N}_$tag.err
   echo "$tag: $(tail -1 gpurun_out/ab_${N}_$tag.err | sed 's/.*tcgen05 GEMM/GEMM/')"
 }
+run warm TSW_X=0
 run dynamic_1 TSW_X=0
-run static_1 TSW_GEMM_STATIC=1
+run static_1 TSW_FMHA_STATIC=1
 run dynamic_2 TSW_X=0
-run static_2 TSW_GEMM_STATIC=1
+run static_2 TSW_FMHA_STATIC=1
