@@ -20,7 +20,10 @@ namespace cg = cooperative_groups;
 namespace tsw {
 
 
-constexpr int kAspThreads = 256;
+#ifndef TSW_ASP_THREADS
+#define TSW_ASP_THREADS 512   /* 256: one wave's time was the same, the non-resident loops want the extra loads in flight */
+#endif
+constexpr int kAspThreads = TSW_ASP_THREADS;
 constexpr int kMaxCPT = 2;  // vector chunks per thread along d (d <= 256 * kMaxCPT * VN)
 
 template <typename T>
@@ -94,6 +97,7 @@ asp_fwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, float* __r
     for (int i = 0; i < kMaxCPT; ++i)
 #pragma unroll
       for (int j = 0; j < VN; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
     for (int t = map.rg; t < nrows; t += map.RG) {
 #pragma unroll
       for (int i = 0; i < kMaxCPT; ++i) {
@@ -152,6 +156,7 @@ asp_fwd_kernel(const T* __restrict__ x, int Tlen, int d, float gamma, float* __r
     for (int i = 0; i < kMaxCPT; ++i)
 #pragma unroll
       for (int j = 0; j < VN; ++j) a1[i][j] = a2[i][j] = 0.f;
+#pragma unroll 4
     for (int t = map.rg; t < nrows; t += map.RG) {
       const float a = sc[t];
       const T* row = RESIDENT ? slab + (int64_t)t * d : xb + (int64_t)(r0 + t) * d;
@@ -350,7 +355,16 @@ static int launch_cluster(Kern kern, int CL, int B, size_t smem, cudaStream_t st
   return TSW_OK;
 }
 
-static int asp_cluster_size(int64_t T) { return T >= 64 ? 8 : T >= 16 ? 4 : T >= 4 ? 2 : 1; }
+// CTAs per utterance.  Eight keep a 500-frame slab resident in shared memory, but 32 utterances x 8 CTAs of ~200 KB are three waves
+// of whole clusters (92 / 160 us forward / backward at 32 x 500 x 1024); four CTAs per utterance run as ONE wave and re-read their
+// frames from L2 instead (70 / 97 us): the cluster is sized so that the launch fits the machine once.
+static int asp_cluster_size(int64_t T, int64_t B) {
+  static const int forced = getenv("TSW_ASP_CLUSTER") ? atoi(getenv("TSW_ASP_CLUSTER")) : 0;   // 1 | 2 | 4 | 8: A/B knob
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return (int)std::min<int64_t>(forced, T);
+  int cl = T >= 64 ? 8 : T >= 16 ? 4 : T >= 4 ? 2 : 1;
+  while (cl > 1 && B * cl > 132) cl >>= 1;   // 4-CTA clusters: 132 CTAs resident at once (B300_MICROARCH.md, chip-level scheduling)
+  return cl;
+}
 
 // ============================================================================================ K8 AAM-Softmax
 // margin logit and its derivative w.r.t. the (un-clamped) cosine
@@ -672,7 +686,7 @@ extern "C" int tsw_asp_pool_fwd(const void* x, int dtype, int64_t B, int64_t T, 
   const int vn = dtype == TSW_F32 ? 4 : 8;
   TSW_CHECK_ARG(dtype == TSW_F32 || dtype == TSW_BF16, "asp_pool_fwd: bad dtype");
   TSW_CHECK_ARG(d % vn == 0 && d / vn <= kAspThreads * kMaxCPT && aligned16(x), "asp_pool_fwd: d=%lld unsupported / x unaligned", (long long)d);
-  const int CL = asp_cluster_size(T);
+  const int CL = asp_cluster_size(T, B);
   const int rows_per = (int)((T + CL - 1) / CL);
   const size_t fixed = asp_fixed_smem(d, rows_per, 4, 1);
   const size_t slab = (((size_t)rows_per * d * (dtype == TSW_F32 ? 4 : 2)) + 127) & ~(size_t)127;
@@ -693,7 +707,7 @@ extern "C" int tsw_asp_pool_bwd(const void* x, int dtype, int64_t B, int64_t T, 
   const int vn = dtype == TSW_F32 ? 4 : 8;
   TSW_CHECK_ARG(dtype == TSW_F32 || dtype == TSW_BF16, "asp_pool_bwd: bad dtype");
   TSW_CHECK_ARG(d % vn == 0 && d / vn <= kAspThreads * kMaxCPT && aligned16(x) && aligned16(gx), "asp_pool_bwd: d=%lld unsupported / unaligned", (long long)d);
-  const int CL = asp_cluster_size(T);
+  const int CL = asp_cluster_size(T, B);
   const int rows_per = (int)((T + CL - 1) / CL);
   const size_t fixed = asp_fixed_smem(d, rows_per, 5, 2);
   const size_t slab = (((size_t)rows_per * d * (dtype == TSW_F32 ? 4 : 2)) + 127) & ~(size_t)127;
