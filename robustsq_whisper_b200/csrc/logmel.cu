@@ -77,6 +77,11 @@ __device__ __forceinline__ float float_from_key(unsigned int k) {
 
 struct LogmelSmem {
   float2 tw[kNfft];
+  // the two tables the first stage reads with lane-dependent indices, laid out so that consecutive lanes read consecutive words:
+  // reading the window as tw[n].x (stride 16 B) and the stage twiddles as tw[2 n2 k1] (stride 16 k1 B) were 2- to 16-way bank
+  // conflicts on 23 loads per task
+  alignas(8) float hann[kNfft];        // periodic Hann window
+  float2 tw8[8 * 25];                  // W200^(n2 k1) at [k1 * 25 + n2]
   alignas(16) float seg[kSeg];
   float2 buf[kFPB][kHalf];
   float pw[kFPB][kBins];
@@ -122,7 +127,8 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t n_samples, int64_t
       bulk_load_span(s.seg, a + base, (uint32_t)(kSeg * sizeof(float)), &s.bar);
     }
   }
-  for (int i = tid; i < kNfft; i += kThreads) s.tw[i] = c_tw[i];
+  for (int i = tid; i < kNfft; i += kThreads) { const float2 w = c_tw[i]; s.tw[i] = w; s.hann[i] = 0.5f - 0.5f * w.x; }
+  for (int i = tid; i < 8 * 25; i += kThreads) { const int k1 = i / 25, n2 = i - k1 * 25; s.tw8[i] = c_tw[2 * n2 * k1]; }
   if (bulk) {
     mbar_wait(&s.bar, 0);
   } else {
@@ -147,13 +153,13 @@ logmel_frames_kernel(const float* __restrict__ audio, int64_t n_samples, int64_t
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
       const int n = 2 * (25 * n1 + n2);
-      const float w0 = 0.5f - 0.5f * s.tw[n].x, w1 = 0.5f - 0.5f * s.tw[n + 1].x;  // periodic Hann
+      const float2 w = *reinterpret_cast<const float2*>(s.hann + n);
       const float2 v = *reinterpret_cast<const float2*>(x + n);
-      z[n1] = make_float2(v.x * w0, v.y * w1);
+      z[n1] = make_float2(v.x * w.x, v.y * w.y);
     }
     dft8(z, Y);
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) s.buf[f][k1 * 25 + n2] = cmul(Y[k1], s.tw[2 * n2 * k1]);
+    for (int k1 = 0; k1 < 8; ++k1) s.buf[f][k1 * 25 + n2] = cmul(Y[k1], s.tw8[k1 * 25 + n2]);
   }
   __syncthreads();
 
