@@ -30,6 +30,14 @@ def rel_err(a, b):
     return ((a - b).abs().max() / (b.abs().max() + 1e-30)).item()
 
 
+def assert_close_elementwise(a, b, rtol, atol, what=""):
+    """|a - b| <= atol + rtol |b| for EVERY element: the norm-wise rel_err above lets small entries of a wide-dynamic-range
+    tensor (LayerNorm outputs, softmax probabilities) hide behind the largest one."""
+    a, b = a.double().cpu(), b.double().cpu()
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    assert not bad.any(), f"{what}: {int(bad.sum())} of {bad.numel()} elements off, worst |diff| {(a - b).abs().max().item():.3e}"
+
+
 # ------------------------------------------------------------------------------------------------ K1
 def test_logmel_golden_and_port(K, golden_dir):
     gold = np.load(os.path.join(golden_dir, "logmel.npz"))
@@ -79,6 +87,10 @@ def test_layernorm_fwd_bwd(K, dtype, d, rows):
     dx, dg, db = K.layernorm_bwd(dyq.cuda(), xq.cuda(), gamma.cuda(), mean, rstd)
     assert rel_err(dx.float(), xr.grad) < tol
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    # element-wise: one output rounding (bf16: 2^-8 relative) plus fp32 statistics noise on entries near zero
+    rt, at = (2e-5, 2e-5) if dtype == torch.float32 else (8e-3, 2e-2)
+    assert_close_elementwise(y.float(), yr, rt, at, "layernorm y")
+    assert_close_elementwise(dx.float(), xr.grad, rt, at, "layernorm dx")
 
 
 @pytest.mark.parametrize("d,rows", [(1024, 5004), (768, 9000), (384, 4100), (512, 4096), (1024, 5003), (1024, 3456), (768, 2048), (1024, 1000)])
@@ -233,12 +245,17 @@ def test_softmax_masks_fwd_bwd(K, dtype):
     p = K.softmax_fwd(s.cuda().clone(), B, H, Sq, Sk, scale, key_len=key_len.cuda())
     tol = 1e-6 if dtype == torch.float32 else 1e-2
     assert rel_err(p.float(), ref) < tol
+    # element-wise, so that the small probabilities count too; masked entries are exactly zero
+    rt, at = (2e-6, 1e-7) if dtype == torch.float32 else (8e-3, 1e-6)
+    assert_close_elementwise(p.float(), ref, rt, at, "softmax p")
+    assert (p.cpu()[mask.expand_as(ref)] == 0).all()
     # causal (square)
     s2 = torch.randn(B, H, Sq, Sq).to(dtype)
     cm = torch.full((Sq, Sq), float("-inf")).triu_(1)
     ref2 = torch.softmax(s2.float() * scale + cm, -1)
     p2 = K.softmax_fwd(s2.cuda().clone(), B, H, Sq, Sq, scale, causal=1)
     assert rel_err(p2.float(), ref2) < tol
+    assert_close_elementwise(p2.float(), ref2, rt, at, "causal softmax p")
     # backward
     pr = ref2.to(dtype).float()
     dp = torch.randn(B, H, Sq, Sq).to(dtype)
