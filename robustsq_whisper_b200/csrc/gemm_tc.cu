@@ -996,9 +996,11 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
       at[na].val.clusterDim.x = CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
       ++na;
     }
-    // measured on the medium training step: 195.3 / 196.7 ms with, 196.1 ms without (the step is throughput-bound under the
-    // power cap, not gap-bound), so the attribute is opt-in here; the decode chain's short kernels do use it (3.9 -> 3.2 ms)
-    static const bool gemm_pdl = pdl_enabled() && getenv("TSW_GEMM_PDL") != nullptr;
+    // programmatic dependent launch: barrier init, TMEM allocation and descriptor prefetch of this launch run under the previous
+    // kernel's last, partially filled wave.  Round 1 measured it neutral on the step (195.3 / 196.7 ms with, 196.1 ms without);
+    // with the dynamic work list and the shorter decoder-side kernels of round 2 it is 176.9 / 177.1 / 177.6 ms against
+    // 180.6 / 180.2 / 178.5 ms on the same boxes, so it is on (TSW_GEMM_NO_PDL switches it off).
+    static const bool gemm_pdl = pdl_enabled() && getenv("TSW_GEMM_NO_PDL") == nullptr;
     if (gemm_pdl && p.splits == 1 && !ep.colsum) {   // not behind this call's own memsets (split-K / colsum zero-fill): those are not grids
       at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[na].val.programmaticStreamSerializationAllowed = 1;
