@@ -117,10 +117,12 @@ typedef struct {
    * dx = dy W + (dy s B) A ride in the main loop of the base GEMM as one extra k-block instead of a second pass over y.
    * NULL / 0 when unused.  Both kernels take it with every epilogue. */
   const void* A2; const void* B2; int64_t K2, lda2, ldb2;
-  /* Optional (N) fp32: receives the column sums over m of the stored result (before rounding to d_dtype) — the bias
-   * gradient of the layer whose output gradient this GEMM produces (the fc1 bias of an MLP: its dY is the MUL_AUX dgrad
-   * of fc2), so no separate pass re-reads D.  tcgen05 kernel, epilogue NONE or MUL_AUX without residual / aux_out / beta,
-   * N % 4 == 0, unbatched; zeroed by the call, accumulated with fp32 atomics (summation order not fixed).  NULL when unused. */
+  /* Optional (N) fp32: receives the column sums over m of the result — the bias gradient of the layer whose output gradient this
+   * GEMM produces (the fc1 bias of an MLP: its dY is the MUL_AUX dgrad of fc2), so no separate pass re-reads D.  With the TMA-store
+   * epilogue (bf16 D, N % 64 == 0) the sums are taken over the values AS STORED (rounded to bf16: what a separate reduction over D
+   * would see); the register epilogue sums them before rounding.  tcgen05 kernel, epilogue NONE or MUL_AUX without residual /
+   * aux_out / beta, N % 4 == 0, unbatched; zeroed by the call, accumulated with fp32 atomics (summation order not fixed).
+   * NULL when unused. */
   float* colsum_out;
   /* Optional GROUPED contraction (tcgen05 kernel, bf16 operands, batch_outer == 1, no A2 / B2): the k index runs over
    * `kgroups` groups of Kg = K / kgroups columns, and inside group g each operand is read through a window on its OUTER

@@ -386,3 +386,41 @@ def test_models_without_espnet_keep_the_same_surface():
     out = m.collect_feats(speech, lens, None, None)
     assert torch.equal(out["feats"], speech) and torch.equal(out["feats_lengths"], lens)
     assert m.ctc is None and m.error_calculator is None and m.extract_feats_in_collect_stats
+
+
+def test_implicit_conv_host_logic_on_cpu():
+    """Host side of the implicit-GEMM conv stem (functional.py): which inputs take it, the tap-major weight shadow and its cache,
+    and the algebra the three backward GEMMs rely on (even input rows see tap 1 only, odd rows taps 0 and 2) — checked with plain
+    torch on the CPU against F.conv1d's own gradients."""
+    import torch.nn.functional as F
+    from robustsq_whisper_b200 import functional as TF
+    torch.manual_seed(0)
+    w = torch.randn(16, 64, 3, requires_grad=True)
+    # eligibility: CUDA bf16 time-major input with channels % 64 == 0 only (CPU tensors never: no CPU path exists)
+    assert not TF.conv_implicit_ok(torch.zeros(2, 10, 64, dtype=torch.bfloat16), w, 2, False)
+    # tap-major shadow = permute(2, 0, 1), cached until the parameter's version changes
+    s1 = TF.shadow_taps(w, torch.float32)
+    assert s1.shape == (3, 16, 64) and torch.equal(s1, w.detach().permute(2, 0, 1)) and s1.is_contiguous()
+    assert TF.shadow_taps(w, torch.float32) is s1
+    with torch.no_grad():
+        w.mul_(2.0)
+    s2 = TF.shadow_taps(w, torch.float32)
+    assert s2 is not s1 and torch.equal(s2, w.detach().permute(2, 0, 1))
+    # the decomposition of the stride-2 input gradient used by _ConvK3GeluImplicit.backward
+    for T in (10, 11):
+        x = torch.randn(2, T, 64, requires_grad=True)
+        y = F.conv1d(x.permute(0, 2, 1), w, None, stride=2, padding=1).permute(0, 2, 1)       # (B, To, D)
+        To = y.shape[1]
+        assert To == (T + 2 - 3) // 2 + 1
+        g = torch.randn_like(y)
+        gx_ref, gw_ref = torch.autograd.grad(y, (x, w), g)
+        wt = w.detach().permute(2, 0, 1)                                                       # (3, D, C)
+        gx = torch.zeros(2, T, 64)
+        gx[:, 0::2] = g[:, : (T + 1) // 2] @ wt[1]                                             # even rows 2 j: dpre[j] W_1
+        gpad = torch.cat([g, torch.zeros(2, 1, 16)], 1)                                        # dpre[To] reads as zero
+        n_odd = T // 2
+        gx[:, 1::2] = gpad[:, 1:n_odd + 1] @ wt[0] + gpad[:, :n_odd] @ wt[2]                   # odd rows: dpre[j + 1] W_0 + dpre[j] W_2
+        assert torch.allclose(gx, gx_ref, atol=1e-4)
+        xp = torch.cat([torch.zeros(2, 1, 64), x.detach(), torch.zeros(2, 2, 64)], 1)          # rows t * 2 + tap - 1 with zero padding
+        gw = torch.stack([torch.einsum("btd,btc->dc", g, xp[:, tap:tap + 2 * To:2]) for tap in range(3)], 0)
+        assert torch.allclose(gw.permute(1, 2, 0), gw_ref, atol=1e-3)
