@@ -417,7 +417,12 @@ def run_b200(args):
     # state during warm-up and no cudaMalloc lands inside a timed region)
     res = resident_inputs()
     staged = [{k: v.clone() for k, v in res.items()} for _ in range(args.steps)]
-    for _ in range(max(args.warmup, 3)):
+    # Data-parallel runs take 5 more untimed steps: the reducer learns its buckets in step 1 and publishes the bucket views in
+    # step 2, NCCL brings its channels up during the first exchanges, and the first process on a fresh box runs its host side
+    # cold — measured: the first 8 steps of the first 2-GPU run on a box average 208-216 ms where the same process settles
+    # at 182-190 ms (profiles/r2b_summary.md).
+    n_warm = max(args.warmup, 3) + (5 if world > 1 else 0)
+    for _ in range(n_warm):
         step({k: v.clone() for k, v in res.items()})
     sync_all()
 
@@ -535,6 +540,7 @@ def run_b200(args):
                                    + (f", LoRA q/k/v/o r={args.lora} on the Whisper blocks with the base frozen" if args.lora > 0 else ""),
                        "launch": "eager (one launch per kernel)" if graphed is None else "one CUDA graph per step (forward + backward + gradient all-reduce), host-side utt-id parsing / negative sampling outside it",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "untimed_steps_before_the_timed_region": n_warm,   # warmup + 5 settling steps when data-parallel (see the comment at the warm-up loop)
                        "l2_policy": "per-step inputs and activations (>10 GB) exceed the 126 MB L2; fresh input copies each step",
                        "loss_last": None if last is None else float(last)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
