@@ -1,5 +1,6 @@
 #!/usr/bin/env bash
-# gpurun --gpus N -- 'bash tools/n2_sched_ab.sh N': data-parallel step with the dynamic (cluster launch control) and the static work list
+# gpurun --gpus N -- 'bash tools/n2_sched_ab.sh N': data-parallel step, alternating runs on one box: dynamic (cluster launch control) vs static
+# work lists.  GEMM: dynamic by default, TSW_GEMM_STATIC=1 switches it off; attention backward: static by default, TSW_FMHA_DYNAMIC=1 on.
 set -u
 cd "$(dirname "$0")/.."
 N=${1:-2}
@@ -11,7 +12,9 @@ run() {  # tag env...
   echo "$tag: $(tail -1 gpurun_out/ab_${N}_$tag.err | sed 's/.*tcgen05 GEMM/GEMM/')"
 }
 run warm TSW_X=0
-run dynamic_1 TSW_X=0
-run static_1 TSW_FMHA_STATIC=1
-run dynamic_2 TSW_X=0
-run static_2 TSW_FMHA_STATIC=1
+run gemm_dynamic_1 TSW_X=0
+run gemm_static_1 TSW_GEMM_STATIC=1
+run gemm_dynamic_2 TSW_X=0
+run gemm_static_2 TSW_GEMM_STATIC=1
+run fmha_dynamic_1 TSW_FMHA_DYNAMIC=1
+run fmha_static_1 TSW_X=0
