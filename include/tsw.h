@@ -47,7 +47,8 @@ int tsw_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Data-parallel runs: the persistent kernels (tcgen05 GEMM, attention backward) size their grids to sm_count - n_sm so that
  * the communication library's kernels (gradient all-reduce overlapped with backward) always find free SMs.  With a static
  * tile schedule a persistent CTA that has to wait for an SM held by a long all-reduce kernel delays the whole launch.
- * n_sm even, 0 restores the full machine.  Process-wide. */
+ * n_sm even, 0 restores the full machine.  Process-wide.  While a reserve is set the work lists below are static (a dynamic
+ * list launches one cluster per work item and would take every free SM). */
 int tsw_set_sm_reserve(int n_sm);
 /* Work lists of the persistent kernels.  The tcgen05 GEMM always pulls its list dynamically (cluster launch control: one cluster
  * per work item, the clusters that hold an SM cancel and take over the ones not yet launched), which is neutral on an idle GPU and

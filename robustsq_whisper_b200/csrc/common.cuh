@@ -36,6 +36,7 @@ inline cudaStream_t as_stream(tsw_stream_t s) { return reinterpret_cast<cudaStre
 
 int sm_count();  // cached per device
 extern int g_fmha_dynamic;  // tsw_set_fmha_work_list
+extern int g_sm_reserve;    // tsw_set_sm_reserve
 
 template <typename T> struct DT;
 template <> struct DT<float> { static constexpr int code = TSW_F32; };

@@ -12,7 +12,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-static int g_sm_reserve = 0;   // SMs the persistent kernels leave free (for NCCL's kernels in data-parallel runs)
+int g_sm_reserve = 0;   // SMs the persistent kernels leave free (for NCCL's kernels in data-parallel runs)
 int g_fmha_dynamic = getenv("TSW_FMHA_DYNAMIC") != nullptr && atoi(getenv("TSW_FMHA_DYNAMIC")) != 0 ? 1 : 0;
 int sm_count() {
   static int cached[64] = {0};

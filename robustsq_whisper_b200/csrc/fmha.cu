@@ -1576,7 +1576,7 @@ extern "C" int tsw_fmha_bwd(const void* q, const void* k, const void* v, const v
     // persistent, one CTA per SM; with more items than SMs the grid has one CTA per item and the resident CTAs pull the list
     // (opt-in, tsw_set_fmha_work_list: 2 % slower on an idle GPU; unmasked launches only: with key padding / a causal mask some items have no visible query tile, the scores cursor would
     // then need two answers in a row while the other roles still wait on it)
-    p.dynamic = (g_fmha_dynamic && p.total > sm_count() && !key_len && !causal) ? 1 : 0;
+    p.dynamic = (g_fmha_dynamic && g_sm_reserve == 0 && p.total > sm_count() && !key_len && !causal) ? 1 : 0;
     const unsigned grid = (unsigned)(p.dynamic ? p.total : std::min<int64_t>(p.total, sm_count()));
     fmha_bwd_kernel<<<grid, FB_THREADS, smem, st>>>(tq, tk, tv, tdo, tdq, p);
     TSW_LAUNCH_CHECK();

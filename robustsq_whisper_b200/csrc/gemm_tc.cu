@@ -984,7 +984,8 @@ static int tc_go(const tsw_gemm_desc& g, const EpiParams& ep, cudaStream_t st) {
   }
   // dynamic work list (cluster launch control): one cluster per work item, the clusters that get SMs pull the rest
   static const bool static_sched = getenv("TSW_GEMM_STATIC") != nullptr;
-  p.dynamic = (!static_sched && p.total_work > units) ? 1 : 0;   // a list that fits in one wave has nothing to balance
+  // (a list that fits in one wave has nothing to balance; with an SM carve-out the grid must stay at its reduced static size)
+  p.dynamic = (!static_sched && g_sm_reserve == 0 && p.total_work > units) ? 1 : 0;
   const int grid = (int)(p.dynamic ? p.total_work : std::min<int64_t>(p.total_work, units)) * CL;
   {
     cudaLaunchConfig_t cfg = {};
